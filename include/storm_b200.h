@@ -1,0 +1,173 @@
+/*
+ * storm_b200.h - C ABI of the B200-native reverse-diffusion enhancement path.
+ *
+ * Drop-in boundary for ONE hot path of sp-uhh/storm: enhancement.py -> ScoreModel.enhance() ->
+ * predictor-corrector sampler -> NCSN++ score network over complex STFT spectrograms.
+ * The reference is pure Python; its own native boundary is a torch JIT extension
+ * (sgmse/backbones/ncsnpp_utils/op/upfirdn2d.cpp:4-22).  A maintainer binds this library with ctypes
+ * (see INTEGRATION.md); storm_b200/_native.py is that binding.
+ *
+ * Conventions
+ *   - plain C types only; every device pointer is a raw CUDA device address (e.g. torch .data_ptr()).
+ *   - caller allocates inputs and outputs; the library owns only the weight arena and a workspace pool
+ *     that grows on the first call with a new (B, F, T) shape (storm_reserve() pre-builds it).
+ *   - every entry point is stream-ordered on the cudaStream_t passed as `void* stream` (0 = default)
+ *     and performs no host synchronisation unless documented.
+ *   - return value: 0 = ok, negative = error (STORM_E_*); storm_last_error() gives the message.
+ *     The Python shim maps STORM_E_INVALID -> ValueError, everything else -> RuntimeError, mirroring
+ *     the reference's TORCH_CHECK / registry ValueError behaviour (op/upfirdn2d.cpp:8-10,
+ *     util/registry.py:27-30).
+ *   - a handle is bound to the CUDA device current at storm_create() and is not thread-safe;
+ *     distinct handles are independent (one process per GPU, one handle per process).
+ *   - complex spectrograms are interleaved (re, im) float pairs, laid out [B][F][T] with T fastest,
+ *     exactly torch.complex64 [B,1,F,T] contiguous (sgmse/model.py:285-286).
+ */
+#ifndef STORM_B200_H
+#define STORM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STORM_OK 0
+#define STORM_E_INVALID (-1)   /* bad argument / unsupported configuration  -> ValueError   */
+#define STORM_E_CUDA (-2)      /* CUDA runtime error                         -> RuntimeError */
+#define STORM_E_STATE (-3)     /* call sequence error (e.g. weights missing) -> RuntimeError */
+#define STORM_E_NOMEM (-4)
+
+#define STORM_MAX_LEVELS 8
+
+typedef struct StormHandle StormHandle;
+
+/* Topology of the NCSN++ backbone = the ctor options of NCSNpp that this path builds
+ * (sgmse/backbones/ncsnpp.py:40-65; registered variants :36,460-513). */
+typedef struct StormNetConfig {
+  int32_t nf;                                  /* base width (128; 96 for ncsnpp12M/6M)                  */
+  int32_t num_levels;                          /* len(ch_mult)                                           */
+  int32_t ch_mult[STORM_MAX_LEVELS];
+  int32_t num_res_blocks;
+  int32_t num_attn_resolutions;
+  int32_t attn_resolutions[STORM_MAX_LEVELS];  /* compared with the F extent like ncsnpp.py:338,385      */
+  int32_t image_size;                          /* 256: only places attention blocks at build (ncsnpp.py:78,194) */
+  int32_t input_channels;                      /* real channels: 4 = [x.re,x.im,y.re,y.im]; 6 for StoRM  */
+  int32_t discriminative;                      /* 1: 2-channel denoiser, no time conditioning (ncsnpp.py:80-86) */
+  int32_t engine;                              /* 0 = auto (tcgen05 where eligible), 1 = SIMT fp32 only  */
+} StormNetConfig;
+
+/* Sampler options = kwargs of ScoreModel.enhance / get_pc_sampler
+ * (sgmse/model.py:273-277, sgmse/sampling/__init__.py:27-32) + OUVESDE ctor (sgmse/sdes.py:167-188). */
+enum { STORM_PRED_REVERSE_DIFFUSION = 0, STORM_PRED_EULER_MARUYAMA = 1, STORM_PRED_NONE = 2 };
+enum { STORM_CORR_ALD = 0, STORM_CORR_LANGEVIN = 1, STORM_CORR_NONE = 2 };
+
+typedef struct StormSamplerConfig {
+  int32_t predictor;
+  int32_t corrector;
+  int32_t N;                 /* reverse steps                                              */
+  int32_t corrector_steps;
+  float snr;
+  float t_eps;               /* ScoreModel.t_eps, 0.03                                     */
+  float theta, sigma_min, sigma_max;   /* OUVE: 1.5, 0.05, 0.5                             */
+  int32_t denoise;           /* 1: return x_mean of the last step (sampling/__init__.py:64) */
+  int32_t probability_flow;  /* 1: RSDE.discretize PF branch (sdes.py:153-156), fixed-step ODE */
+} StormSamplerConfig;
+
+/* STFT front/back end = SpecsDataModule options (sgmse/data_module.py:141-145,195-204). */
+typedef struct StormSpecConfig {
+  int32_t n_fft;             /* 510 */
+  int32_t hop_length;        /* 128 */
+  int32_t sqrt_window;       /* 0 = hann (periodic), 1 = sqrthann                          */
+  float spec_factor;         /* 0.15 */
+  float spec_abs_exponent;   /* 0.5  */
+} StormSpecConfig;
+
+const char* storm_last_error(void);
+const char* storm_version(void);
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+int storm_create(const StormNetConfig* cfg, StormHandle** out);
+int storm_destroy(StormHandle* h);
+
+/* Parameter table: names/shapes/order of the reference state_dict (output_layer.*, all_modules.{i}.*),
+ * replaces nn.Module.state_dict()/load_state_dict (sgmse/backbones/ncsnpp.py:108,273). */
+int64_t storm_param_floats(const StormHandle* h);        /* total fp32 elements of the blob          */
+int32_t storm_param_entries(const StormHandle* h);
+int storm_param_info(const StormHandle* h, int32_t index, char* name, int32_t name_cap,
+                     int64_t shape[4], int32_t* ndim, int64_t* offset_floats);
+
+/* Upload the flat fp32 blob (tensors concatenated in table order, each C-contiguous) and repack it into
+ * the kernels' layouts.  `blob` may be a host or a device pointer (is_device).  Replaces
+ * load_from_checkpoint + .cuda() (enhancement.py:56-61).  storm_weights_device() exposes the device
+ * copy of the raw blob so that rank 0 can ncclBroadcast it. */
+int storm_load_weights(StormHandle* h, const float* blob, int64_t n_floats, int32_t is_device, void* stream);
+int storm_weights_device(StormHandle* h, float** dev_blob, int64_t* n_floats);
+int storm_repack_weights(StormHandle* h, void* stream);  /* after writing into storm_weights_device() */
+
+int storm_reserve(StormHandle* h, int32_t B, int32_t F, int32_t T);
+int64_t storm_workspace_bytes(const StormHandle* h);
+
+/* ---- score network -------------------------------------------------------------------------------
+ * NCSNpp.forward (sgmse/backbones/ncsnpp.py:281-450).
+ *   in  : complex [B][input_channels/2][F][T]  (x then y [then y_denoised])
+ *   t   : float   [B]  device (ignored when discriminative)
+ *   out : complex [B][F][T]
+ * F, T multiples of 2^(num_levels-1). */
+int storm_net_forward(StormHandle* h, const float* in, const float* t, float* out,
+                      int32_t B, int32_t F, int32_t T, void* stream);
+
+/* Debug taps for layer-level parity tests: copy of activation `name` ("mod{i}", "conv_in", "pyr{lvl}")
+ * of the LAST forward, converted to NCHW fp32.  Enable with storm_set_debug_taps(h, 1) first. */
+int storm_set_debug_taps(StormHandle* h, int32_t enable);
+int storm_get_tap(StormHandle* h, const char* name, float* out_nchw, int64_t cap_floats,
+                  int64_t shape[4], void* stream);
+
+/* ---- sampler --------------------------------------------------------------------------------------
+ * pc_sampler (sgmse/sampling/__init__.py:54-66) with score = -dnn(cat[x, y], t) (sgmse/model.py:127-136).
+ *   Y, X : complex [B][F][T];  cond: optional extra condition channel (StoRM's Y_denoised), or NULL.
+ *   noise: NULL -> counter-based Philox keyed by (seed, utt_ids[b], draw index, element) so results do
+ *          not depend on batch composition or sharding; else injected complex draws
+ *          [n_draws][B][F][T] in the reference's order (prior, then per step corrector..., predictor).
+ *   utt_ids: host array [B] or NULL (-> 0..B-1).   nfe_out: host int or NULL. */
+int storm_pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int32_t B, int32_t F, int32_t T,
+                    const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids,
+                    const float* noise, int32_t* nfe_out, void* stream);
+int32_t storm_pc_num_draws(const StormSamplerConfig* sc);
+/* The Philox draw the sampler would use: complex normal, var 1/2 per component (torch.randn_like on
+ * complex64, sgmse/sdes.py:237). out: complex [n_complex]. */
+int storm_philox_normal(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n_complex, float* out, void* stream);
+/* Probability-flow drift  theta (y - x) - 1/2 g(t)^2 score  for an external ODE solver
+ * (sgmse/sampling/__init__.py:102-104, sgmse/sdes.py:124-141). */
+int storm_ode_drift(StormHandle* h, const float* X, const float* Y, float t, float* drift,
+                    int32_t B, int32_t F, int32_t T, const StormSamplerConfig* sc, void* stream);
+
+/* ---- STFT front / back end -------------------------------------------------------------------------
+ * stft + spec_fwd + pad_spec (sgmse/data_module.py:182-186,217-219, sgmse/util/other.py:102-109) and
+ * spec_back + istft (data_module.py:188-193,221-223).
+ *   wav  : float [B][L] device.  norm: float [B] device = max|wav| per utterance (sgmse/model.py:283-284);
+ *          storm_stft divides by it (pass NULL for no normalisation), storm_istft multiplies.
+ *   spec : complex [B][n_fft/2+1][T_pad]; frames >= 1 + L/hop are zero (pad_spec). */
+int32_t storm_num_frames(int32_t L, const StormSpecConfig* sp);
+int32_t storm_padded_frames(int32_t frames);
+int storm_wave_norm(const float* wav, int32_t B, int32_t L, float* norm, void* stream);
+int storm_stft(const float* wav, const float* norm, int32_t B, int32_t L, float* spec, int32_t T_pad,
+               const StormSpecConfig* sp, void* stream);
+int storm_istft(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
+                const StormSpecConfig* sp, void* stream);
+
+/* ---- one-call enhancement ---------------------------------------------------------------------------
+ * ScoreModel.enhance for a batch (sgmse/model.py:273-310): normalise, STFT, transform, pad, PC-sample,
+ * inverse transform, iSTFT, de-normalise.  wav_in / wav_out: float [B][L] device. */
+int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L,
+                  const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed,
+                  const uint64_t* utt_ids, int32_t* nfe_out, void* stream);
+
+/* Kernel-launch counter (bench.py's gpu_launches) and per-stage timing hooks. */
+int64_t storm_launch_count(const StormHandle* h);
+int storm_reset_launch_count(StormHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STORM_B200_H */

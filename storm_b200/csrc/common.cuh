@@ -1,0 +1,82 @@
+// Shared declarations for the storm_b200 native engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace storm {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define STORM_CUDA_TRY(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::storm::fail(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                     \
+  } while (0)
+
+#define STORM_LAUNCH_CHECK()                                                                        \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess)                                                                          \
+      return ::storm::fail(-2, std::string("kernel launch failed: ") + cudaGetErrorString(_e) +     \
+                                   " at " + __FILE__ + ":" + std::to_string(__LINE__));             \
+  } while (0)
+
+#define STORM_TRY(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ---- activation tensors: NHWC fp32, H = frequency bins (F), W = frames (T) ----------------------------
+struct Act {
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  double* part = nullptr;   // GroupNorm partial sums [B][nchunk][C][2] (sum, sum of squares), or null
+  int nchunk = 0;
+  bool part_valid = false;
+  size_t elems() const { return (size_t)B * H * W * C; }
+};
+
+// ---- implicit-GEMM convolution description -----------------------------------------------------------
+// One K-segment of the GEMM: `taps` (9 = 3x3 pad 1, 1 = 1x1) over the channel concatenation
+// [src0 (C0 ch) | src1 (C1 ch)], optionally passed through y = x*scale + shift (per sample, channel)
+// and SiLU before it enters the convolution (zero padding is applied AFTER this prologue, as
+// F.conv2d(padding=1) does on the activated tensor: layerspp.py:243-260).
+struct ConvSeg {
+  const float* src0;
+  const float* src1;
+  int C0, C1;
+  const float* ss;    // [B][C0+C1][2] scale, shift; null = identity
+  int silu;
+  int taps;
+  const float* w;     // SIMT path: [taps][C0+C1][Cout]
+  const void* wtc;    // tcgen05 path: bf16 hi/lo smem images (see conv_tc.cu)
+};
+
+struct ConvParams {
+  ConvSeg seg[2];
+  int nseg;
+  int B, H, W, Cout;
+  const float* bias;       // [Cout] or null
+  const float* temb;       // [B][temb_stride] per-sample bias or null
+  int temb_stride;
+  const float* res;        // residual NHWC [B][H][W][Cout] or null
+  float out_scale;
+  float* out;              // NHWC [B][H][W][Cout]
+};
+
+int launch_conv_simt(const ConvParams& p, cudaStream_t st);
+bool conv_tc_eligible(const ConvParams& p);
+int launch_conv_tc(const ConvParams& p, cudaStream_t st);
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace storm

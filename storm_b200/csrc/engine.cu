@@ -1,0 +1,991 @@
+// Host side of the native engine: network plan (module list + parameter table mirroring
+// sgmse/backbones/ncsnpp.py:110-273), weight arena + repacking, workspace pool, NCSN++ forward
+// (ncsnpp.py:281-450), PC sampler loop (sgmse/sampling/__init__.py:54-66) and the C ABI of
+// include/storm_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/storm_b200.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace storm {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------
+enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RES, M_ATTN, M_COMBINE, M_GN, M_CONV_OUT };
+
+struct Mod {
+  int index;
+  ModKind kind;
+  int in_ch = 0, out_ch = 0;
+  bool up = false, down = false;
+};
+
+struct ParamEntry {
+  std::string name;
+  int64_t shape[4] = {1, 1, 1, 1};
+  int ndim = 0;
+  int64_t offset = 0, numel = 0;
+};
+
+struct Pool {
+  struct Buf { void* p; size_t bytes; bool free; };
+  std::vector<Buf> bufs;
+  size_t total = 0;
+  int get(size_t bytes, void** out) {
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (size_t i = 0; i < bufs.size(); ++i)
+      if (bufs[i].free && bufs[i].bytes >= bytes && (best < 0 || bufs[i].bytes < bufs[best].bytes)) best = (int)i;
+    if (best >= 0 && bufs[best].bytes <= 2 * bytes + (1 << 20)) {
+      bufs[best].free = false;
+      *out = bufs[best].p;
+      return 0;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(STORM_E_NOMEM, std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e));
+    bufs.push_back({p, bytes, false});
+    total += bytes;
+    *out = p;
+    return 0;
+  }
+  void put(void* p) {
+    if (!p) return;
+    for (auto& b : bufs)
+      if (b.p == p) { b.free = true; return; }
+  }
+  void destroy() {
+    for (auto& b : bufs) cudaFree(b.p);
+    bufs.clear();
+    total = 0;
+  }
+};
+
+struct ResPack {
+  const float *gn0_g = nullptr, *gn0_b = nullptr, *gn1_g = nullptr, *gn1_b = nullptr;
+  const float *b0 = nullptr;        // Conv_0.bias
+  float* b12 = nullptr;             // Conv_1.bias (+ Conv_2.bias)
+  float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;   // SIMT layouts
+  void *tc0 = nullptr, *tc1 = nullptr, *tc2 = nullptr; // tcgen05 layouts
+  int temb_off = 0;
+  bool has_skip_conv = false;
+};
+struct AttnPack {
+  const float *gn_g = nullptr, *gn_b = nullptr;
+  const float* w[4] = {nullptr, nullptr, nullptr, nullptr};   // NIN W is already [in][out]
+  const float* b[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* tc[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+struct SmallConvPack { float* w = nullptr; const float* b = nullptr; void* tc = nullptr; };
+
+}  // namespace storm
+
+using namespace storm;
+
+struct StormHandle {
+  StormNetConfig cfg;
+  std::vector<Mod> mods;
+  std::vector<ParamEntry> table;
+  std::map<std::string, int> index;
+  int64_t n_floats = 0;
+  float* raw = nullptr;
+  bool weights_loaded = false;
+  std::vector<void*> packed;            // every cudaMalloc'd packed buffer
+  std::map<int, ResPack> res;
+  std::map<int, AttnPack> attn;
+  std::map<int, SmallConvPack> conv_in, conv_out, combine;
+  float *W1t = nullptr, *W2t = nullptr, *denseWt = nullptr, *denseB = nullptr;
+  int dense_total = 0;
+  Pool pool;
+  int64_t launches = 0;
+  bool taps_on = false;
+  std::map<std::string, Act> taps;
+  int device = 0;
+
+  bool conditional() const { return !cfg.discriminative; }
+  int in_ch() const { return cfg.discriminative ? 2 : cfg.input_channels; }
+  const float* P(const std::string& name) const {
+    auto it = index.find(name);
+    return it == index.end() ? nullptr : raw + table[it->second].offset;
+  }
+};
+
+namespace storm {
+
+static void add_param(StormHandle* h, const std::string& name, std::initializer_list<int64_t> shape) {
+  ParamEntry e;
+  e.name = name;
+  e.ndim = (int)shape.size();
+  int i = 0;
+  e.numel = 1;
+  for (auto s : shape) { e.shape[i++] = s; e.numel *= s; }
+  e.offset = h->n_floats;
+  h->n_floats += e.numel;
+  h->index[name] = (int)h->table.size();
+  h->table.push_back(e);
+}
+
+static int build_plan(StormHandle* h) {
+  const StormNetConfig& c = h->cfg;
+  if (c.nf <= 0 || c.nf % 4 != 0) return fail(STORM_E_INVALID, "nf must be a positive multiple of 4");
+  if (c.num_levels < 1 || c.num_levels > STORM_MAX_LEVELS) return fail(STORM_E_INVALID, "num_levels out of range");
+  if (c.num_res_blocks < 1) return fail(STORM_E_INVALID, "num_res_blocks must be >= 1");
+  if (!c.discriminative && c.input_channels != 4 && c.input_channels != 6 && c.input_channels != 2)
+    return fail(STORM_E_INVALID, "input_channels must be 2, 4 or 6");
+  const int nf = c.nf, nres = c.num_levels, inch = h->in_ch();
+  auto in_attn = [&](int r) {
+    for (int i = 0; i < c.num_attn_resolutions; ++i)
+      if (c.attn_resolutions[i] == r) return true;
+    return false;
+  };
+  std::vector<Mod>& mods = h->mods;
+  auto add = [&](ModKind k, int ic, int oc, bool up = false, bool down = false) {
+    Mod m; m.index = (int)mods.size(); m.kind = k; m.in_ch = ic; m.out_ch = oc; m.up = up; m.down = down;
+    mods.push_back(m);
+  };
+  add(M_FOURIER, 0, nf);
+  if (h->conditional()) { add(M_LINEAR, 2 * nf, 4 * nf); add(M_LINEAR, 4 * nf, 4 * nf); }
+  add(M_CONV_IN, inch, nf);
+  std::vector<int> hs_c{nf};
+  int in_c = nf;
+  for (int lvl = 0; lvl < nres; ++lvl) {
+    const int r = c.image_size >> lvl;
+    for (int b = 0; b < c.num_res_blocks; ++b) {
+      int out_c = nf * c.ch_mult[lvl];
+      add(M_RES, in_c, out_c);
+      in_c = out_c;
+      if (in_attn(r)) add(M_ATTN, in_c, in_c);
+      hs_c.push_back(in_c);
+    }
+    if (lvl != nres - 1) {
+      add(M_RES, in_c, in_c, false, true);
+      add(M_COMBINE, inch, in_c);
+      hs_c.push_back(in_c);
+    }
+  }
+  in_c = hs_c.back();
+  add(M_RES, in_c, in_c);
+  add(M_ATTN, in_c, in_c);
+  add(M_RES, in_c, in_c);
+  for (int lvl = nres - 1; lvl >= 0; --lvl) {
+    const int r = c.image_size >> lvl;
+    for (int b = 0; b < c.num_res_blocks + 1; ++b) {
+      int out_c = nf * c.ch_mult[lvl];
+      add(M_RES, in_c + hs_c.back(), out_c);
+      hs_c.pop_back();
+      in_c = out_c;
+    }
+    if (in_attn(r)) add(M_ATTN, in_c, in_c);
+    add(M_GN, in_c, in_c);
+    add(M_CONV_OUT, in_c, inch);
+    if (lvl != 0) add(M_RES, in_c, in_c, true, false);
+  }
+  // parameter table in reference state_dict order
+  add_param(h, "output_layer.weight", {2, inch, 1, 1});
+  add_param(h, "output_layer.bias", {2});
+  const int64_t temb_dim = 4 * nf;
+  for (const Mod& m : mods) {
+    std::string p = "all_modules." + std::to_string(m.index);
+    switch (m.kind) {
+      case M_FOURIER: add_param(h, p + ".W", {m.out_ch}); break;
+      case M_LINEAR: add_param(h, p + ".weight", {m.out_ch, m.in_ch}); add_param(h, p + ".bias", {m.out_ch}); break;
+      case M_CONV_IN:
+      case M_CONV_OUT: add_param(h, p + ".weight", {m.out_ch, m.in_ch, 3, 3}); add_param(h, p + ".bias", {m.out_ch}); break;
+      case M_GN: add_param(h, p + ".weight", {m.in_ch}); add_param(h, p + ".bias", {m.in_ch}); break;
+      case M_COMBINE: add_param(h, p + ".Conv_0.weight", {m.out_ch, m.in_ch, 1, 1}); add_param(h, p + ".Conv_0.bias", {m.out_ch}); break;
+      case M_ATTN:
+        add_param(h, p + ".GroupNorm_0.weight", {m.in_ch}); add_param(h, p + ".GroupNorm_0.bias", {m.in_ch});
+        for (int i = 0; i < 4; ++i) {
+          add_param(h, p + ".NIN_" + std::to_string(i) + ".W", {m.in_ch, m.in_ch});
+          add_param(h, p + ".NIN_" + std::to_string(i) + ".b", {m.in_ch});
+        }
+        break;
+      case M_RES:
+        add_param(h, p + ".GroupNorm_0.weight", {m.in_ch}); add_param(h, p + ".GroupNorm_0.bias", {m.in_ch});
+        add_param(h, p + ".Conv_0.weight", {m.out_ch, m.in_ch, 3, 3}); add_param(h, p + ".Conv_0.bias", {m.out_ch});
+        add_param(h, p + ".Dense_0.weight", {m.out_ch, temb_dim}); add_param(h, p + ".Dense_0.bias", {m.out_ch});
+        add_param(h, p + ".GroupNorm_1.weight", {m.out_ch}); add_param(h, p + ".GroupNorm_1.bias", {m.out_ch});
+        add_param(h, p + ".Conv_1.weight", {m.out_ch, m.out_ch, 3, 3}); add_param(h, p + ".Conv_1.bias", {m.out_ch});
+        if (m.in_ch != m.out_ch || m.up || m.down) {
+          add_param(h, p + ".Conv_2.weight", {m.out_ch, m.in_ch, 1, 1}); add_param(h, p + ".Conv_2.bias", {m.out_ch});
+        }
+        break;
+    }
+  }
+  return 0;
+}
+
+#define LAUNCH(h, call)   \
+  do {                    \
+    STORM_TRY(call);      \
+    ++(h)->launches;      \
+  } while (0)
+
+static int dev_alloc(StormHandle* h, size_t floats, float** out) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(floats, 64) * sizeof(float));
+  if (e != cudaSuccess) return fail(STORM_E_NOMEM, std::string("weight cudaMalloc failed: ") + cudaGetErrorString(e));
+  h->packed.push_back(p);
+  *out = (float*)p;
+  return 0;
+}
+
+static void free_packed(StormHandle* h) {
+  for (void* p : h->packed) cudaFree(p);
+  h->packed.clear();
+  h->res.clear(); h->attn.clear(); h->conv_in.clear(); h->conv_out.clear(); h->combine.clear();
+  h->W1t = h->W2t = h->denseWt = h->denseB = nullptr;
+}
+
+// Build the kernel-native copies of the weights from the raw blob.
+static int repack(StormHandle* h, cudaStream_t st) {
+  free_packed(h);
+  const int nf = h->cfg.nf;
+  const int D = 4 * nf;
+  const bool use_tc = h->cfg.engine == 0;
+  // Dense_0 of every ResnetBlock -> one [D][dense_total] matrix
+  h->dense_total = 0;
+  for (const Mod& m : h->mods)
+    if (m.kind == M_RES) h->dense_total += m.out_ch;
+  if (h->conditional()) {
+    STORM_TRY(dev_alloc(h, (size_t)2 * nf * D, &h->W1t));
+    STORM_TRY(dev_alloc(h, (size_t)D * D, &h->W2t));
+    STORM_TRY(dev_alloc(h, (size_t)D * h->dense_total, &h->denseWt));
+    STORM_TRY(dev_alloc(h, (size_t)h->dense_total, &h->denseB));
+    LAUNCH(h, launch_transpose_into(h->P("all_modules.1.weight"), h->W1t, D, 2 * nf, D, 0, st));
+    LAUNCH(h, launch_transpose_into(h->P("all_modules.2.weight"), h->W2t, D, D, D, 0, st));
+  }
+  int off = 0;
+  for (const Mod& m : h->mods) {
+    const std::string p = "all_modules." + std::to_string(m.index);
+    if (m.kind == M_RES) {
+      ResPack r;
+      r.gn0_g = h->P(p + ".GroupNorm_0.weight"); r.gn0_b = h->P(p + ".GroupNorm_0.bias");
+      r.gn1_g = h->P(p + ".GroupNorm_1.weight"); r.gn1_b = h->P(p + ".GroupNorm_1.bias");
+      r.b0 = h->P(p + ".Conv_0.bias");
+      r.has_skip_conv = h->P(p + ".Conv_2.weight") != nullptr;
+      STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &r.w0));
+      LAUNCH(h, launch_pack_conv_simt(h->P(p + ".Conv_0.weight"), r.w0, m.out_ch, m.in_ch, 9, st));
+      STORM_TRY(dev_alloc(h, (size_t)9 * m.out_ch * m.out_ch, &r.w1));
+      LAUNCH(h, launch_pack_conv_simt(h->P(p + ".Conv_1.weight"), r.w1, m.out_ch, m.out_ch, 9, st));
+      STORM_TRY(dev_alloc(h, (size_t)m.out_ch, &r.b12));
+      if (r.has_skip_conv) {
+        STORM_TRY(dev_alloc(h, (size_t)m.in_ch * m.out_ch, &r.w2));
+        LAUNCH(h, launch_pack_conv_simt(h->P(p + ".Conv_2.weight"), r.w2, m.out_ch, m.in_ch, 1, st));
+        LAUNCH(h, launch_add_vec(h->P(p + ".Conv_1.bias"), h->P(p + ".Conv_2.bias"), r.b12, m.out_ch, 1.0f, st));
+      } else {
+        LAUNCH(h, launch_add_vec(h->P(p + ".Conv_1.bias"), nullptr, r.b12, m.out_ch, 1.0f, st));
+      }
+      if (use_tc) {
+        STORM_TRY(tc_pack_weights(h->P(p + ".Conv_0.weight"), m.out_ch, m.in_ch, 9, &r.tc0, &h->packed, st));
+        STORM_TRY(tc_pack_weights(h->P(p + ".Conv_1.weight"), m.out_ch, m.out_ch, 9, &r.tc1, &h->packed, st));
+        if (r.has_skip_conv) STORM_TRY(tc_pack_weights(h->P(p + ".Conv_2.weight"), m.out_ch, m.in_ch, 1, &r.tc2, &h->packed, st));
+      }
+      r.temb_off = off;
+      if (h->conditional()) {
+        LAUNCH(h, launch_transpose_into(h->P(p + ".Dense_0.weight"), h->denseWt, m.out_ch, D, h->dense_total, off, st));
+        STORM_CUDA_TRY(cudaMemcpyAsync(h->denseB + off, h->P(p + ".Dense_0.bias"), m.out_ch * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+      }
+      off += m.out_ch;
+      h->res[m.index] = r;
+    } else if (m.kind == M_ATTN) {
+      AttnPack a;
+      a.gn_g = h->P(p + ".GroupNorm_0.weight"); a.gn_b = h->P(p + ".GroupNorm_0.bias");
+      for (int i = 0; i < 4; ++i) {
+        a.w[i] = h->P(p + ".NIN_" + std::to_string(i) + ".W");
+        a.b[i] = h->P(p + ".NIN_" + std::to_string(i) + ".b");
+        if (use_tc) STORM_TRY(tc_pack_weights_io(a.w[i], m.in_ch, m.in_ch, &a.tc[i], &h->packed, st));
+      }
+      h->attn[m.index] = a;
+    } else if (m.kind == M_CONV_IN) {
+      SmallConvPack s;
+      s.b = h->P(p + ".bias");
+      STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &s.w));
+      LAUNCH(h, launch_pack_conv_simt(h->P(p + ".weight"), s.w, m.out_ch, m.in_ch, 9, st));
+      h->conv_in[m.index] = s;
+    } else if (m.kind == M_CONV_OUT) {
+      // [9][C][8] zero padded on the output-channel axis
+      SmallConvPack s;
+      s.b = h->P(p + ".bias");
+      STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * 8, &s.w));
+      STORM_CUDA_TRY(cudaMemsetAsync(s.w, 0, (size_t)9 * m.in_ch * 8 * sizeof(float), st));
+      float* tmp = nullptr;
+      STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &tmp));
+      LAUNCH(h, launch_pack_conv_simt(h->P(p + ".weight"), tmp, m.out_ch, m.in_ch, 9, st));   // [9][C][Co]
+      STORM_CUDA_TRY(cudaMemcpy2DAsync(s.w, 8 * sizeof(float), tmp, m.out_ch * sizeof(float), m.out_ch * sizeof(float),
+                                       (size_t)9 * m.in_ch, cudaMemcpyDeviceToDevice, st));
+      h->conv_out[m.index] = s;
+    } else if (m.kind == M_COMBINE) {
+      SmallConvPack s;
+      s.b = h->P(p + ".Conv_0.bias");
+      s.w = const_cast<float*>(h->P(p + ".Conv_0.weight"));   // [C][Cin] as stored
+      h->combine[m.index] = s;
+    }
+  }
+  h->weights_loaded = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+struct Fwd {
+  StormHandle* h;
+  cudaStream_t st;
+  int B;
+
+  int alloc(Act& a, int H, int W, int C) {
+    a = Act();
+    a.B = B; a.H = H; a.W = W; a.C = C;
+    void* p;
+    STORM_TRY(h->pool.get(a.elems() * sizeof(float), &p));
+    a.p = (float*)p;
+    a.nchunk = gn_num_chunks(H * W);
+    return 0;
+  }
+  void release(Act& a) {
+    h->pool.put(a.p);
+    h->pool.put(a.part);
+    a.p = nullptr; a.part = nullptr; a.part_valid = false;
+  }
+  int stats(Act& a) {
+    if (a.part_valid) return 0;
+    void* p;
+    STORM_TRY(h->pool.get((size_t)a.B * a.nchunk * a.C * 2 * sizeof(double), &p));
+    a.part = (double*)p;
+    LAUNCH(h, launch_gn_partial(a, st));
+    a.part_valid = true;
+    return 0;
+  }
+  int gn_ss(Act& a0, Act* a1, const float* g, const float* b, float** ss) {
+    STORM_TRY(stats(a0));
+    if (a1) STORM_TRY(stats(*a1));
+    void* p;
+    STORM_TRY(h->pool.get((size_t)B * (a0.C + (a1 ? a1->C : 0)) * 2 * sizeof(float), &p));
+    *ss = (float*)p;
+    LAUNCH(h, launch_gn_finalize(a0, a1, g, b, *ss, st));
+    return 0;
+  }
+  int conv(const ConvParams& p) {
+    if (h->cfg.engine == 0 && conv_tc_eligible(p)) { LAUNCH(h, launch_conv_tc(p, st)); }
+    else { LAUNCH(h, launch_conv_simt(p, st)); }
+    return 0;
+  }
+  int tap(const std::string& name, const Act& a) {
+    if (!h->taps_on) return 0;
+    Act c = a;
+    c.part = nullptr; c.part_valid = false;
+    void* p = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&p, a.elems() * sizeof(float)));
+    STORM_CUDA_TRY(cudaMemcpyAsync(p, a.p, a.elems() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    c.p = (float*)p;
+    auto it = h->taps.find(name);
+    if (it != h->taps.end()) cudaFree(it->second.p);
+    h->taps[name] = c;
+    return 0;
+  }
+
+  // ResnetBlockBigGANpp.forward (layerspp.py:242-274).  x1 != null: input is cat[x0, x1] (ncsnpp.py:381).
+  int res_block(const Mod& m, Act& x0, Act* x1, const float* tembias, Act& out) {
+    const ResPack& r = h->res.at(m.index);
+    const int Cin = x0.C + (x1 ? x1->C : 0);
+    if (Cin != m.in_ch) return fail(STORM_E_STATE, "res_block: channel mismatch");
+    float* ss0 = nullptr;
+    STORM_TRY(gn_ss(x0, x1, r.gn0_g, r.gn0_b, &ss0));
+    Act hr, xr;       // FIR-resampled activated / raw inputs (up/down blocks)
+    const bool resamp = m.up || m.down;
+    int H = x0.H, W = x0.W;
+    if (resamp) {
+      if (x1) return fail(STORM_E_STATE, "res_block: resampling block with concatenated input");
+      H = m.up ? 2 * x0.H : x0.H / 2;
+      W = m.up ? 2 * x0.W : x0.W / 2;
+      STORM_TRY(alloc(hr, H, W, Cin));
+      STORM_TRY(alloc(xr, H, W, Cin));
+      LAUNCH(h, launch_resample(x0, ss0, hr.p, xr.p, m.up ? 1 : 2, st));
+    }
+    Act h1;
+    STORM_TRY(alloc(h1, H, W, m.out_ch));
+    {
+      ConvParams p{};
+      p.nseg = 1;
+      ConvSeg& s = p.seg[0];
+      if (resamp) { s.src0 = hr.p; s.C0 = Cin; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; }
+      else { s.src0 = x0.p; s.C0 = x0.C; s.src1 = x1 ? x1->p : nullptr; s.C1 = x1 ? x1->C : 0; s.ss = ss0; s.silu = 1; }
+      s.taps = 9; s.w = r.w0; s.wtc = r.tc0;
+      p.B = B; p.H = H; p.W = W; p.Cout = m.out_ch;
+      p.bias = r.b0;
+      p.temb = tembias ? tembias + r.temb_off : nullptr;
+      p.temb_stride = h->dense_total;
+      p.res = nullptr; p.out_scale = 1.0f; p.out = h1.p;
+      STORM_TRY(conv(p));
+    }
+    h->pool.put(ss0);
+    if (resamp) release(hr);
+    float* ss1 = nullptr;
+    STORM_TRY(gn_ss(h1, nullptr, r.gn1_g, r.gn1_b, &ss1));
+    STORM_TRY(alloc(out, H, W, m.out_ch));
+    {
+      ConvParams p{};
+      ConvSeg& s = p.seg[0];
+      s.src0 = h1.p; s.C0 = m.out_ch; s.src1 = nullptr; s.C1 = 0; s.ss = ss1; s.silu = 1; s.taps = 9; s.w = r.w1; s.wtc = r.tc1;
+      p.nseg = 1;
+      p.res = nullptr;
+      if (r.has_skip_conv) {
+        ConvSeg& k = p.seg[1];
+        if (resamp) { k.src0 = xr.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; }
+        else { k.src0 = x0.p; k.C0 = x0.C; k.src1 = x1 ? x1->p : nullptr; k.C1 = x1 ? x1->C : 0; }
+        k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2; k.wtc = r.tc2;
+        p.nseg = 2;
+      } else {
+        p.res = x0.p;     // identity skip: in_ch == out_ch, no resampling, single source
+      }
+      p.B = B; p.H = H; p.W = W; p.Cout = m.out_ch;
+      p.bias = r.b12; p.temb = nullptr; p.temb_stride = 0;
+      p.out_scale = 0.70710678118654752f;   // (x + h) / sqrt(2), layerspp.py:274
+      p.out = out.p;
+      STORM_TRY(conv(p));
+    }
+    h->pool.put(ss1);
+    release(h1);
+    if (resamp) release(xr);
+    return 0;
+  }
+
+  // AttnBlockpp.forward (layerspp.py:75-91)
+  int attn_block(const Mod& m, Act& x, Act& out) {
+    const AttnPack& a = h->attn.at(m.index);
+    const int C = x.C, N = x.H * x.W;
+    float* ss = nullptr;
+    STORM_TRY(gn_ss(x, nullptr, a.gn_g, a.gn_b, &ss));
+    Act q, k, v, o;
+    STORM_TRY(alloc(q, x.H, x.W, C)); STORM_TRY(alloc(k, x.H, x.W, C)); STORM_TRY(alloc(v, x.H, x.W, C));
+    Act* qkv[3] = {&q, &k, &v};
+    for (int i = 0; i < 3; ++i) {
+      ConvParams p{};
+      p.nseg = 1;
+      ConvSeg& s = p.seg[0];
+      s.src0 = x.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = ss; s.silu = 0; s.taps = 1; s.w = a.w[i]; s.wtc = a.tc[i];
+      p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[i]; p.out_scale = 1.0f; p.out = qkv[i]->p;
+      STORM_TRY(conv(p));
+    }
+    h->pool.put(ss);
+    STORM_TRY(alloc(o, x.H, x.W, C));
+    LAUNCH(h, launch_attention_simt(q.p, k.p, v.p, o.p, B, N, C, st));
+    release(q); release(k); release(v);
+    STORM_TRY(alloc(out, x.H, x.W, C));
+    {
+      ConvParams p{};
+      p.nseg = 1;
+      ConvSeg& s = p.seg[0];
+      s.src0 = o.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; s.taps = 1; s.w = a.w[3]; s.wtc = a.tc[3];
+      p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[3]; p.res = x.p; p.out_scale = 0.70710678118654752f; p.out = out.p;
+      STORM_TRY(conv(p));
+    }
+    release(o);
+    return 0;
+  }
+};
+
+static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out, int B, int F, int T, cudaStream_t st) {
+  if (!h->weights_loaded) return fail(STORM_E_STATE, "weights not loaded: call storm_load_weights first");
+  const StormNetConfig& c = h->cfg;
+  const int nres = c.num_levels;
+  const int div = 1 << (nres - 1);
+  if (B < 1 || F < div || T < div || F % div || T % div)
+    return fail(STORM_E_INVALID, "F and T must be positive multiples of 2^(num_levels-1) = " + std::to_string(div));
+  if (h->conditional() && !t) return fail(STORM_E_INVALID, "time conditioning tensor t is required");
+  Fwd f{h, st, B};
+  const int inch = h->in_ch();
+  const int nf = c.nf;
+  auto in_attn = [&](int r) {
+    for (int i = 0; i < c.num_attn_resolutions; ++i)
+      if (c.attn_resolutions[i] == r) return true;
+    return false;
+  };
+  if (h->taps_on) {
+    for (auto& kv : h->taps) cudaFree(kv.second.p);
+    h->taps.clear();
+  }
+
+  // ---- time embedding -> per-block biases --------------------------------------------------------------
+  float* tembias = nullptr;
+  float* act = nullptr;
+  if (h->conditional()) {
+    void* p;
+    STORM_TRY(h->pool.get((size_t)B * 4 * nf * sizeof(float), &p)); act = (float*)p;
+    STORM_TRY(h->pool.get((size_t)B * h->dense_total * sizeof(float), &p)); tembias = (float*)p;
+    LAUNCH(h, launch_temb_mlp(t, h->P("all_modules.0.W"), h->W1t, h->P("all_modules.1.bias"), h->W2t,
+                              h->P("all_modules.2.bias"), act, B, nf, st));
+    LAUNCH(h, launch_dense_all(act, h->denseWt, h->denseB, tembias, B, 4 * nf, h->dense_total, st));
+  }
+
+  // ---- input ---------------------------------------------------------------------------------------------
+  size_t mi = h->conditional() ? 3 : 1;
+  Act x0;
+  STORM_TRY(f.alloc(x0, F, T, inch));
+  LAUNCH(h, launch_unpack_input(src, x0.p, B, inch / 2, F * T, st));
+  std::vector<Act> hs;
+  {
+    const Mod& m = h->mods[mi];
+    const SmallConvPack& s = h->conv_in.at(m.index);
+    Act a;
+    STORM_TRY(f.alloc(a, F, T, nf));
+    ConvParams p{};
+    p.nseg = 1;
+    p.seg[0].src0 = x0.p; p.seg[0].C0 = inch; p.seg[0].taps = 9; p.seg[0].w = s.w;
+    p.B = B; p.H = F; p.W = T; p.Cout = nf; p.bias = s.b; p.out_scale = 1.0f; p.out = a.p;
+    LAUNCH(h, launch_conv_simt(p, st));
+    STORM_TRY(f.tap("conv_in", a));
+    hs.push_back(a);
+    ++mi;
+  }
+  Act pyr_in = x0;     // input pyramid (ncsnpp.py:326-328)
+  auto tapmod = [&](const Mod& m, const Act& a) { return f.tap("mod" + std::to_string(m.index), a); };
+
+  // ---- down path -----------------------------------------------------------------------------------------
+  for (int lvl = 0; lvl < nres; ++lvl) {
+    for (int b = 0; b < c.num_res_blocks; ++b) {
+      Act o;
+      STORM_TRY(f.res_block(h->mods[mi], hs.back(), nullptr, tembias, o));
+      STORM_TRY(tapmod(h->mods[mi], o));
+      ++mi;
+      if (in_attn(o.H)) {
+        Act o2;
+        STORM_TRY(f.attn_block(h->mods[mi], o, o2));
+        STORM_TRY(tapmod(h->mods[mi], o2));
+        ++mi;
+        f.release(o);
+        o = o2;
+      }
+      hs.push_back(o);
+    }
+    if (lvl != nres - 1) {
+      Act o;
+      STORM_TRY(f.res_block(h->mods[mi], hs.back(), nullptr, tembias, o));
+      STORM_TRY(tapmod(h->mods[mi], o));
+      ++mi;
+      Act pd;
+      STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, inch));
+      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, inch, st));
+      f.release(pyr_in);
+      pyr_in = pd;
+      const SmallConvPack& s = h->combine.at(h->mods[mi].index);
+      Act o2;
+      STORM_TRY(f.alloc(o2, o.H, o.W, o.C));
+      LAUNCH(h, launch_combine(o.p, pyr_in.p, s.w, s.b, o2.p, B, o.H * o.W, o.C, inch, st));
+      STORM_TRY(tapmod(h->mods[mi], o2));
+      ++mi;
+      f.release(o);
+      hs.push_back(o2);
+    }
+  }
+  f.release(pyr_in);
+
+  // ---- middle ----------------------------------------------------------------------------------------------
+  Act hcur;
+  {
+    Act a, b2, c2;
+    STORM_TRY(f.res_block(h->mods[mi], hs.back(), nullptr, tembias, a)); STORM_TRY(tapmod(h->mods[mi], a)); ++mi;
+    STORM_TRY(f.attn_block(h->mods[mi], a, b2)); STORM_TRY(tapmod(h->mods[mi], b2)); ++mi;
+    f.release(a);
+    STORM_TRY(f.res_block(h->mods[mi], b2, nullptr, tembias, c2)); STORM_TRY(tapmod(h->mods[mi], c2)); ++mi;
+    f.release(b2);
+    hcur = c2;
+  }
+
+  // ---- up path ---------------------------------------------------------------------------------------------
+  Act pyr;   // progressive output pyramid, [B][H][W][inch]
+  bool have_pyr = false;
+  for (int lvl = nres - 1; lvl >= 0; --lvl) {
+    for (int b = 0; b < c.num_res_blocks + 1; ++b) {
+      Act skip = hs.back();
+      hs.pop_back();
+      Act o;
+      STORM_TRY(f.res_block(h->mods[mi], hcur, &skip, tembias, o));
+      STORM_TRY(tapmod(h->mods[mi], o));
+      ++mi;
+      f.release(hcur);
+      f.release(skip);
+      hcur = o;
+    }
+    if (in_attn(hcur.H)) {
+      Act o2;
+      STORM_TRY(f.attn_block(h->mods[mi], hcur, o2));
+      STORM_TRY(tapmod(h->mods[mi], o2));
+      ++mi;
+      f.release(hcur);
+      hcur = o2;
+    }
+    {
+      const Mod& g = h->mods[mi];
+      const Mod& co = h->mods[mi + 1];
+      const std::string gp = "all_modules." + std::to_string(g.index);
+      float* ss = nullptr;
+      STORM_TRY(f.gn_ss(hcur, nullptr, h->P(gp + ".weight"), h->P(gp + ".bias"), &ss));
+      const SmallConvPack& s = h->conv_out.at(co.index);
+      Act np;
+      STORM_TRY(f.alloc(np, hcur.H, hcur.W, inch));
+      LAUNCH(h, launch_conv_out_small(hcur, ss, s.w, s.b, have_pyr ? pyr.p : nullptr, np.p, inch, st));
+      h->pool.put(ss);
+      if (have_pyr) f.release(pyr);
+      pyr = np;
+      have_pyr = true;
+      STORM_TRY(f.tap("pyr" + std::to_string(lvl), pyr));
+      mi += 2;
+    }
+    if (lvl != 0) {
+      Act o;
+      STORM_TRY(f.res_block(h->mods[mi], hcur, nullptr, tembias, o));
+      STORM_TRY(tapmod(h->mods[mi], o));
+      ++mi;
+      f.release(hcur);
+      hcur = o;
+    }
+  }
+  f.release(hcur);
+  if (!hs.empty() || mi != h->mods.size()) return fail(STORM_E_STATE, "forward: module walk out of sync");
+
+  // ---- head ------------------------------------------------------------------------------------------------
+  LAUNCH(h, launch_head(pyr.p, h->conditional() ? t : nullptr, h->P("output_layer.weight"), h->P("output_layer.bias"), out, B,
+                        F * T, inch, st));
+  f.release(pyr);
+  if (act) h->pool.put(act);
+  if (tembias) h->pool.put(tembias);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// OUVE SDE scalars (sdes.py:200-228) and the PC sampler
+// ---------------------------------------------------------------------------------------------------
+static double ouve_std(const StormSamplerConfig& s, double t) {
+  const double ls = log((double)s.sigma_max / (double)s.sigma_min), th = s.theta, sm = s.sigma_min;
+  return sqrt(sm * sm * exp(-2 * th * t) * (exp(2 * (th + ls) * t) - 1) * ls / (th + ls));
+}
+static double ouve_diffusion(const StormSamplerConfig& s, double t) {
+  const double ls = log((double)s.sigma_max / (double)s.sigma_min);
+  return (double)s.sigma_min * pow((double)s.sigma_max / (double)s.sigma_min, t) * sqrt(2 * ls);
+}
+// torch.linspace(1, eps, N) in fp32 (sampling/__init__.py:58)
+static float linspace_at(float start, float end, int steps, int i) {
+  if (steps == 1) return start;
+  const float step = (end - start) / (float)(steps - 1);
+  return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - i - 1);
+}
+
+static int check_sampler(const StormSamplerConfig* sc) {
+  if (!sc) return fail(STORM_E_INVALID, "sampler config is null");
+  if (sc->predictor < 0 || sc->predictor > 2) return fail(STORM_E_INVALID, "Predictor with this id unknown.");
+  if (sc->corrector < 0 || sc->corrector > 2) return fail(STORM_E_INVALID, "Corrector with this id unknown.");
+  if (sc->N < 1 || sc->corrector_steps < 0) return fail(STORM_E_INVALID, "N must be >= 1 and corrector_steps >= 0");
+  if (!(sc->sigma_min > 0) || !(sc->sigma_max > sc->sigma_min)) return fail(STORM_E_INVALID, "need 0 < sigma_min < sigma_max");
+  return 0;
+}
+
+static int pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int B, int F, int T, const StormSamplerConfig& sc,
+                     uint64_t seed, const uint64_t* utt_ids, const float* noise, int* nfe_out, cudaStream_t st) {
+  const int64_t n = (int64_t)F * T;
+  const int ncplx = h->in_ch() / 2;
+  if (ncplx == 3 && !cond) return fail(STORM_E_INVALID, "6-channel score net needs the extra condition spectrogram");
+  if (ncplx < 2) return fail(STORM_E_INVALID, "sampler needs a score network with (x, y) input");
+  void* p;
+  float *xt, *xm, *d, *tdev;
+  uint64_t* ids_dev = nullptr;
+  double* scratch = nullptr;
+  UpdateCoef* coef_dev = nullptr;
+  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xt = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xm = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); d = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * sizeof(float), &p)); tdev = (float*)p;
+  if (utt_ids) {
+    STORM_TRY(h->pool.get((size_t)B * sizeof(uint64_t), &p)); ids_dev = (uint64_t*)p;
+    STORM_CUDA_TRY(cudaMemcpyAsync(ids_dev, utt_ids, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  }
+  if (sc.corrector == STORM_CORR_LANGEVIN) {
+    STORM_TRY(h->pool.get((size_t)B * 64 * 2 * sizeof(double), &p)); scratch = (double*)p;
+    STORM_TRY(h->pool.get(sizeof(UpdateCoef), &p)); coef_dev = (UpdateCoef*)p;
+  }
+  uint32_t draw = 0;
+  auto noise_at = [&](uint32_t dr) -> const float* { return noise ? noise + (size_t)dr * B * n * 2 : nullptr; };
+  auto score = [&](float tval) -> int {   // d = dnn(cat[x, y(, cond)], t); score = -d (model.py:127-132)
+    LAUNCH(h, launch_fill(tdev, tval, B, st));
+    UnpackSrc src{};
+    src.p[0] = xt; src.bstride[0] = n;
+    src.p[1] = Y; src.bstride[1] = n;
+    if (ncplx == 3) { src.p[2] = cond; src.bstride[2] = n; }
+    return net_forward(h, src, tdev, d, B, F, T, st);
+  };
+  // prior: x_T = y + randn * std(T=1) (sdes.py:233-237); StoRM uses the same form around its mean
+  {
+    UpdateCoef c{0.f, 1.f, 0.f, (float)ouve_std(sc, 1.0)};
+    LAUNCH(h, launch_sampler_update(nullptr, Y, nullptr, nullptr, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+    ++draw;
+  }
+  const int N = sc.N;
+  const int n_corr = sc.corrector == STORM_CORR_NONE ? 0 : sc.corrector_steps;
+  bool have_mean = false;
+  for (int i = 0; i < N; ++i) {
+    const float t = linspace_at(1.0f, sc.t_eps, N, i);
+    // ---- corrector (correctors.py:45-93)
+    for (int k = 0; k < n_corr; ++k) {
+      STORM_TRY(score(t));
+      if (sc.corrector == STORM_CORR_ALD) {
+        const double std = ouve_std(sc, t);
+        const double step = (sc.snr * std) * (sc.snr * std) * 2.0;
+        UpdateCoef c{1.f, 0.f, (float)(-step), (float)sqrt(step * 2.0)};
+        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      } else {
+        STORM_TRY(launch_langevin_coef(d, noise_at(draw), seed, ids_dev, draw, sc.snr, B, n, scratch, coef_dev, st));
+        h->launches += 2;
+        UpdateCoef c{1.f, 0.f, 0.f, 1.f};
+        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, coef_dev, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      }
+      ++draw;
+      have_mean = true;
+    }
+    // ---- predictor (predictors.py:41-69; sdes.py:73-90,147-157)
+    if (sc.predictor == STORM_PRED_REVERSE_DIFFUSION) {
+      STORM_TRY(score(t));
+      const double dt = 1.0 / N;
+      const double G = ouve_diffusion(sc, t) * sqrt(dt);
+      const double pf = sc.probability_flow ? 0.5 : 1.0;
+      UpdateCoef c{(float)(1.0 + sc.theta * dt), (float)(-sc.theta * dt), (float)(-G * G * pf), sc.probability_flow ? 0.f : (float)G};
+      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      ++draw;
+      have_mean = true;
+    } else if (sc.predictor == STORM_PRED_EULER_MARUYAMA) {
+      STORM_TRY(score(t));
+      const double g = ouve_diffusion(sc, t);
+      UpdateCoef c{(float)(1.0 + sc.theta / N), (float)(-sc.theta / N), (float)(-g * g / N), (float)(g * sqrt(1.0 / N))};
+      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      ++draw;
+      have_mean = true;
+    } else {
+      // NonePredictor returns (x, x): the mean of this step is the current state (predictors.py:72-80)
+      STORM_CUDA_TRY(cudaMemcpyAsync(xm, xt, (size_t)B * n * 8, cudaMemcpyDeviceToDevice, st));
+      have_mean = true;
+    }
+  }
+  const float* result = (sc.denoise && have_mean) ? xm : xt;   // sampling/__init__.py:64
+  STORM_CUDA_TRY(cudaMemcpyAsync(X, result, (size_t)B * n * 8, cudaMemcpyDeviceToDevice, st));
+  if (nfe_out) *nfe_out = N * (n_corr + 1);
+  h->pool.put(xt); h->pool.put(xm); h->pool.put(d); h->pool.put(tdev);
+  h->pool.put(ids_dev); h->pool.put(scratch); h->pool.put(coef_dev);
+  return 0;
+}
+
+}  // namespace storm
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* storm_last_error(void) { return g_last_error.c_str(); }
+const char* storm_version(void) { return "storm_b200 0.1 (sm_100a)"; }
+
+int storm_create(const StormNetConfig* cfg, StormHandle** out) {
+  if (!cfg || !out) return fail(STORM_E_INVALID, "storm_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(STORM_E_CUDA, "storm_create: no CUDA device available (this library has no CPU path)");
+  StormHandle* h = new StormHandle();
+  h->cfg = *cfg;
+  cudaGetDevice(&h->device);
+  int rc = build_plan(h);
+  if (rc != 0) { delete h; return rc; }
+  void* p = nullptr;
+  e = cudaMalloc(&p, (size_t)h->n_floats * sizeof(float));
+  if (e != cudaSuccess) { delete h; return fail(STORM_E_NOMEM, "storm_create: weight arena allocation failed"); }
+  h->raw = (float*)p;
+  *out = h;
+  return 0;
+}
+
+int storm_destroy(StormHandle* h) {
+  if (!h) return 0;
+  cudaDeviceSynchronize();
+  free_packed(h);
+  for (auto& kv : h->taps) cudaFree(kv.second.p);
+  h->pool.destroy();
+  cudaFree(h->raw);
+  delete h;
+  return 0;
+}
+
+int64_t storm_param_floats(const StormHandle* h) { return h ? h->n_floats : 0; }
+int32_t storm_param_entries(const StormHandle* h) { return h ? (int32_t)h->table.size() : 0; }
+int storm_param_info(const StormHandle* h, int32_t i, char* name, int32_t cap, int64_t shape[4], int32_t* ndim, int64_t* off) {
+  if (!h || i < 0 || i >= (int)h->table.size()) return fail(STORM_E_INVALID, "storm_param_info: index out of range");
+  const ParamEntry& e = h->table[i];
+  if (name && cap > 0) { strncpy(name, e.name.c_str(), cap - 1); name[cap - 1] = 0; }
+  if (shape) for (int k = 0; k < 4; ++k) shape[k] = k < e.ndim ? e.shape[k] : 1;
+  if (ndim) *ndim = e.ndim;
+  if (off) *off = e.offset;
+  return 0;
+}
+
+int storm_load_weights(StormHandle* h, const float* blob, int64_t n, int32_t is_device, void* stream) {
+  if (!h || !blob) return fail(STORM_E_INVALID, "storm_load_weights: null argument");
+  if (n != h->n_floats)
+    return fail(STORM_E_INVALID, "storm_load_weights: blob has " + std::to_string(n) + " floats, expected " + std::to_string(h->n_floats));
+  cudaStream_t st = (cudaStream_t)stream;
+  STORM_CUDA_TRY(cudaMemcpyAsync(h->raw, blob, (size_t)n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return repack(h, st);
+}
+int storm_weights_device(StormHandle* h, float** dev, int64_t* n) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  if (dev) *dev = h->raw;
+  if (n) *n = h->n_floats;
+  return 0;
+}
+int storm_repack_weights(StormHandle* h, void* stream) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  return repack(h, (cudaStream_t)stream);
+}
+
+int64_t storm_workspace_bytes(const StormHandle* h) { return h ? (int64_t)h->pool.total : 0; }
+int64_t storm_launch_count(const StormHandle* h) { return h ? h->launches : 0; }
+int storm_reset_launch_count(StormHandle* h) { if (h) h->launches = 0; return 0; }
+
+int storm_net_forward(StormHandle* h, const float* in, const float* t, float* out, int32_t B, int32_t F, int32_t T, void* stream) {
+  if (!h || !in || !out) return fail(STORM_E_INVALID, "storm_net_forward: null argument");
+  const int nc = h->in_ch() / 2;
+  UnpackSrc src{};
+  for (int ch = 0; ch < nc; ++ch) { src.p[ch] = in + (size_t)ch * F * T * 2; src.bstride[ch] = (long long)nc * F * T; }
+  return net_forward(h, src, t, out, B, F, T, (cudaStream_t)stream);
+}
+
+int storm_reserve(StormHandle* h, int32_t B, int32_t F, int32_t T) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  const int nc = h->in_ch() / 2;
+  void *a, *b, *c;
+  STORM_TRY(h->pool.get((size_t)B * nc * F * T * 8, &a));
+  STORM_TRY(h->pool.get((size_t)B * F * T * 8, &b));
+  STORM_TRY(h->pool.get((size_t)B * 4, &c));
+  STORM_CUDA_TRY(cudaMemset(a, 0, (size_t)B * nc * F * T * 8));
+  int rc = launch_fill((float*)c, 0.5f, B, 0);
+  if (rc == 0) rc = storm_net_forward(h, (const float*)a, (const float*)c, (float*)b, B, F, T, nullptr);
+  cudaDeviceSynchronize();
+  h->pool.put(a); h->pool.put(b); h->pool.put(c);
+  return rc;
+}
+
+int storm_set_debug_taps(StormHandle* h, int32_t enable) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  h->taps_on = enable != 0;
+  if (!h->taps_on) { for (auto& kv : h->taps) cudaFree(kv.second.p); h->taps.clear(); }
+  return 0;
+}
+int storm_get_tap(StormHandle* h, const char* name, float* out, int64_t cap, int64_t shape[4], void* stream) {
+  if (!h || !name) return fail(STORM_E_INVALID, "null argument");
+  auto it = h->taps.find(name);
+  if (it == h->taps.end()) return fail(STORM_E_INVALID, std::string("no tap named ") + name);
+  const Act& a = it->second;
+  if (shape) { shape[0] = a.B; shape[1] = a.C; shape[2] = a.H; shape[3] = a.W; }
+  if (!out) return 0;
+  if (cap < (int64_t)a.elems()) return fail(STORM_E_INVALID, "tap buffer too small");
+  return launch_nhwc_to_nchw(a.p, out, a.B, a.H * a.W, a.C, (cudaStream_t)stream);
+}
+
+int32_t storm_pc_num_draws(const StormSamplerConfig* sc) {
+  if (!sc) return 0;
+  const int n_corr = sc->corrector == STORM_CORR_NONE ? 0 : sc->corrector_steps;
+  return 1 + sc->N * (n_corr + (sc->predictor == STORM_PRED_NONE ? 0 : 1));
+}
+
+int storm_pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int32_t B, int32_t F, int32_t T,
+                    const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int32_t* nfe_out,
+                    void* stream) {
+  if (!h || !Y || !X) return fail(STORM_E_INVALID, "storm_pc_sample: null argument");
+  STORM_TRY(check_sampler(sc));
+  return pc_sample(h, Y, cond, X, B, F, T, *sc, seed, utt_ids, noise, nfe_out, (cudaStream_t)stream);
+}
+
+int storm_philox_normal(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n, float* out, void* stream) {
+  if (!out || n < 0) return fail(STORM_E_INVALID, "storm_philox_normal: bad argument");
+  return launch_philox_fill(seed, utt_id, draw, n, out, (cudaStream_t)stream);
+}
+
+int storm_ode_drift(StormHandle* h, const float* X, const float* Y, float t, float* drift, int32_t B, int32_t F, int32_t T,
+                    const StormSamplerConfig* sc, void* stream) {
+  if (!h || !X || !Y || !drift) return fail(STORM_E_INVALID, "storm_ode_drift: null argument");
+  STORM_TRY(check_sampler(sc));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)F * T;
+  void* p;
+  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); float* d = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * 4, &p)); float* tdev = (float*)p;
+  LAUNCH(h, launch_fill(tdev, t, B, st));
+  UnpackSrc src{};
+  src.p[0] = X; src.bstride[0] = n; src.p[1] = Y; src.bstride[1] = n;
+  STORM_TRY(net_forward(h, src, tdev, d, B, F, T, st));
+  const double g = ouve_diffusion(*sc, t);
+  LAUNCH(h, launch_ode_drift(X, Y, d, drift, sc->theta, (float)(0.5 * g * g), (int64_t)B * n, st));
+  h->pool.put(d); h->pool.put(tdev);
+  return 0;
+}
+
+int32_t storm_num_frames(int32_t L, const StormSpecConfig* sp) { return sp && sp->hop_length > 0 ? 1 + L / sp->hop_length : 0; }
+int32_t storm_padded_frames(int32_t frames) { return (frames + 63) / 64 * 64; }
+
+int storm_wave_norm(const float* wav, int32_t B, int32_t L, float* norm, void* stream) {
+  if (!wav || !norm) return fail(STORM_E_INVALID, "storm_wave_norm: null argument");
+  return launch_wave_norm(wav, B, L, norm, (cudaStream_t)stream);
+}
+int storm_stft(const float* wav, const float* norm, int32_t B, int32_t L, float* spec, int32_t T_pad, const StormSpecConfig* sp,
+               void* stream) {
+  if (!wav || !spec || !sp) return fail(STORM_E_INVALID, "storm_stft: null argument");
+  return launch_stft(wav, norm, B, L, spec, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+                     sp->spec_abs_exponent, (cudaStream_t)stream);
+}
+int storm_istft(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
+                const StormSpecConfig* sp, void* stream) {
+  if (!h || !spec || !wav || !sp) return fail(STORM_E_INVALID, "storm_istft: null argument");
+  void* p;
+  STORM_TRY(h->pool.get((size_t)B * T_pad * sp->n_fft * sizeof(float), &p));
+  int rc = launch_istft(spec, norm, B, T_pad, (float*)p, wav, L, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+                        sp->spec_abs_exponent, (cudaStream_t)stream);
+  h->launches += 2;
+  h->pool.put(p);
+  return rc;
+}
+
+int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const StormSamplerConfig* sc,
+                  const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids, int32_t* nfe_out, void* stream) {
+  if (!h || !wav_in || !wav_out || !sp) return fail(STORM_E_INVALID, "storm_enhance: null argument");
+  STORM_TRY(check_sampler(sc));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = sp->n_fft / 2 + 1;
+  const int T_pad = storm_padded_frames(storm_num_frames(L, sp));
+  void* p;
+  STORM_TRY(h->pool.get((size_t)B * 4, &p)); float* norm = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* Y = (float*)p;
+  STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* X = (float*)p;
+  LAUNCH(h, launch_wave_norm(wav_in, B, L, norm, st));
+  LAUNCH(h, launch_stft(wav_in, norm, B, L, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+                        sp->spec_abs_exponent, st));
+  STORM_TRY(pc_sample(h, Y, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
+  STORM_TRY(storm_istft(h, X, norm, B, T_pad, wav_out, L, sp, stream));
+  h->pool.put(norm); h->pool.put(Y); h->pool.put(X);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,977 @@
+// Small kernels of the reverse-diffusion path: weight packing, time embedding, GroupNorm statistics,
+// FIR resampling, input/pyramid/head, attention (SIMT), sampler updates with Philox noise, STFT/iSTFT.
+// Every kernel here is HBM- or latency-bound; the FLOPs live in conv_simt.cu / conv_tc.cu.
+#include "kernels.cuh"
+
+#include <math.h>
+
+namespace storm {
+
+namespace {
+constexpr float PI_F = 3.14159274101257324f;   // float(np.pi), as torch's fp32 scalar multiply sees it
+constexpr double PI_D = 3.14159265358979323846;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+}  // namespace
+
+// =====================================================================================================
+// weights
+// =====================================================================================================
+__global__ void pack_conv_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps) {
+  size_t n = (size_t)Cout * Cin * taps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int co = i % Cout;
+    int ci = (i / Cout) % Cin;
+    int tap = i / ((size_t)Cout * Cin);
+    out[i] = w[((size_t)co * Cin + ci) * taps + tap];
+  }
+}
+int launch_pack_conv_simt(const float* w, float* out, int Cout, int Cin, int taps, cudaStream_t st) {
+  size_t n = (size_t)Cout * Cin * taps;
+  pack_conv_simt_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, taps);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void transpose_into_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int cols,
+                                      int out_stride, int out_off) {
+  size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = i % rows;
+    int c = i / rows;
+    out[(size_t)c * out_stride + out_off + r] = w[(size_t)r * cols + c];
+  }
+}
+int launch_transpose_into(const float* w, float* out, int rows, int cols, int out_stride, int out_off, cudaStream_t st) {
+  size_t n = (size_t)rows * cols;
+  transpose_into_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, rows, cols, out_stride, out_off);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n, float sb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? sb * b[i] : 0.f);
+}
+int launch_add_vec(const float* a, const float* b, float* out, int n, float scale_b, cudaStream_t st) {
+  add_vec_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, out, n, scale_b);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// time embedding
+// =====================================================================================================
+__global__ void temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ Wf, const float* __restrict__ W1t,
+                                const float* __restrict__ b1, const float* __restrict__ W2t, const float* __restrict__ b2,
+                                float* __restrict__ act, int nf) {
+  extern __shared__ float sm[];
+  const int E = 2 * nf, D = 4 * nf;
+  float* e = sm;        // [E]
+  float* h = sm + E;    // [D]
+  const int b = blockIdx.x;
+  // log in double then rounded: the correctly rounded fp32 log (torch.log on CPU is <= 1 ulp)
+  const float lt = (float)log((double)t[b]);
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    // x[:, None] * W[None, :] * 2 * np.pi evaluated left to right in fp32 (layerspp.py:40)
+    float p = __fmul_rn(__fmul_rn(__fmul_rn(lt, Wf[i]), 2.0f), PI_F);
+    e[i] = (float)sin((double)p);
+    e[nf + i] = (float)cos((double)p);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < D; o += blockDim.x) {
+    float s = b1[o];
+    for (int i = 0; i < E; ++i) s = fmaf(e[i], W1t[(size_t)i * D + o], s);
+    h[o] = silu_f(s);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < D; o += blockDim.x) {
+    float s = b2[o];
+    for (int i = 0; i < D; ++i) s = fmaf(h[i], W2t[(size_t)i * D + o], s);
+    act[(size_t)b * D + o] = silu_f(s);   // every consumer applies act(temb) first (layerspp.py:263)
+  }
+}
+int launch_temb_mlp(const float* t, const float* Wf, const float* W1t, const float* b1, const float* W2t, const float* b2,
+                    float* act, int B, int nf, cudaStream_t st) {
+  temb_mlp_kernel<<<B, 256, 6 * nf * sizeof(float), st>>>(t, Wf, W1t, b1, W2t, b2, act, nf);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                 float* __restrict__ out, int B, int in_dim, int out_dim) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_dim) return;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[o];
+    const int nb = min(8, B - b0);
+    for (int i = 0; i < in_dim; ++i) {
+      float w = Wt[(size_t)i * out_dim + o];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nb) acc[j] = fmaf(w, __ldg(act + (size_t)(b0 + j) * in_dim + i), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nb) out[(size_t)(b0 + j) * out_dim + o] = acc[j];
+  }
+}
+int launch_dense_all(const float* act, const float* Wt, const float* bias, float* out, int B, int in_dim, int out_dim,
+                     cudaStream_t st) {
+  dense_all_kernel<<<ceil_div(out_dim, 128), 128, 0, st>>>(act, Wt, bias, out, B, in_dim, out_dim);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// GroupNorm statistics
+// =====================================================================================================
+int gn_num_chunks(int HW) {
+  int n = HW / 256;
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  return n;
+}
+
+__global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int nchunk) {
+  extern __shared__ double smd[];   // [rows][C4][8]
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int C4 = C >> 2;
+  const int rows = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
+  const int per = (HW + nchunk - 1) / nchunk;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (r < rows) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)b * HW * C) + c4;
+    for (int p = p0 + r; p < p1; p += rows) {
+      float4 v = __ldg(xp + (size_t)p * C4);
+      s[0] += v.x; q[0] += (double)v.x * v.x;
+      s[1] += v.y; q[1] += (double)v.y * v.y;
+      s[2] += v.z; q[2] += (double)v.z * v.z;
+      s[3] += v.w; q[3] += (double)v.w * v.w;
+    }
+    double* d = smd + ((size_t)r * C4 + c4) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { d[j] = s[j]; d[4 + j] = q[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    double ts[4] = {0, 0, 0, 0}, tq[4] = {0, 0, 0, 0};
+    for (int rr = 0; rr < rows; ++rr) {
+      const double* d = smd + ((size_t)rr * C4 + threadIdx.x) * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ts[j] += d[j]; tq[j] += d[4 + j]; }
+    }
+    double* o = part + (((size_t)b * nchunk + chunk) * C + threadIdx.x * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = ts[j]; o[2 * j + 1] = tq[j]; }
+  }
+}
+int launch_gn_partial(const Act& a, cudaStream_t st) {
+  if (a.C % 4 != 0 || a.C / 4 > 256) return fail(-1, "gn_partial: unsupported channel count");
+  const int C4 = a.C / 4;
+  int threads = 256;
+  int rows = threads / C4;
+  size_t smem = (size_t)rows * C4 * 8 * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    STORM_CUDA_TRY(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  gn_partial_kernel<<<dim3(a.nchunk, a.B), threads, smem, st>>>(a.p, a.part, a.H * a.W, a.C, a.nchunk);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ part0, int C0, int nchunk0, const double* __restrict__ part1,
+                                   int C1, int nchunk1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ ss, int HW, int G) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = C0 + C1;
+  const int cpg = C / G;
+  double s = 0, q = 0;
+  const int maxchunk = max(nchunk0, nchunk1);
+  for (int i = threadIdx.x; i < cpg * maxchunk; i += blockDim.x) {
+    int cc = g * cpg + i % cpg;
+    int ch = i / cpg;
+    if (cc < C0) {
+      if (ch < nchunk0) {
+        const double* d = part0 + (((size_t)b * nchunk0 + ch) * C0 + cc) * 2;
+        s += d[0]; q += d[1];
+      }
+    } else if (ch < nchunk1) {
+      const double* d = part1 + (((size_t)b * nchunk1 + ch) * C1 + (cc - C0)) * 2;
+      s += d[0]; q += d[1];
+    }
+  }
+  __shared__ double rs[32], rq[32];
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { S += rs[i]; Q += rq[i]; }
+    double n = (double)cpg * HW;
+    double mean = S / n;
+    double var = Q / n - mean * mean;
+    if (var < 0) var = 0;
+    rs[0] = mean;
+    rq[0] = 1.0 / sqrt(var + 1e-6);
+  }
+  __syncthreads();
+  const double mean = rs[0], rstd = rq[0];
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    int cc = g * cpg + i;
+    double sc = (double)gamma[cc] * rstd;
+    float* o = ss + ((size_t)b * C + cc) * 2;
+    o[0] = (float)sc;
+    o[1] = (float)((double)beta[cc] - mean * sc);
+  }
+}
+int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const float* beta, float* ss, cudaStream_t st) {
+  const int C = a0.C + (a1 ? a1->C : 0);
+  int G = C / 4 < 32 ? C / 4 : 32;
+  if (G < 1 || C % G != 0) return fail(-1, "gn_finalize: channels not divisible into groups");
+  gn_finalize_kernel<<<dim3(G, a0.B), 128, 0, st>>>(a0.part, a0.C, a0.nchunk, a1 ? a1->part : nullptr, a1 ? a1->C : 0,
+                                                     a1 ? a1->nchunk : 0, gamma, beta, ss, a0.H * a0.W, G);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// FIR resampling
+// =====================================================================================================
+__device__ __forceinline__ float4 act4(float4 v, const float* ss4) {
+  // ss4 -> 4 consecutive (scale, shift) pairs
+  float4 a = __ldg(reinterpret_cast<const float4*>(ss4));
+  float4 b = __ldg(reinterpret_cast<const float4*>(ss4) + 1);
+  float4 r;
+  r.x = silu_f(fmaf(v.x, a.x, a.y));
+  r.y = silu_f(fmaf(v.y, a.z, a.w));
+  r.z = silu_f(fmaf(v.z, b.x, b.y));
+  r.w = silu_f(fmaf(v.w, b.z, b.w));
+  return r;
+}
+
+__global__ void resample_kernel(const float* __restrict__ x, const float* __restrict__ ss, float* __restrict__ h_out,
+                                float* __restrict__ x_out, int B, int H, int W, int C, int mode) {
+  const int C4 = C >> 2;
+  const int OH = mode == 1 ? 2 * H : H / 2, OW = mode == 1 ? 2 * W : W / 2;
+  const size_t total = (size_t)B * OH * OW * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t r = i / C4;
+    const int ox = r % OW; r /= OW;
+    const int oy = r % OH;
+    const int b = r / OH;
+    const float* ssp = ss ? ss + ((size_t)b * C + c4 * 4) * 2 : nullptr;
+    float4 ax = make_float4(0, 0, 0, 0), ah = make_float4(0, 0, 0, 0);
+    int ys[4], xs[4];
+    float wy[4], wx[4];
+    int ny, nx;
+    if (mode == 1) {   // up: o[2i] = x[i-1]/4 + 3x[i]/4 ; o[2i+1] = 3x[i]/4 + x[i+1]/4
+      ny = nx = 2;
+      int iy = oy >> 1, ix = ox >> 1;
+      if (oy & 1) { ys[0] = iy; wy[0] = 0.75f; ys[1] = iy + 1; wy[1] = 0.25f; }
+      else        { ys[0] = iy - 1; wy[0] = 0.25f; ys[1] = iy; wy[1] = 0.75f; }
+      if (ox & 1) { xs[0] = ix; wx[0] = 0.75f; xs[1] = ix + 1; wx[1] = 0.25f; }
+      else        { xs[0] = ix - 1; wx[0] = 0.25f; xs[1] = ix; wx[1] = 0.75f; }
+    } else {           // down: o[i] = (x[2i-1] + 3x[2i] + 3x[2i+1] + x[2i+2]) / 8
+      ny = nx = 4;
+      const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ys[j] = 2 * oy - 1 + j; wy[j] = k[j]; xs[j] = 2 * ox - 1 + j; wx[j] = k[j]; }
+    }
+    for (int jy = 0; jy < ny; ++jy) {
+      if ((unsigned)ys[jy] >= (unsigned)H) continue;
+      for (int jx = 0; jx < nx; ++jx) {
+        if ((unsigned)xs[jx] >= (unsigned)W) continue;
+        const float wgt = wy[jy] * wx[jx];
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + ys[jy]) * W + xs[jx]) * C) + c4);
+        ax.x = fmaf(wgt, v.x, ax.x); ax.y = fmaf(wgt, v.y, ax.y); ax.z = fmaf(wgt, v.z, ax.z); ax.w = fmaf(wgt, v.w, ax.w);
+        if (h_out) {
+          float4 a = ssp ? act4(v, ssp) : v;
+          ah.x = fmaf(wgt, a.x, ah.x); ah.y = fmaf(wgt, a.y, ah.y); ah.z = fmaf(wgt, a.z, ah.z); ah.w = fmaf(wgt, a.w, ah.w);
+        }
+      }
+    }
+    const size_t o = (((size_t)b * OH + oy) * OW + ox) * C4 + c4;
+    if (x_out) reinterpret_cast<float4*>(x_out)[o] = ax;
+    if (h_out) reinterpret_cast<float4*>(h_out)[o] = ah;
+  }
+}
+int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, int mode, cudaStream_t st) {
+  if (x.C % 4 != 0) return fail(-1, "resample: C must be a multiple of 4");
+  if (mode == 2 && ((x.H | x.W) & 1)) return fail(-1, "resample: downsampling needs even extents");
+  const int OH = mode == 1 ? 2 * x.H : x.H / 2, OW = mode == 1 ? 2 * x.W : x.W / 2;
+  size_t total = (size_t)x.B * OH * OW * (x.C / 4);
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  resample_kernel<<<blocks, 256, 0, st>>>(x.p, ss, h_out, x_out, x.B, x.H, x.W, x.C, mode);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const size_t total = (size_t)B * OH * OW * C;
+  const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    size_t r = i / C;
+    const int ox = r % OW; r /= OW;
+    const int oy = r % OH;
+    const int b = r / OH;
+    float acc = 0.f;
+    for (int jy = 0; jy < 4; ++jy) {
+      int y = 2 * oy - 1 + jy;
+      if ((unsigned)y >= (unsigned)H) continue;
+      for (int jx = 0; jx < 4; ++jx) {
+        int xx = 2 * ox - 1 + jx;
+        if ((unsigned)xx >= (unsigned)W) continue;
+        acc = fmaf(k[jy] * k[jx], __ldg(x + (((size_t)b * H + y) * W + xx) * C + c), acc);
+      }
+    }
+    out[i] = acc;
+  }
+}
+int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, cudaStream_t st) {
+  size_t total = (size_t)B * (H / 2) * (W / 2) * C;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  if (blocks == 0) blocks = 1;
+  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// input / pyramid / head
+// =====================================================================================================
+__global__ void unpack_input_kernel(UnpackSrc src, float* __restrict__ out, int B, int nc, int HW) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = i / HW;
+    const int p = i % HW;
+    for (int ch = 0; ch < nc; ++ch) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(src.p[ch]) + (size_t)b * src.bstride[ch] + p);
+      out[i * (2 * nc) + 2 * ch] = 2.0f * v.x - 1.0f;
+      out[i * (2 * nc) + 2 * ch + 1] = 2.0f * v.y - 1.0f;
+    }
+  }
+}
+int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int HW, cudaStream_t st) {
+  if (nc < 1 || nc > 3) return fail(-1, "unpack_input: 1..3 complex channels");
+  size_t total = (size_t)B * HW;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  unpack_input_kernel<<<blocks, 256, 0, st>>>(src, out, B, nc, HW);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void fill_kernel(float* p, float v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int launch_fill(float* p, float v, int n, cudaStream_t st) {
+  fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p, v, n);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void combine_kernel(const float* __restrict__ h, const float* __restrict__ pyr, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ out, size_t npix, int C, int Cin) {
+  const int C4 = C >> 2;
+  const size_t total = npix * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    const size_t p = i / C4;
+    float4 hv = __ldg(reinterpret_cast<const float4*>(h) + i);
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = bias[c4 * 4 + j];
+    for (int k = 0; k < Cin; ++k) {
+      float pv = __ldg(pyr + p * Cin + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(__ldg(w + (size_t)(c4 * 4 + j) * Cin + k), pv, acc[j]);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(acc[0] + hv.x, acc[1] + hv.y, acc[2] + hv.z, acc[3] + hv.w);
+  }
+}
+int launch_combine(const float* h, const float* pyr, const float* w, const float* bias, float* out, int B, int HW, int C,
+                   int Cin, cudaStream_t st) {
+  size_t total = (size_t)B * HW * (C / 4);
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  combine_kernel<<<blocks, 256, 0, st>>>(h, pyr, w, bias, out, (size_t)B * HW, C, Cin);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- progressive output branch: conv3x3 C -> Co<=8 with GN+SiLU prologue ------------------------------
+namespace {
+constexpr int OT = 16;            // 16x16 output pixels per CTA
+constexpr int OKC = 8;
+constexpr int OHL = OT + 2;
+constexpr int OHP = OHL + 1;      // padded row pitch
+}
+__global__ void __launch_bounds__(256) conv_out_small_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ prev, float* __restrict__ out,
+                                                             int H, int W, int C, int Co) {
+  __shared__ float sA[OKC][OHL][OHP];
+  __shared__ __align__(16) float sW[9][OKC][8];
+  const int tiles_x = (W + OT - 1) / OT;
+  const int ty0 = (blockIdx.x / tiles_x) * OT, tx0 = (blockIdx.x % tiles_x) * OT;
+  const int b = blockIdx.y;
+  const int py = threadIdx.x / OT, px = threadIdx.x % OT;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += OKC) {
+    for (int e = threadIdx.x; e < OKC * OHL * OHL; e += 256) {
+      int ch = e % OKC;
+      int pix = e / OKC;
+      int hy = pix / OHL, hx = pix % OHL;
+      int y = ty0 + hy - 1, xx = tx0 + hx - 1;
+      float v = 0.f;
+      if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W && c0 + ch < C) {
+        v = __ldg(x + (((size_t)b * H + y) * W + xx) * C + c0 + ch);
+        if (ss) {
+          const float* s2 = ss + ((size_t)b * C + c0 + ch) * 2;
+          v = silu_f(fmaf(v, __ldg(s2), __ldg(s2 + 1)));
+        }
+      }
+      sA[ch][hy][hx] = v;
+    }
+    for (int e = threadIdx.x; e < 9 * OKC * 8; e += 256) {
+      int j = e % 8;
+      int ch = (e / 8) % OKC;
+      int tap = e / (8 * OKC);
+      sW[tap][ch][j] = (c0 + ch < C) ? __ldg(w + ((size_t)tap * C + c0 + ch) * 8 + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ch = 0; ch < OKC; ++ch) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          float a = sA[ch][py + dy][px + dx];
+          float4 w0 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][0]);
+          float4 w1 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][4]);
+          acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+          acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+        }
+    }
+    __syncthreads();
+  }
+  const int y = ty0 + py, xx = tx0 + px;
+  if (y >= H || xx >= W) return;
+  for (int j = 0; j < Co; ++j) {
+    float v = acc[j] + bias[j];
+    if (prev) {   // + FIR_up(prev) at (y, xx): prev is [B][H/2][W/2][Co]
+      const int PH = H / 2, PW = W / 2;
+      int iy = y >> 1, ix = xx >> 1;
+      int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+      if (y & 1) { y0 = iy; wy0 = 0.75f; y1 = iy + 1; wy1 = 0.25f; } else { y0 = iy - 1; wy0 = 0.25f; y1 = iy; wy1 = 0.75f; }
+      if (xx & 1) { x0 = ix; wx0 = 0.75f; x1 = ix + 1; wx1 = 0.25f; } else { x0 = ix - 1; wx0 = 0.25f; x1 = ix; wx1 = 0.75f; }
+      float u = 0.f;
+      const float* pb = prev + (size_t)b * PH * PW * Co + j;
+      if ((unsigned)y0 < (unsigned)PH) {
+        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy0 * wx0, __ldg(pb + ((size_t)y0 * PW + x0) * Co), u);
+        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy0 * wx1, __ldg(pb + ((size_t)y0 * PW + x1) * Co), u);
+      }
+      if ((unsigned)y1 < (unsigned)PH) {
+        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy1 * wx0, __ldg(pb + ((size_t)y1 * PW + x0) * Co), u);
+        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy1 * wx1, __ldg(pb + ((size_t)y1 * PW + x1) * Co), u);
+      }
+      v = u + v;   // pyramid = upsample(pyramid) + pyramid_h (ncsnpp.py:405-410)
+    }
+    out[(((size_t)b * H + y) * W + xx) * Co + j] = v;
+  }
+}
+int launch_conv_out_small(const Act& h, const float* ss, const float* w, const float* bias, const float* prev, float* out,
+                          int Co, cudaStream_t st) {
+  if (Co > 8) return fail(-1, "conv_out_small: Co > 8");
+  dim3 grid(ceil_div(h.W, OT) * ceil_div(h.H, OT), h.B);
+  conv_out_small_kernel<<<grid, 256, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void head_kernel(const float* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ w,
+                            const float* __restrict__ bias, float2* __restrict__ out, int B, int HW, int Ci) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = i / HW;
+    float re = bias[0], im = bias[1];
+    const float tb = t ? t[b] : 1.0f;
+    for (int k = 0; k < Ci; ++k) {
+      float v = __ldg(pyr + i * Ci + k);
+      if (t) v = v / tb;                     // h / used_sigmas before the output conv (ncsnpp.py:441-446)
+      re = fmaf(w[k], v, re);
+      im = fmaf(w[Ci + k], v, im);
+    }
+    out[i] = make_float2(re, im);
+  }
+}
+int launch_head(const float* pyr, const float* t, const float* w, const float* bias, float* out_c, int B, int HW, int Ci,
+                cudaStream_t st) {
+  size_t total = (size_t)B * HW;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  head_kernel<<<blocks, 256, 0, st>>>(pyr, t, w, bias, reinterpret_cast<float2*>(out_c), B, HW, Ci);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// attention (SIMT flash-style): one CTA = 16 queries, key tiles of 32
+// =====================================================================================================
+namespace {
+constexpr int AQ = 16, AK = 32;
+}
+__global__ void __launch_bounds__(256) attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                             const float* __restrict__ v, float* __restrict__ o, int N, int C,
+                                                             float scale) {
+  extern __shared__ float sm[];
+  const int CP = C + 4;
+  float* Qs = sm;                    // [AQ][CP]
+  float* Ks = Qs + AQ * CP;          // [AK][CP]
+  float* Vs = Ks + AK * CP;          // [AK][C]
+  float* Ss = Vs + AK * C;           // [AQ][AK]
+  float* alpha = Ss + AQ * AK;       // [AQ]
+  float* lsum = alpha + AQ;          // [AQ]
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * AQ;
+  const int tid = threadIdx.x;
+  const int C4 = C >> 2;
+  const float* qb = q + (size_t)b * N * C;
+  const float* kb = k + (size_t)b * N * C;
+  const float* vb = v + (size_t)b * N * C;
+  for (int e = tid; e < AQ * C4; e += 256) {
+    int r = e / C4, c4 = e % C4;
+    float4 val = make_float4(0, 0, 0, 0);
+    if (q0 + r < N) val = __ldg(reinterpret_cast<const float4*>(qb + (size_t)(q0 + r) * C) + c4);
+    *reinterpret_cast<float4*>(Qs + r * CP + c4 * 4) = val;
+  }
+  float O[AQ];
+#pragma unroll
+  for (int i = 0; i < AQ; ++i) O[i] = 0.f;
+  const int sq = tid >> 4;      // query row handled in the score phase
+  const int sk = tid & 15;      // keys sk and sk + 16
+  float m_run = -INFINITY, l_run = 0.f;   // replicated across the 16 lanes of a query row
+  for (int k0 = 0; k0 < N; k0 += AK) {
+    __syncthreads();
+    for (int e = tid; e < AK * C4; e += 256) {
+      int r = e / C4, c4 = e % C4;
+      float4 kv = make_float4(0, 0, 0, 0), vv = make_float4(0, 0, 0, 0);
+      if (k0 + r < N) {
+        kv = __ldg(reinterpret_cast<const float4*>(kb + (size_t)(k0 + r) * C) + c4);
+        vv = __ldg(reinterpret_cast<const float4*>(vb + (size_t)(k0 + r) * C) + c4);
+      }
+      *reinterpret_cast<float4*>(Ks + r * CP + c4 * 4) = kv;
+      *reinterpret_cast<float4*>(Vs + r * C + c4 * 4) = vv;
+    }
+    __syncthreads();
+    // ---- scores
+    float s0 = 0.f, s1 = 0.f;
+    {
+      const float4* qp = reinterpret_cast<const float4*>(Qs + sq * CP);
+      const float4* k0p = reinterpret_cast<const float4*>(Ks + sk * CP);
+      const float4* k1p = reinterpret_cast<const float4*>(Ks + (sk + 16) * CP);
+      for (int c4 = 0; c4 < C4; ++c4) {
+        float4 a = qp[c4], b0 = k0p[c4], b1 = k1p[c4];
+        s0 = fmaf(a.x, b0.x, s0); s0 = fmaf(a.y, b0.y, s0); s0 = fmaf(a.z, b0.z, s0); s0 = fmaf(a.w, b0.w, s0);
+        s1 = fmaf(a.x, b1.x, s1); s1 = fmaf(a.y, b1.y, s1); s1 = fmaf(a.z, b1.z, s1); s1 = fmaf(a.w, b1.w, s1);
+      }
+    }
+    s0 = (k0 + sk < N) ? s0 * scale : -INFINITY;
+    s1 = (k0 + sk + 16 < N) ? s1 * scale : -INFINITY;
+    float mx = fmaxf(s0, s1);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float m_new = fmaxf(m_run, mx);
+    const float p0 = expf(s0 - m_new), p1 = expf(s1 - m_new);
+    float ps = p0 + p1;
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+    const float al = expf(m_run - m_new);
+    l_run = l_run * al + ps;
+    m_run = m_new;
+    Ss[sq * AK + sk] = p0;
+    Ss[sq * AK + sk + 16] = p1;
+    if (sk == 0) alpha[sq] = al;
+    __syncthreads();
+    // ---- O = O * alpha + P V   (thread = channel)
+    if (tid < C) {
+#pragma unroll
+      for (int i = 0; i < AQ; ++i) O[i] *= alpha[i];
+      for (int kk = 0; kk < AK; kk += 4) {
+        float v0 = Vs[(kk + 0) * C + tid], v1 = Vs[(kk + 1) * C + tid], v2 = Vs[(kk + 2) * C + tid], v3 = Vs[(kk + 3) * C + tid];
+#pragma unroll
+        for (int i = 0; i < AQ; ++i) {
+          float4 p = *reinterpret_cast<const float4*>(Ss + i * AK + kk);
+          O[i] = fmaf(p.x, v0, O[i]); O[i] = fmaf(p.y, v1, O[i]); O[i] = fmaf(p.z, v2, O[i]); O[i] = fmaf(p.w, v3, O[i]);
+        }
+      }
+    }
+  }
+  if (sk == 0) lsum[sq] = l_run;
+  __syncthreads();
+  if (tid < C) {
+#pragma unroll
+    for (int i = 0; i < AQ; ++i)
+      if (q0 + i < N) o[((size_t)b * N + q0 + i) * C + tid] = O[i] / lsum[i];
+  }
+}
+int launch_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int N, int C, cudaStream_t st) {
+  if (C > 256 || C % 4 != 0) return fail(-1, "attention_simt: C must be <= 256 and a multiple of 4");
+  size_t smem = ((size_t)AQ * (C + 4) + (size_t)AK * (C + 4) + (size_t)AK * C + AQ * AK + 2 * AQ) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    STORM_CUDA_TRY(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  attention_simt_kernel<<<dim3(ceil_div(N, AQ), B), 256, smem, st>>>(q, k, v, o, N, C, 1.0f / sqrtf((float)C));
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// sampler updates + Philox
+// =====================================================================================================
+namespace {
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// complex standard normal (var 1/2 per component), counter = (element, draw, utterance id), key = seed
+__device__ __forceinline__ float2 philox_cnormal(uint64_t seed, uint64_t utt, uint32_t draw, uint32_t idx) {
+  uint32_t c[4] = {idx, draw, (uint32_t)utt, (uint32_t)(utt >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-logf(u1));   // sqrt(-2 ln u1) * sqrt(1/2)
+  float s, co;
+  sincospif(2.0f * u2, &s, &co);
+  return make_float2(r * co, r * s);
+}
+}  // namespace
+
+__global__ void sampler_update_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ d,
+                                      float2* __restrict__ x_mean, float2* __restrict__ x_new, UpdateCoef coef,
+                                      const UpdateCoef* __restrict__ coef_dev, const float2* __restrict__ noise, uint64_t seed,
+                                      const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n) {
+  const int b = blockIdx.y;
+  if (coef_dev) coef = *coef_dev;
+  const uint64_t utt = utt_ids ? utt_ids[b] : (uint64_t)b;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const size_t g = (size_t)b * n + i;
+    float2 m = make_float2(0.f, 0.f);
+    if (coef.a != 0.f) { float2 v = x[g]; m.x = coef.a * v.x; m.y = coef.a * v.y; }
+    if (coef.b != 0.f) { float2 v = y[g]; m.x = fmaf(coef.b, v.x, m.x); m.y = fmaf(coef.b, v.y, m.y); }
+    if (coef.c != 0.f) { float2 v = d[g]; m.x = fmaf(coef.c, v.x, m.x); m.y = fmaf(coef.c, v.y, m.y); }
+    if (x_mean) x_mean[g] = m;
+    if (x_new) {
+      float2 z = make_float2(0.f, 0.f);
+      if (coef.e != 0.f || noise) z = noise ? noise[g] : philox_cnormal(seed, utt, draw, (uint32_t)i);
+      x_new[g] = make_float2(fmaf(coef.e, z.x, m.x), fmaf(coef.e, z.y, m.y));
+    }
+  }
+}
+int launch_sampler_update(const float* x, const float* y, const float* d, float* x_mean, float* x_new, UpdateCoef coef,
+                          const UpdateCoef* coef_dev, const float* noise, uint64_t seed, const uint64_t* utt_ids_dev,
+                          uint32_t draw, int B, int64_t n, cudaStream_t st) {
+  unsigned bx = (unsigned)((n + 255) / 256 > 148 * 4 ? 148 * 4 : (n + 255) / 256);
+  sampler_update_kernel<<<dim3(bx, B), 256, 0, st>>>(
+      reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), reinterpret_cast<const float2*>(d),
+      reinterpret_cast<float2*>(x_mean), reinterpret_cast<float2*>(x_new), coef, coef_dev,
+      reinterpret_cast<const float2*>(noise), seed, utt_ids_dev, draw, n);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void philox_fill_kernel(uint64_t seed, uint64_t utt, uint32_t draw, int64_t n, float2* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = philox_cnormal(seed, utt, draw, (uint32_t)i);
+}
+int launch_philox_fill(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n, float* out, cudaStream_t st) {
+  unsigned bx = (unsigned)((n + 255) / 256 > 148 * 4 ? 148 * 4 : (n + 255) / 256);
+  philox_fill_kernel<<<bx, 256, 0, st>>>(seed, utt_id, draw, n, reinterpret_cast<float2*>(out));
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// scratch: [B][64][2] doubles
+__global__ void sqnorm_partial_kernel(const float2* __restrict__ d, const float2* __restrict__ noise, uint64_t seed,
+                                      const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n, double* scratch) {
+  const int b = blockIdx.y;
+  const uint64_t utt = utt_ids ? utt_ids[b] : (uint64_t)b;
+  double sd = 0, sz = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 v = d[(size_t)b * n + i];
+    float2 z = noise ? noise[(size_t)b * n + i] : philox_cnormal(seed, utt, draw, (uint32_t)i);
+    sd += (double)v.x * v.x + (double)v.y * v.y;
+    sz += (double)z.x * z.x + (double)z.y * z.y;
+  }
+  __shared__ double r0[8], r1[8];
+  sd = warp_sum_d(sd); sz = warp_sum_d(sz);
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = sd; r1[threadIdx.x >> 5] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < 8; ++i) { a += r0[i]; c += r1[i]; }
+    scratch[((size_t)b * gridDim.x + blockIdx.x) * 2] = a;
+    scratch[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
+  }
+}
+__global__ void langevin_coef_kernel(const double* scratch, int B, int nblk, float snr, UpdateCoef* out) {
+  if (threadIdx.x != 0) return;
+  float gn = 0.f, zn = 0.f;   // mean over the batch of per-sample L2 norms (correctors.py:53-54)
+  for (int b = 0; b < B; ++b) {
+    double a = 0, c = 0;
+    for (int i = 0; i < nblk; ++i) { a += scratch[((size_t)b * nblk + i) * 2]; c += scratch[((size_t)b * nblk + i) * 2 + 1]; }
+    gn += (float)sqrt(a);
+    zn += (float)sqrt(c);
+  }
+  gn /= (float)B; zn /= (float)B;
+  float r = snr * zn / gn;
+  float step = r * r * 2.0f;
+  out->a = 1.f; out->b = 0.f; out->c = -step; out->e = sqrtf(step * 2.0f);
+}
+int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* utt_ids_dev, uint32_t draw,
+                         float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st) {
+  const int nblk = 64;
+  sqnorm_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(reinterpret_cast<const float2*>(d), reinterpret_cast<const float2*>(noise),
+                                                       seed, utt_ids_dev, draw, n, scratch);
+  STORM_LAUNCH_CHECK();
+  langevin_coef_kernel<<<1, 32, 0, st>>>(scratch, B, nblk, snr, coef_out);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void ode_drift_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ d,
+                                 float2* __restrict__ out, float theta, float half_g2, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 xv = x[i], yv = y[i], dv = d[i];
+    out[i] = make_float2(fmaf(half_g2, dv.x, theta * (yv.x - xv.x)), fmaf(half_g2, dv.y, theta * (yv.y - xv.y)));
+  }
+}
+int launch_ode_drift(const float* x, const float* y, const float* d, float* out, float theta, float half_g2, int64_t n_total,
+                     cudaStream_t st) {
+  unsigned bx = (unsigned)((n_total + 255) / 256 > 148 * 8 ? 148 * 8 : (n_total + 255) / 256);
+  ode_drift_kernel<<<bx, 256, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y),
+                                       reinterpret_cast<const float2*>(d), reinterpret_cast<float2*>(out), theta, half_g2, n_total);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// STFT / iSTFT (direct DFT of length n_fft = 510 = 2*3*5*17: not a power of two, data_module.py:143,232)
+// =====================================================================================================
+__global__ void wave_norm_kernel(const float* __restrict__ wav, int L, float* __restrict__ norm) {
+  const int b = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(wav[(size_t)b * L + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float r[32];
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, r[i]);
+    norm[b] = m;
+  }
+}
+int launch_wave_norm(const float* wav, int B, int L, float* norm, cudaStream_t st) {
+  wave_norm_kernel<<<B, 1024, 0, st>>>(wav, L, norm);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace {
+__device__ __forceinline__ float window_at(int n, int n_fft, int sqrt_window) {
+  // torch.hann_window(n_fft, periodic=True) = 0.5 - 0.5 cos(2 pi n / n_fft)   (data_module.py:19-25)
+  double w = 0.5 - 0.5 * cospi(2.0 * (double)n / (double)n_fft);
+  return sqrt_window ? (float)sqrt(w) : (float)w;
+}
+}  // namespace
+
+// smem: frame[n_fft] floats, tw[n_fft] float2
+__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav, const float* __restrict__ norm, int L,
+                                                   float2* __restrict__ spec, int T_pad, int n_frames, int n_fft, int hop,
+                                                   int sqrt_window, float factor, float expo) {
+  extern __shared__ float sm[];
+  float* frame = sm;
+  float2* tw = reinterpret_cast<float2*>(sm + n_fft + (n_fft & 1));
+  const int f = blockIdx.x, b = blockIdx.y;
+  const int nb = n_fft / 2 + 1;
+  if (f >= n_frames) {   // pad_spec: zero frames up to the next multiple of 64 (util/other.py:102-109)
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) spec[((size_t)b * nb + k) * T_pad + f] = make_float2(0.f, 0.f);
+    return;
+  }
+  const float nrm = norm ? norm[b] : 1.0f;
+  const int pad = n_fft / 2;
+  for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+    int j = f * hop + n - pad;                 // center=True, reflect padding (torch.stft)
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    float v = wav[(size_t)b * L + j];
+    if (norm) v = v / nrm;                     // y = y / norm_factor (model.py:284)
+    frame[n] = v * window_at(n, n_fft, sqrt_window);
+    double s, c;
+    sincospi(2.0 * (double)n / (double)n_fft, &s, &c);
+    tw[n] = make_float2((float)c, (float)s);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    int idx = 0;
+    for (int n = 0; n < n_fft; ++n) {
+      const float2 w = tw[idx];
+      const float v = frame[n];
+      re = fmaf(v, w.x, re);
+      im = fmaf(-v, w.y, im);
+      idx += k;
+      if (idx >= n_fft) idx -= n_fft;
+    }
+    // spec_fwd: |z|^e e^{i angle z} * factor (data_module.py:182-186)
+    if (expo != 1.0f) {
+      const float mag = hypotf(re, im);
+      if (mag > 0.f) {
+        const float m2 = (expo == 0.5f) ? sqrtf(mag) : powf(mag, expo);
+        re = m2 * (re / mag);
+        im = m2 * (im / mag);
+      } else {
+        re = 0.f; im = 0.f;
+      }
+    }
+    spec[((size_t)b * nb + k) * T_pad + f] = make_float2(re * factor, im * factor);
+  }
+}
+int launch_stft(const float* wav, const float* norm, int B, int L, float* spec, int T_pad, int n_fft, int hop, int sqrt_window,
+                float factor, float expo, cudaStream_t st) {
+  if (L <= n_fft / 2) return fail(-1, "stft: signal shorter than the reflect padding");
+  const int n_frames = 1 + L / hop;
+  if (T_pad < n_frames) return fail(-1, "stft: T_pad smaller than the frame count");
+  size_t smem = (size_t)(n_fft + (n_fft & 1)) * sizeof(float) + (size_t)n_fft * sizeof(float2);
+  stft_kernel<<<dim3(T_pad, B), 256, smem, st>>>(wav, norm, L, reinterpret_cast<float2*>(spec), T_pad, n_frames, n_fft, hop,
+                                                sqrt_window, factor, expo);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// frames_buf[b][f][n] = window[n] * irfft(spec_back(spec[b][:, f]))[n]
+__global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restrict__ spec, int T_pad, float* __restrict__ frames_buf,
+                                                           int n_fft, int sqrt_window, float factor, float expo) {
+  extern __shared__ float sm[];
+  const int nb = n_fft / 2 + 1;
+  float2* X = reinterpret_cast<float2*>(sm);          // [nb]
+  float2* tw = X + nb;                                // [n_fft]
+  const int f = blockIdx.x, b = blockIdx.y;
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    float2 z = spec[((size_t)b * nb + k) * T_pad + f];
+    float re = z.x / factor, im = z.y / factor;        // spec / spec_factor (data_module.py:189)
+    if (expo != 1.0f) {
+      const float mag = hypotf(re, im);
+      if (mag > 0.f) {
+        const float inv = 1.0f / expo;
+        const float m2 = (expo == 0.5f) ? mag * mag : powf(mag, inv);
+        re = m2 * (re / mag);
+        im = m2 * (im / mag);
+      } else {
+        re = 0.f; im = 0.f;
+      }
+    }
+    X[k] = make_float2(re, im);
+  }
+  for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)n / (double)n_fft, &s, &c);
+    tw[n] = make_float2((float)c, (float)s);
+  }
+  __syncthreads();
+  const float invn = 1.0f / (float)n_fft;
+  for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+    // c2r inverse of a one-sided spectrum (imaginary parts of DC / Nyquist ignored), n_fft even
+    float acc = 0.f;
+    int idx = n;   // k * n mod n_fft for k = 1
+    for (int k = 1; k < nb - 1; ++k) {
+      const float2 w = tw[idx];
+      const float2 xk = X[k];
+      acc = fmaf(xk.x, w.x, acc);
+      acc = fmaf(-xk.y, w.y, acc);
+      idx += n;
+      if (idx >= n_fft) idx -= n_fft;
+    }
+    float v = X[0].x + ((n & 1) ? -X[nb - 1].x : X[nb - 1].x) + 2.0f * acc;
+    v *= invn;
+    frames_buf[((size_t)b * T_pad + f) * n_fft + n] = v * window_at(n, n_fft, sqrt_window);
+  }
+}
+__global__ void istft_ola_kernel(const float* __restrict__ frames_buf, const float* __restrict__ norm, int T_pad,
+                                 float* __restrict__ wav, int L, int n_fft, int hop, int sqrt_window) {
+  const int b = blockIdx.y;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < L; m += gridDim.x * blockDim.x) {
+    const int mp = m + n_fft / 2;
+    int f_lo = (mp - n_fft + 1 + hop - 1) / hop;
+    if (mp - n_fft + 1 < 0) f_lo = 0;
+    int f_hi = mp / hop;
+    if (f_hi > T_pad - 1) f_hi = T_pad - 1;
+    float y = 0.f, env = 0.f;
+    for (int f = f_lo; f <= f_hi; ++f) {
+      const int n = mp - f * hop;
+      const float w = window_at(n, n_fft, sqrt_window);
+      y += frames_buf[((size_t)b * T_pad + f) * n_fft + n];
+      env = fmaf(w, w, env);
+    }
+    float v = (f_hi >= f_lo) ? y / env : 0.f;
+    if (norm) v *= norm[b];                    // x_hat * norm_factor (model.py:302)
+    wav[(size_t)b * L + m] = v;
+  }
+}
+int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* frames_buf, float* wav, int L, int n_fft, int hop,
+                 int sqrt_window, float factor, float expo, cudaStream_t st) {
+  if (n_fft & 1) return fail(-1, "istft: n_fft must be even");
+  const int nb = n_fft / 2 + 1;
+  size_t smem = (size_t)(nb + n_fft) * sizeof(float2);
+  istft_frames_kernel<<<dim3(T_pad, B), 256, smem, st>>>(reinterpret_cast<const float2*>(spec), T_pad, frames_buf, n_fft, sqrt_window,
+                                                        factor, expo);
+  STORM_LAUNCH_CHECK();
+  istft_ola_kernel<<<dim3(ceil_div(L, 256) > 512 ? 512 : ceil_div(L, 256), B), 256, 0, st>>>(frames_buf, norm, T_pad, wav, L, n_fft, hop,
+                                                                                       sqrt_window);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const size_t r = i / C;
+    const int p = r % HW;
+    const size_t b = r / HW;
+    out[(b * C + c) * HW + p] = in[i];
+  }
+}
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t st) {
+  size_t total = (size_t)B * HW * C;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  nhwc_to_nchw_kernel<<<blocks, 256, 0, st>>>(in, out, HW, C, total);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace storm

@@ -1,0 +1,248 @@
+"""``ScoreModel``: the reference-facing entry point of the path (sgmse/model.py:24-310).
+
+Same constructor keywords, ``forward`` / ``get_pc_sampler`` / ``get_ode_sampler`` / ``enhance`` signatures and
+return forms; ``load_from_checkpoint`` reads the reference's Lightning ``.ckpt`` files (state_dict under
+``dnn.*`` plus the ``torch_ema`` shadow parameters, model.py:86-111) without needing pytorch_lightning.
+Training code (losses, optimisers, dataloaders) is out of scope.  New: ``enhance_batch`` (the reference
+handles one utterance per call) and sharding helpers used by ``enhancement.py --gpus``.
+"""
+from __future__ import annotations
+
+import time
+from math import ceil
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import _native, sampling
+from .backbones import BackboneRegistry
+from .data_module import SpecsDataModule
+from .sdes import SDERegistry
+from .util.other import pad_spec
+
+
+class ScoreModel:
+    def __init__(self, backbone: str = "ncsnpp", sde: str = "ouve", lr: float = 1e-4, ema_decay: float = 0.999,
+                 t_eps: float = 3e-2, transform: str = "none", nolog: bool = False, num_eval_files: int = 50,
+                 loss_type: str = "mse", data_module_cls=None, seed: int = 42, **kwargs):
+        if sde == "ouvesde":          # the reference's own (unregistered) default spelling, model.py:26
+            sde = "ouve"
+        dnn_cls = BackboneRegistry.get_by_name(backbone)
+        kwargs.update(input_channels=4)                       # model.py:47
+        self.dnn = dnn_cls(**kwargs)
+        self.sde = SDERegistry.get_by_name(sde)(**kwargs)
+        self.t_eps = t_eps
+        self.data_module = (data_module_cls or SpecsDataModule)(**kwargs)
+        self.hparams = dict(backbone=backbone, sde=sde, t_eps=t_eps, **kwargs)
+        self._seed = seed
+        self._calls = 0
+        self._ema_shadow: Optional[List[torch.Tensor]] = None
+        self._raw_params: Optional[List[torch.Tensor]] = None
+        self.device = torch.device("cpu")
+
+    # ---- nn.Module-like plumbing ----------------------------------------------------------------------------
+    def cuda(self, device=None):
+        self.dnn.cuda(device)
+        self.device = next(self.dnn.parameters()).device
+        return self
+
+    def to(self, *args, **kwargs):
+        self.dnn.to(*args, **kwargs)
+        self.device = next(self.dnn.parameters()).device
+        return self
+
+    def parameters(self):
+        return self.dnn.parameters()
+
+    def state_dict(self):
+        return {"dnn." + k: v for k, v in self.dnn.state_dict().items()}
+
+    def load_state_dict(self, sd, strict=True):
+        return self.dnn.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("dnn.")}, strict=strict)
+
+    def eval(self, no_ema: bool = False):
+        """Swap the EMA shadow weights in for inference unless ``no_ema`` (model.py:97-111)."""
+        if self._ema_shadow is not None and not no_ema and self._raw_params is None:
+            params = list(self.dnn.parameters())
+            self._raw_params = [p.detach().clone() for p in params]
+            with torch.no_grad():
+                for p, s in zip(params, self._ema_shadow):
+                    p.copy_(s.to(p.device))
+            self.dnn.mark_weights_changed()
+        return self
+
+    def train(self, mode: bool = True, no_ema: bool = False):
+        if mode:
+            if self._raw_params is not None:
+                with torch.no_grad():
+                    for p, s in zip(self.dnn.parameters(), self._raw_params):
+                        p.copy_(s)
+                self._raw_params = None
+                self.dnn.mark_weights_changed()
+            return self
+        return self.eval(no_ema=no_ema)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        """Read a reference Lightning checkpoint (enhancement.py:56-60)."""
+        ckpt = _load_ckpt(checkpoint_path, map_location)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.pop("data_module_cls", None)
+        hp.update({k: v for k, v in overrides.items() if k not in ("kwargs",)})
+        model = cls(**hp)
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        ema = ckpt.get("ema")
+        if ema is not None and ema.get("shadow_params") is not None:
+            model._ema_shadow = [s.detach().clone() for s in ema["shadow_params"]][: len(list(model.dnn.parameters()))]
+        return model
+
+    def next_seed(self) -> int:
+        self._calls += 1
+        return (self._seed * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+
+    # ---- score ------------------------------------------------------------------------------------------------
+    def _raw_dnn_output(self, x, t, y):
+        return self.dnn(torch.cat([x, y], dim=1), t)                 # model.py:127-129
+
+    def forward(self, x, t, y, **kwargs):
+        return -self._raw_dnn_output(x, t, y)                        # model.py:131-136
+
+    __call__ = forward
+
+    # ---- samplers ---------------------------------------------------------------------------------------------
+    def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, scale_factor=None, **kwargs):
+        sde = self.sde.copy()
+        sde.N = self.sde.N if N is None else N
+        kwargs = {"eps": self.t_eps, **kwargs}
+        if minibatch is None:
+            return sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self, y=y, **kwargs)
+        return self._minibatched(lambda ym, ids: sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self,
+                                                                        y=ym, utt_ids=ids, **kwargs), y, minibatch)
+
+    def get_ode_sampler(self, y, N=None, minibatch=1, **kwargs):
+        sde = self.sde.copy()
+        sde.N = self.sde.N if N is None else N
+        kwargs = {"eps": self.t_eps, **kwargs}
+        if minibatch is None:
+            return sampling.get_ode_sampler(sde, self, y=y, **kwargs)
+        return self._minibatched(lambda ym, ids: sampling.get_ode_sampler(sde, self, y=ym, utt_ids=ids, **kwargs), y, minibatch)
+
+    @staticmethod
+    def _minibatched(make, y, minibatch):                            # model.py:208-222
+        M = y.shape[0]
+
+        def batched_sampling_fn():
+            samples, ns = [], []
+            for i in range(int(ceil(M / minibatch))):
+                lo, hi = i * minibatch, min(M, (i + 1) * minibatch)
+                sample, n = make(y[lo:hi], list(range(lo, hi)))()
+                samples.append(sample)
+                ns.append(n)
+            return torch.cat(samples, dim=0), ns
+
+        return batched_sampling_fn
+
+    # ---- audio <-> spectrogram ----------------------------------------------------------------------------------
+    def _forward_transform(self, spec):
+        return self.data_module.spec_fwd(spec)
+
+    def _backward_transform(self, spec):
+        return self.data_module.spec_back(spec)
+
+    def _stft(self, sig):
+        return self.data_module.stft(sig)
+
+    def _istft(self, spec, length=None):
+        return self.data_module.istft(spec, length)
+
+    def to_audio(self, spec, length=None):
+        return self._istft(self._backward_transform(spec), length)
+
+    # ---- one-call enhancement ---------------------------------------------------------------------------------
+    def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=50, corrector_steps=1, snr=0.5,
+                timeit=False, scale_factor=None, return_stft=False, **kwargs):
+        """One utterance ``y`` [1, L] -> enhanced waveform [L] on the CPU, like model.py:273-310."""
+        start = time.time()
+        T_orig = y.size(1)
+        dev = self._device()
+        yd = y.to(dev, torch.float32)
+        if sampler_type == "pc" and not return_stft and not kwargs:
+            sc = self._sampler_cfg(predictor, corrector, N, corrector_steps, snr)
+            x_hat, nfe = self.dnn.engine().enhance(yd, sc, self.data_module.spec_config(), seed=self.next_seed())
+            x_hat = x_hat.squeeze().cpu()
+        else:
+            norm = _native.wave_norm(yd)
+            T_pad = _native.padded_frames(_native.num_frames(T_orig, self.data_module.spec_config()))
+            Y = _native.stft(yd, norm, self.data_module.spec_config(), T_pad).unsqueeze(1)
+            if sampler_type == "pc":
+                sampler = self.get_pc_sampler(predictor, corrector, Y, N=N, corrector_steps=corrector_steps, snr=snr, **kwargs)
+            elif sampler_type == "ode":
+                sampler = self.get_ode_sampler(Y, N=N, **kwargs)
+            else:
+                raise ValueError("{} is not a valid sampler type!".format(sampler_type))
+            sample, nfe = sampler()
+            if return_stft:
+                return sample.squeeze(), Y.squeeze(), T_orig, norm.item()
+            x_hat = self.dnn.engine().istft(sample.squeeze(1), norm, T_orig, self.data_module.spec_config()).squeeze().cpu()
+        if timeit:
+            return x_hat, nfe, (time.time() - start) / (len(x_hat) / 16000)
+        return x_hat
+
+    def enhance_batch(self, ys: Union[torch.Tensor, Sequence[torch.Tensor]], predictor="reverse_diffusion", corrector="ald", N=50,
+                      corrector_steps=1, snr=0.5, seed: Optional[int] = None, utt_ids: Optional[Sequence[int]] = None,
+                      return_nfe: bool = False):
+        """Batch of equal-length utterances [B, L] (or a list of [L]/[1, L]) -> [B, L] on the input's device.
+        Host tensors are staged through pinned memory; noise is keyed per utterance id, so results do not
+        depend on how a set of utterances is split into batches or across GPUs."""
+        if not torch.is_tensor(ys):
+            ys = torch.stack([y.reshape(-1) for y in ys])
+        src_dev = ys.device
+        dev = self._device()
+        yd = ys.to(torch.float32)
+        if not yd.is_cuda:
+            yd = yd.pin_memory().to(dev, non_blocking=True)
+        sc = self._sampler_cfg(predictor, corrector, N, corrector_steps, snr)
+        out, nfe = self.dnn.engine().enhance(yd, sc, self.data_module.spec_config(), seed=self.next_seed() if seed is None else seed,
+                                             utt_ids=utt_ids)
+        out = out.to(src_dev)
+        return (out, nfe) if return_nfe else out
+
+    def _sampler_cfg(self, predictor, corrector, N, corrector_steps, snr):
+        s = self.sde
+        return _native.make_sampler_config(predictor, corrector, N, corrector_steps, snr, self.t_eps, s.theta, s.sigma_min, s.sigma_max)
+
+    def _device(self):
+        p = next(self.dnn.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("ScoreModel.enhance needs the model on a CUDA device: call model.cuda() first "
+                               "(the reference hard-codes y.cuda(), model.py:285)")
+        return p.device
+
+
+class _Tolerant:
+    """Stand-in for classes pickled into reference checkpoints whose modules are absent here
+    (the pickled ``data_module_cls`` hyper-parameter, model.py:61-62)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        pass
+
+
+def _load_ckpt(path, map_location):
+    import pickle
+
+    class _U(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except Exception:  # noqa: BLE001
+                return _Tolerant
+
+    class _P:
+        Unpickler = _U
+        load = staticmethod(pickle.load)
+        __name__ = "pickle"
+
+    return torch.load(path, map_location=map_location, pickle_module=_P, weights_only=False)

@@ -1,0 +1,241 @@
+"""Parity of the CUDA path (through the C ABI) with the reference-generated fixtures and the CPU oracle.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, sub_sd
+from oracle import storm_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+TOL = 1e-3          # north-star tolerance on fp32 spectrogram values
+TIGHT = 2e-4        # what the fp32 / bf16x3 kernels are expected to reach
+
+
+def _model(name="ncsnpp", sd=None, **kw):
+    from storm_b200 import BackboneRegistry
+    m = BackboneRegistry.get_by_name(name)(**kw)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("fix,kw", [
+    ("ncsnpp_tiny", dict(nf=8)),
+    ("ncsnpp_tiny_6ch", dict(nf=8, input_channels=6)),
+    ("ncsnpp_tiny_disc", dict(nf=8, discriminative=True)),
+    ("ncsnpplarge_tiny", dict(nf=8, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,))),
+])
+def test_tiny_networks_vs_reference(fix, kw):
+    g = load_golden(fix)
+    m = _model("ncsnpp", sub_sd(g, "sd/"), **kw)
+    t = T(g["t"]).cuda() if "t" in g else None
+    y = m(T(g["x"]).cuda(), t).cpu()
+    assert y.shape == g["y"].shape
+    assert rel_l2(y, g["y"]) < TIGHT
+
+
+def _full(name):
+    from storm_b200 import ncsnpp_spec
+    fix = {"ncsnpp": "ncsnpp_full_64x64", "ncsnpplarge": "ncsnpplarge_full_256x64"}[name]
+    g = load_golden(fix)
+    m = _model(name)
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=int(g["seed"]), init_scale=float(g["init_scale"]), bias_std=float(g["bias_std"]))
+    m.load_state_dict(sd)
+    return g, m, sd
+
+
+@pytest.mark.parametrize("name", ["ncsnpp", "ncsnpplarge"])
+def test_full_width_vs_reference(name):
+    g, m, _ = _full(name)
+    y = m(T(g["x"]).cuda(), T(g["t"]).cuda()).cpu()
+    err = rel_l2(y, g["y"])
+    print(f"{name}: rel-L2 vs reference = {err:.3e}")
+    assert err < TOL
+
+
+def test_layer_taps_vs_oracle():
+    """Every module output of the full-width ncsnpp against the oracle's activation at the same point."""
+    g, m, sd = _full("ncsnpp")
+    eng = m.engine()
+    eng.set_taps(True)
+    y = m(T(g["x"]).cuda(), T(g["t"]).cuda())
+    taps = {}
+    O.ncsnpp_forward(sd, O.NetCfg(), T(g["x"]), T(g["t"]), taps=taps)
+    worst = 0.0
+    for name, ref in taps.items():
+        got = eng.get_tap(name).cpu()
+        assert got.shape == ref.shape, name
+        e = rel_l2(got, ref)
+        worst = max(worst, e)
+        print(f"{name:10s} {tuple(ref.shape)} rel-L2 {e:.3e}")
+        assert e < TOL, f"layer {name} deviates: {e}"
+    eng.set_taps(False)
+    print("worst layer error", worst)
+
+
+def _noise(arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+@pytest.mark.parametrize("tag,pred,corr", [("rd_ald", "reverse_diffusion", "ald"), ("rd_ald2", "reverse_diffusion", "ald"),
+                                           ("em_langevin", "euler_maruyama", "langevin"),
+                                           ("rd_none", "reverse_diffusion", "none"), ("none_ald", "none", "ald")])
+def test_pc_sampler_vs_reference(tag, pred, corr):
+    from storm_b200 import _native
+    g = load_golden("sampler")
+    m = _model("ncsnpp", sub_sd(g, "sd/"), nf=8)
+    sc = _native.make_sampler_config(pred, corr, int(g[f"{tag}/N"]), int(g[f"{tag}/csteps"]), float(g[f"{tag}/snr"]), 0.03)
+    x, nfe = m.engine().pc_sample(T(g["y"]).cuda(), sc, noise=_noise(g[f"{tag}/noise"]))
+    assert nfe == int(g[f"{tag}/nfe"])
+    assert rel_l2(x.cpu(), g[f"{tag}/x"]) < TIGHT
+
+
+def test_registry_level_sampler_and_errors():
+    from storm_b200 import ScoreModel, sampling
+    g = load_golden("sampler")
+    model = ScoreModel(backbone="ncsnpp", sde="ouve", nf=8)
+    model.load_state_dict({"dnn." + k: v for k, v in sub_sd(g, "sd/").items()})
+    model.cuda()
+    Y = T(g["y"]).cuda()
+    sampler = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=int(g["rd_ald/N"]), snr=0.5, noise=_noise(g["rd_ald/noise"]))
+    x, nfe = sampler()
+    assert nfe == 6 and rel_l2(x.cpu(), g["rd_ald/x"]) < TIGHT
+    with pytest.raises(ValueError):
+        model.get_pc_sampler("no_such_predictor", "ald", Y, N=3)
+    with pytest.raises(ValueError):
+        sampling.CorrectorRegistry.get_by_name("nope")
+    # score function contract: ScoreModel.forward = -dnn(cat[x, y], t)
+    t = torch.tensor([0.5, 0.7], device="cuda")
+    s = model(Y, t, Y)
+    sref = O.make_score_fn(sub_sd(g, "sd/"), O.NetCfg(nf=8))(T(g["y"]), t.cpu(), T(g["y"]))
+    assert rel_l2(s.cpu(), sref) < TIGHT
+
+
+def test_ode_sampler_vs_reference():
+    from storm_b200 import ScoreModel
+    g = load_golden("sampler")
+    model = ScoreModel(backbone="ncsnpp", sde="ouve", nf=8)
+    model.load_state_dict({"dnn." + k: v for k, v in sub_sd(g, "sd/").items()})
+    model.cuda()
+    Y = T(g["y"]).cuda()
+    sampler = model.get_ode_sampler(Y, N=int(g["ode/N"]), minibatch=None, noise=_noise(g["ode/noise"]))
+    x, nfe = sampler()
+    assert abs(nfe - int(g["ode/nfe"])) <= 12          # adaptive solver: step count may move by a stage or two
+    assert rel_l2(x.cpu(), g["ode/x"]) < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_stft_istft_vs_reference(tag):
+    from storm_b200 import _native, SpecsDataModule
+    g = load_golden("stft")
+    dm = SpecsDataModule()
+    sig = T(g[f"{tag}/sig"]).cuda()
+    S = dm.stft(sig)
+    assert tuple(S.shape) == g[f"{tag}/stft"].shape                      # frame/bin counts: exact
+    assert rel_l2(S.cpu(), g[f"{tag}/stft"]) < 1e-5
+    L = sig.shape[-1]
+    T_pad = _native.padded_frames(_native.num_frames(L, dm.spec_config()))
+    assert T_pad == int(g[f"{tag}/padded_T"])
+    Sf = _native.stft(sig, None, dm.spec_config(), T_pad)
+    frames = g[f"{tag}/fwd"].shape[-1]
+    assert rel_l2(Sf[..., :frames].cpu(), g[f"{tag}/fwd"]) < 1e-5
+    assert torch.count_nonzero(Sf[..., frames:]) == 0                    # pad_spec zeros: exact
+    back = dm.istft(dm.spec_back(T(g[f"{tag}/fwd"]).cuda()), L)
+    assert tuple(back.shape) == g[f"{tag}/back"].shape
+    assert rel_l2(back.cpu(), g[f"{tag}/back"]) < 1e-5
+    back2 = m_istft_fused(T(g[f"{tag}/fwd"]).cuda(), L, dm)
+    assert rel_l2(back2.cpu(), g[f"{tag}/back"]) < 1e-5
+
+
+def m_istft_fused(spec, L, dm):
+    from storm_b200.data_module import _scratch_engine
+    return _scratch_engine().istft(spec, None, L, dm.spec_config())
+
+
+def test_stft_sqrthann_identity_transform():
+    from storm_b200 import SpecsDataModule
+    g = load_golden("stft")
+    dm = SpecsDataModule(spec_factor=0.33, spec_abs_exponent=1.0, window="sqrthann")
+    S = dm.stft(T(g["d/sig"]).cuda())
+    assert rel_l2(S.cpu(), g["d/stft"]) < 1e-5
+    assert rel_l2(dm.spec_fwd(S).cpu(), g["d/fwd"]) < 1e-5
+    assert rel_l2(dm.istft(dm.spec_back(dm.spec_fwd(S)), 3000).cpu(), g["d/back"]) < 1e-5
+
+
+def test_enhance_chain_vs_reference():
+    """normalise -> STFT -> transform -> pad -> PC sampler (injected noise) -> inverse, as ScoreModel.enhance."""
+    from storm_b200 import _native
+    g = load_golden("enhance")
+    m = _model("ncsnpp", sub_sd(g, "sd/"), nf=8)
+    sp = _native.make_spec_config()
+    y = T(g["y"]).cuda()
+    L = y.shape[1]
+    norm = _native.wave_norm(y)
+    assert float(norm[0]) == float(np.abs(g["y"]).max())                  # exact
+    T_pad = _native.padded_frames(_native.num_frames(L, sp))
+    Y = _native.stft(y, norm, sp, T_pad).unsqueeze(1)
+    assert tuple(Y.shape) == g["Y"].shape
+    assert rel_l2(Y.cpu(), g["Y"]) < 1e-5
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", int(g["N"]), 1, 0.5, 0.03)
+    X, nfe = m.engine().pc_sample(Y, sc, noise=_noise(g["noise"]))
+    assert nfe == int(g["nfe"])
+    assert rel_l2(X.cpu(), g["sample"]) < TIGHT
+    x_hat = m.engine().istft(X.squeeze(1), norm, L, sp)
+    assert rel_l2(x_hat.squeeze().cpu(), g["x_hat"]) < TIGHT
+
+
+def test_philox_sampler_matches_oracle_and_is_sharding_invariant():
+    from storm_b200 import _native
+    g = load_golden("sampler")
+    sd = sub_sd(g, "sd/")
+    m = _model("ncsnpp", sd, nf=8)
+    eng = m.engine()
+    Y = T(g["y"]).cuda()
+    B, n = Y.shape[0], Y[0].numel()
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 2, 1, 0.5, 0.03)
+    ids = [7, 11]
+    X, _ = eng.pc_sample(Y, sc, seed=123, utt_ids=ids)
+    nd = 1 + 2 * 2
+    draws = torch.stack([torch.stack([_native.philox_normal(123, u, d, n).reshape(Y.shape[1:]) for u in ids]) for d in range(nd)])
+    z = draws.reshape(nd * B, -1)
+    assert abs(float(z.real.var()) - 0.5) < 0.02 and abs(float(z.imag.var()) - 0.5) < 0.02 and abs(float(z.real.mean())) < 0.01
+    it = iter([d.cpu() for d in draws])
+    xo, _ = O.pc_sample(O.make_score_fn(sd, O.NetCfg(nf=8)), T(g["y"]), O.OUVE(), 2, noise=lambda x: next(it))
+    assert rel_l2(X.cpu(), xo) < TIGHT
+    # each utterance alone (another batch composition / another "rank") gives bit-identical results
+    for b in range(B):
+        Xb, _ = eng.pc_sample(Y[b:b + 1], sc, seed=123, utt_ids=[ids[b]])
+        assert torch.equal(Xb[0], X[b])
+
+
+def test_enhance_batch_api_and_shapes():
+    from storm_b200 import ScoreModel
+    model = ScoreModel(backbone="ncsnpp", sde="ouve", nf=8, init_scale=1.0).cuda()
+    ys = torch.stack([O.synth_utterance(b, 5000) for b in range(3)])
+    out = model.enhance_batch(ys, N=2, seed=5, utt_ids=[0, 1, 2])
+    assert out.shape == ys.shape and out.device == ys.device and torch.isfinite(out).all()
+    one = model.enhance_batch(ys[1:2], N=2, seed=5, utt_ids=[1])
+    assert torch.equal(one[0], out[1])                                   # batch-composition invariance
+    x1 = model.enhance(ys[0:1], N=2)
+    assert x1.shape == (5000,) and x1.device.type == "cpu"
+    x2, nfe, rtf = model.enhance(ys[0:1], N=2, timeit=True)
+    assert nfe == 4 and rtf > 0
+    with pytest.raises(ValueError):
+        model.enhance(ys[0:1], sampler_type="bogus", return_stft=True)
+
+
+def test_full_size_properties():
+    """BASELINE shape (256x256, full-width ncsnpp): finite output, batch-order equivariance (bit-exact),
+    and the score network's exact scaling law in the output layer (d(t) * t is affine in the pyramid)."""
+    from storm_b200 import ncsnpp_spec
+    m = _model("ncsnpp")
+    m.load_state_dict(ncsnpp_spec.random_state_dict(m.cfg, seed=0, init_scale=1.0, bias_std=0.05))
+    gen = torch.Generator().manual_seed(0)
+    x = torch.complex(torch.randn(2, 2, 256, 256, generator=gen), torch.randn(2, 2, 256, 256, generator=gen)).cuda() * 0.3
+    t = torch.tensor([0.9, 0.4], device="cuda")
+    y = m(x, t)
+    assert torch.isfinite(torch.view_as_real(y)).all()
+    y_sw = m(x.flip(0), t.flip(0))
+    assert torch.equal(y_sw.flip(0), y)
