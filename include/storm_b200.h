@@ -97,7 +97,8 @@ int32_t storm_param_entries(const StormHandle* h);
 int storm_param_info(const StormHandle* h, int32_t index, char* name, int32_t name_cap,
                      int64_t shape[4], int32_t* ndim, int64_t* offset_floats);
 
-/* Upload the flat fp32 blob (tensors concatenated in table order, each C-contiguous) and repack it into
+/* Upload the flat fp32 blob (tensor i occupies [offset_i, offset_i + numel_i), C-contiguous; offsets are
+ * 64-float aligned, gaps are ignored; storm_param_floats() is the padded total) and repack it into
  * the kernels' layouts.  `blob` may be a host or a device pointer (is_device).  Replaces
  * load_from_checkpoint + .cuda() (enhancement.py:56-61).  storm_weights_device() exposes the device
  * copy of the raw blob so that rank 0 can ncclBroadcast it. */
@@ -163,9 +164,16 @@ int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B
                   const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed,
                   const uint64_t* utt_ids, int32_t* nfe_out, void* stream);
 
-/* Kernel-launch counter (bench.py's gpu_launches) and per-stage timing hooks. */
+/* Kernel-launch counter (bench.py's gpu_launches). */
 int64_t storm_launch_count(const StormHandle* h);
 int storm_reset_launch_count(StormHandle* h);
+
+/* Live roofline measurement of the dominant kernel class (the implicit-GEMM convolutions): while enabled,
+ * every conv launch is bracketed by CUDA events on its stream.  storm_get_profile synchronises the device
+ * and returns, per engine (0 = tcgen05, 1 = SIMT): launches, summed device milliseconds and summed
+ * algorithmic FLOPs (2 * B*H*W * Cout * sum_seg taps*Cin) since the last storm_set_profile(h, 1). */
+int storm_set_profile(StormHandle* h, int32_t enable);
+int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double flops[2]);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,8 @@ _PROTOS = {
                                 C.POINTER(SpecConfig), C.c_uint64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "storm_launch_count": (C.c_int64, [C.c_void_p]),
     "storm_reset_launch_count": (C.c_int, [C.c_void_p]),
+    "storm_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
+    "storm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 
@@ -249,6 +251,16 @@ class Engine:
 
     def reset_launch_count(self):
         lib().storm_reset_launch_count(self._h)
+
+    def set_profile(self, on: bool):
+        _check(lib().storm_set_profile(self._h, int(on)))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        n = (C.c_int64 * 2)()
+        ms = (C.c_double * 2)()
+        fl = (C.c_double * 2)()
+        _check(lib().storm_get_profile(self._h, n, ms, fl))
+        return {k: dict(launches=int(n[i]), ms=float(ms[i]), flops=float(fl[i])) for i, k in enumerate(("tcgen05", "simt"))}
 
     # ---- sampler ------------------------------------------------------------------------------------------
     def pc_sample(self, Y: torch.Tensor, sc: SamplerConfig, seed: int = 0, utt_ids: Optional[Sequence[int]] = None,

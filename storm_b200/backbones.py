@@ -67,9 +67,15 @@ class NCSNpp(nn.Module):
     def mark_weights_changed(self):
         self._dirty = True
 
-    def flat_weights(self) -> torch.Tensor:
+    def flat_weights(self, table, total: int) -> torch.Tensor:
+        """The engine's blob: tensor ``name`` at its (64-float aligned) offset, zeros in the gaps."""
         sd = self.state_dict()
-        return torch.cat([sd[k].reshape(-1).to(torch.float32) for k, _ in ncsnpp_spec.param_table(self.cfg)])
+        dev = next(iter(sd.values())).device
+        blob = torch.zeros(total, dtype=torch.float32, device=dev)
+        for name, shape, off in table:
+            v = sd[name]
+            blob[off:off + v.numel()] = v.reshape(-1).to(torch.float32)
+        return blob
 
     def engine(self) -> _native.Engine:
         if self._engine is None:
@@ -78,12 +84,12 @@ class NCSNpp(nn.Module):
                                           attn_resolutions=c.attn_resolutions, image_size=c.image_size,
                                           input_channels=c.input_channels, discriminative=c.discriminative,
                                           engine=self._engine_kind)
-            table = [(n, s) for n, s, _ in self._engine.param_table()]
-            if table != ncsnpp_spec.param_table(c):
+            self._table = self._engine.param_table()
+            if [(n, s) for n, s, _ in self._table] != ncsnpp_spec.param_table(c):
                 raise RuntimeError("native parameter table disagrees with the Python specification")
             self._dirty = True
         if self._dirty:
-            self._engine.load_blob(self.flat_weights())
+            self._engine.load_blob(self.flat_weights(self._table, self._engine.param_floats()))
             self._dirty = False
         return self._engine
 

@@ -116,6 +116,10 @@ struct StormHandle {
   int64_t launches = 0;
   bool taps_on = false;
   std::map<std::string, Act> taps;
+  bool profile_on = false;
+  struct ProfRec { cudaEvent_t a, b; int eng; double flops; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_free;
   int device = 0;
 
   bool conditional() const { return !cfg.discriminative; }
@@ -135,8 +139,8 @@ static void add_param(StormHandle* h, const std::string& name, std::initializer_
   int i = 0;
   e.numel = 1;
   for (auto s : shape) { e.shape[i++] = s; e.numel *= s; }
-  e.offset = h->n_floats;
-  h->n_floats += e.numel;
+  e.offset = h->n_floats;                         // every tensor starts 256-byte aligned inside the blob
+  h->n_floats += (e.numel + 63) / 64 * 64;
   h->index[name] = (int)h->table.size();
   h->table.push_back(e);
 }
@@ -384,8 +388,25 @@ struct Fwd {
     return 0;
   }
   int conv(const ConvParams& p) {
-    if (h->cfg.engine == 0 && conv_tc_eligible(p)) { LAUNCH(h, launch_conv_tc(p, st)); }
+    const bool tc = h->cfg.engine == 0 && conv_tc_eligible(p);
+    StormHandle::ProfRec rec{};
+    if (h->profile_on) {
+      for (cudaEvent_t* e : {&rec.a, &rec.b}) {
+        if (!h->ev_free.empty()) { *e = h->ev_free.back(); h->ev_free.pop_back(); }
+        else STORM_CUDA_TRY(cudaEventCreate(e));
+      }
+      double k = 0;
+      for (int i = 0; i < p.nseg; ++i) k += (double)p.seg[i].taps * (p.seg[i].C0 + p.seg[i].C1);
+      rec.flops = 2.0 * (double)p.B * p.H * p.W * p.Cout * k;
+      rec.eng = tc ? 0 : 1;
+      STORM_CUDA_TRY(cudaEventRecord(rec.a, st));
+    }
+    if (tc) { LAUNCH(h, launch_conv_tc(p, st)); }
     else { LAUNCH(h, launch_conv_simt(p, st)); }
+    if (h->profile_on) {
+      STORM_CUDA_TRY(cudaEventRecord(rec.b, st));
+      h->prof.push_back(rec);
+    }
     return 0;
   }
   int tap(const std::string& name, const Act& a) {
@@ -824,6 +845,8 @@ int storm_destroy(StormHandle* h) {
   cudaDeviceSynchronize();
   free_packed(h);
   for (auto& kv : h->taps) cudaFree(kv.second.p);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->ev_free) cudaEventDestroy(e);
   h->pool.destroy();
   cudaFree(h->raw);
   delete h;
@@ -940,6 +963,25 @@ int storm_ode_drift(StormHandle* h, const float* X, const float* Y, float t, flo
   const double g = ouve_diffusion(*sc, t);
   LAUNCH(h, launch_ode_drift(X, Y, d, drift, sc->theta, (float)(0.5 * g * g), (int64_t)B * n, st));
   h->pool.put(d); h->pool.put(tdev);
+  return 0;
+}
+
+int storm_set_profile(StormHandle* h, int32_t enable) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  for (auto& r : h->prof) { h->ev_free.push_back(r.a); h->ev_free.push_back(r.b); }
+  h->prof.clear();
+  h->profile_on = enable != 0;
+  return 0;
+}
+int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double flops[2]) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  STORM_CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < 2; ++i) { launches[i] = 0; ms[i] = 0; flops[i] = 0; }
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    STORM_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    launches[r.eng] += 1; ms[r.eng] += t; flops[r.eng] += r.flops;
+  }
   return 0;
 }
 
