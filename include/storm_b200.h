@@ -175,6 +175,16 @@ int storm_reset_launch_count(StormHandle* h);
 int storm_set_profile(StormHandle* h, int32_t enable);
 int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double flops[2]);
 
+/* Test hook: run ONE fused convolution through the chosen kernel (engine 0 = tcgen05, 1 = SIMT):
+ *   out = out_scale * ( conv_taps( act(cat[x0, x1]) ; w ) [+ conv_1x1(x2 ; w2)] + bias [+ res] )
+ * x*: NHWC fp32 device tensors [B][H][W][C*]; ss: [B][C0+C1][2] scale/shift or NULL; w: OIHW fp32
+ * [Cout][C0+C1][taps] device; w2: [Cout][C2] or NULL; out NHWC.  Returns STORM_E_INVALID when the shape
+ * is not eligible for the requested kernel. */
+int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                     int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout,
+                     const float* bias, const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

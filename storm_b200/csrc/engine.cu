@@ -985,6 +985,46 @@ int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double 
   return 0;
 }
 
+int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                     int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
+                     const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  if (!x0 || !w || !out) return fail(STORM_E_INVALID, "storm_debug_conv: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<void*> owned;
+  ConvParams p{};
+  p.nseg = x2 ? 2 : 1;
+  p.seg[0].src0 = x0; p.seg[0].src1 = x1; p.seg[0].C0 = C0; p.seg[0].C1 = x1 ? C1 : 0; p.seg[0].ss = ss; p.seg[0].silu = silu;
+  p.seg[0].taps = taps;
+  if (x2) { p.seg[1].src0 = x2; p.seg[1].C0 = C2; p.seg[1].taps = 1; }
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.bias = bias; p.res = res; p.out_scale = out_scale; p.out = out;
+  int rc = 0;
+  const int Cin = C0 + (x1 ? C1 : 0);
+  if (engine == 0) {
+    void *t0 = nullptr, *t1 = nullptr;
+    rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st);
+    if (rc == 0 && x2) rc = tc_pack_weights(w2, Cout, C2, 1, &t1, &owned, st);
+    p.seg[0].wtc = t0; p.seg[1].wtc = t1;
+    if (rc == 0 && !conv_tc_eligible(p)) rc = fail(STORM_E_INVALID, "storm_debug_conv: shape not eligible for the tcgen05 kernel");
+    if (rc == 0) rc = launch_conv_tc(p, st);
+  } else {
+    float *s0 = nullptr, *s1 = nullptr;
+    if (cudaMalloc((void**)&s0, (size_t)taps * Cin * Cout * 4) != cudaSuccess) return fail(STORM_E_NOMEM, "debug conv alloc");
+    owned.push_back(s0);
+    rc = launch_pack_conv_simt(w, s0, Cout, Cin, taps, st);
+    if (rc == 0 && x2) {
+      if (cudaMalloc((void**)&s1, (size_t)C2 * Cout * 4) != cudaSuccess) return fail(STORM_E_NOMEM, "debug conv alloc");
+      owned.push_back(s1);
+      rc = launch_pack_conv_simt(w2, s1, Cout, C2, 1, st);
+    }
+    p.seg[0].w = s0; p.seg[1].w = s1;
+    if (rc == 0) rc = launch_conv_simt(p, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (void* q : owned) cudaFree(q);
+  if (rc == 0 && e != cudaSuccess) return fail(STORM_E_CUDA, std::string("storm_debug_conv: ") + cudaGetErrorString(e));
+  return rc;
+}
+
 int32_t storm_num_frames(int32_t L, const StormSpecConfig* sp) { return sp && sp->hop_length > 0 ? 1 + L / sp->hop_length : 0; }
 int32_t storm_padded_frames(int32_t frames) { return (frames + 63) / 64 * 64; }
 
