@@ -69,13 +69,19 @@ struct ConvParams {
   const float* res;        // residual NHWC [B][H][W][Cout] or null
   float out_scale;
   float* out;              // NHWC [B][H][W][Cout]
+  double* stats_out;       // optional GroupNorm partial sums of `out`: [B][stats_chunks][Cout][2] (tcgen05 mode P only)
+  int stats_chunks;
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);
 bool conv_tc_eligible(const ConvParams& p);
+// number of GroupNorm partial-sum chunks the tcgen05 kernel would emit for this launch (0 = cannot emit)
+int conv_tc_stats_chunks(const ConvParams& p);
 int launch_conv_tc(const ConvParams& p, cudaStream_t st);
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// fast variant for the tensor-core producers (ex2.approx + approximate division, ~1e-6 relative)
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvParams p, Tc
               }
               if (s.silu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
               }
               float r[8];
               hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
@@ -430,22 +430,319 @@ bool choose_cfg(const ConvParams& p, TcCfg& c) {
   return true;
 }
 
+
+// =====================================================================================================
+// Mode P ("pixels as N"): D[cout, pixel].  A operand = weight image (M = 128 output channels),
+// B operand = halo tile of N = 8*R pixels (R rows x 8 columns; R = 32 or 16), both K-major / no swizzle.
+// Shared-memory operand traffic per MMA is 4 KB (A) + 8 KB (B) per 128 cycles for every Cout (the
+// "cout as N" mode above degenerates to 128 B/clk when Cout = 128), the epilogue's lanes are output
+// channels so global stores / residual loads are coalesced, bias / temb are per-thread scalars, and the
+// GroupNorm partial sums of the OUTPUT tensor fall out of the epilogue for free (each thread owns one
+// channel of the tile).  CTA = NPT pixel tiles x NMB 128-channel blocks, NPT*NMB*N <= 512 TMEM columns.
+// Warps 0-7: activation producers then epilogue; warp 8: weight producer; warp 9: TMEM alloc + MMA issue.
+// =====================================================================================================
+constexpr int P_THREADS = 320;
+constexpr int P_PRODUCERS = 256;
+
+struct TcpCfg {
+  int rows;            // R: pixel-tile rows (32 or 16)
+  int ncol;            // N = 8 * R accumulator columns per (pixel tile, M block)
+  int npt, nmb;        // pixel tiles / 128-channel blocks per CTA
+  int msplit;          // grid.y = Cout / (128 * nmb)
+  int hx, hy, np;      // halo geometry
+  int sa, sw;
+  int a_half, a_stage, w_half, w_stage;
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t w_base = a_base + c.sa * c.a_stage;
+  const uint32_t bar_base = w_base + c.sw * c.w_stage;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
+  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };
+  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 2 * c.sw);
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / c.tiles_x) * c.rows;
+  const int tx0 = (tile % c.tiles_x) * 8 * c.npt;
+  const int m_lo = blockIdx.y * 128 * c.nmb;       // first output channel of this CTA
+  const int b = blockIdx.z;
+
+  if (tid == 0) {
+    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), P_PRODUCERS); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < 8) {
+    // =================================== activation producers ==========================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int si = 0; si < p.nseg; ++si) {
+      const ConvSeg s = p.seg[si];
+      const int C = s.C0 + s.C1;
+      const bool full_halo = s.taps == 9;
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        mbar_wait(a_empty(stage), phase ^ 1);
+        const uint32_t st_base = a_base + stage * c.a_stage;
+#pragma unroll 1
+        for (int kh = 0; kh < 2; ++kh) {
+          const int cc = c0 + kh * 8;
+          const float* src;
+          int Cs, cl;
+          if (cc < s.C0) { src = s.src0; Cs = s.C0; cl = cc; } else { src = s.src1; Cs = s.C1; cl = cc - s.C0; }
+          float sc[8], sh[8];
+          if (s.ss) {
+            const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + cc) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 v = __ldg(sp + j);
+              sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+            }
+          }
+          for (int ps = tid; ps < c.np; ps += P_PRODUCERS) {
+            const int hy = ps / c.hx, hxx = ps - hy * c.hx;
+            if (!full_halo && (hy == 0 || hy == c.hy - 1 || hxx == 0 || hxx == c.hx - 1)) continue;
+            const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
+              const float4* gp = reinterpret_cast<const float4*>(src + (((size_t)b * p.H + y) * p.W + x) * Cs + cl);
+              float4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
+              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              if (s.ss) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+              }
+              if (s.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+              }
+              float r[8];
+              hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
+              hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
+              hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
+              hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
+              float d0, d1;
+              lo.x = pack_bf16x2(r[0], r[1], d0, d1);
+              lo.y = pack_bf16x2(r[2], r[3], d0, d1);
+              lo.z = pack_bf16x2(r[4], r[5], d0, d1);
+              lo.w = pack_bf16x2(r[6], r[7], d0, d1);
+            }
+            const uint32_t off = st_base + (uint32_t)(kh * c.np + ps) * 16u;
+            st_shared_v4(off, hi);
+            st_shared_v4(off + c.a_half, lo);
+          }
+        }
+        fence_async_shared();
+        mbar_arrive(a_full(stage));
+        if (++stage == c.sa) { stage = 0; phase ^= 1; }
+      }
+    }
+    // =================================== epilogue ======================================================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which half of the work units
+    const int nacc = c.npt * c.nmb;
+    const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
+    const int nunits = nacc * units_per_acc;
+    const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
+    double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
+    for (int u = grp; u < nunits; u += 2) {
+      const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
+      const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
+      const int cout = m_lo + mb * 128 + q * 32 + lane;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
+      float add = 0.f;
+      if (p.bias) add += __ldg(p.bias + cout);
+      if (tembp) add += __ldg(tembp + cout);
+      float fs = 0.f, fq = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int y = ty0 + g32 * 4 + (jj >> 3);
+        const int x = tx0 + 8 * pt + (jj & 7);
+        if (y < p.H && x < p.W) {
+          const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
+          float v = __uint_as_float(r[jj]) + add;
+          if (p.res) v += __ldg(p.res + o);
+          v *= p.out_scale;
+          p.out[o] = v;
+          fs += v;
+          fq = fmaf(v, v, fq);
+        }
+      }
+      s_sum[mb] += (double)fs;
+      s_sq[mb] += (double)fq;
+    }
+    if (p.stats_out) {
+      // chunk index = (tile, grp): every (chunk, channel) slot is written exactly once per launch
+      const int chunk = tile * 2 + grp;
+      for (int mb = 0; mb < c.nmb; ++mb) {
+        const int cout = m_lo + mb * 128 + q * 32 + lane;
+        double* o = p.stats_out + (((size_t)b * p.stats_chunks + chunk) * p.Cout + cout) * 2;
+        o[0] = s_sum[mb];
+        o[1] = s_sq[mb];
+      }
+    }
+  } else if (warp == 8) {
+    // =================================== weight producer ================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int si = 0; si < p.nseg; ++si) {
+        const ConvSeg s = p.seg[si];
+        const int nq = ((s.C0 + s.C1) >> 4) * s.taps;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32;
+        const size_t q_stride = (size_t)64 * p.Cout;
+        for (int qq = 0; qq < nq; ++qq) {
+          mbar_wait(w_empty(stage), phase ^ 1);
+          const uint32_t dst = w_base + stage * c.w_stage;
+          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
+          bulk_g2s(dst, base + qq * q_stride, (uint32_t)c.w_half, w_full(stage));
+          bulk_g2s(dst + c.w_half, base + qq * q_stride + (size_t)32 * p.Cout, (uint32_t)c.w_half, w_full(stage));
+          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =================================== MMA issuer =====================================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(c.ncol);
+      const uint32_t lbo_p = (uint32_t)c.np * 16u, sbo_p = (uint32_t)c.hx * 16u;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      bool first = true;
+      for (int si = 0; si < p.nseg; ++si) {
+        const ConvSeg s = p.seg[si];
+        const int nch = (s.C0 + s.C1) >> 4;
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(a_full(sa), pa);
+          tc_fence_after();
+          const uint32_t a_st = a_base + sa * c.a_stage;
+          for (int tap = 0; tap < s.taps; ++tap) {
+            const int dy = s.taps == 9 ? tap / 3 : 1, dx = s.taps == 9 ? tap - 3 * (tap / 3) : 1;
+            mbar_wait(w_full(sw), pw);
+            tc_fence_after();
+            const uint32_t w_st = w_base + sw * c.w_stage;
+            for (int pt = 0; pt < c.npt; ++pt) {
+              const uint32_t px_addr = a_st + (uint32_t)(dy * c.hx + dx + 8 * pt) * 16u;
+              const uint64_t p_hi = make_desc(px_addr, lbo_p, sbo_p);
+              const uint64_t p_lo = make_desc(px_addr + c.a_half, lbo_p, sbo_p);
+              for (int mb = 0; mb < c.nmb; ++mb) {
+                const uint64_t w_hi = make_desc(w_st + mb * 4096, 128, 256);
+                const uint64_t w_lo = make_desc(w_st + c.w_half + mb * 4096, 128, 256);
+                const uint32_t d = tmem_base + (uint32_t)((pt * c.nmb + mb) * c.ncol);
+                umma_bf16(d, w_hi, p_hi, idesc, first ? 0u : 1u);
+                umma_bf16(d, w_hi, p_lo, idesc, 1u);
+                umma_bf16(d, w_lo, p_hi, idesc, 1u);
+              }
+            }
+            first = false;
+            umma_commit(w_empty(sw));
+            if (++sw == c.sw) { sw = 0; pw ^= 1; }
+          }
+          umma_commit(a_empty(sa));
+          if (++sa == c.sa) { sa = 0; pa ^= 1; }
+        }
+      }
+      umma_commit(acc_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
+  if (p.Cout % 128 != 0 || p.Cout < 128 || p.Cout > 256) return false;
+  for (int i = 0; i < p.nseg; ++i) {
+    const ConvSeg& s = p.seg[i];
+    if (!s.wtc || s.C0 % 16 != 0 || s.C1 % 16 != 0 || s.C0 < 16 || (s.taps != 9 && s.taps != 1)) return false;
+  }
+  const int nblk = p.Cout / 128;
+  // candidates (rows, pixel tiles, M blocks per CTA), largest CTA tile first; take the first that fills the
+  // chip, else the one with the most CTAs
+  struct Cand { int rows, npt, nmb; };
+  const Cand cands1[] = {{32, 2, 1}, {32, 1, 1}, {16, 2, 1}, {16, 1, 1}};              // Cout = 128
+  const Cand cands2[] = {{32, 1, 2}, {16, 2, 2}, {32, 1, 1}, {16, 1, 2}, {16, 1, 1}};  // Cout = 256
+  const Cand* cands = nblk == 1 ? cands1 : cands2;
+  const int ncand = nblk == 1 ? 4 : 5;
+  int best = -1;
+  long best_ctas = -1;
+  for (int i = 0; i < ncand; ++i) {
+    const Cand& k = cands[i];
+    if (k.npt * k.nmb * 8 * k.rows > 512) continue;
+    if (k.npt == 2 && p.W <= 8) continue;
+    if (k.rows == 32 && p.H <= 16) continue;
+    const long ctas = (long)ceil_div(p.H, k.rows) * ceil_div(p.W, 8 * k.npt) * (nblk / k.nmb) * p.B;
+    if (ctas >= 132) { best = i; break; }
+    if (ctas > best_ctas) { best_ctas = ctas; best = i; }
+  }
+  if (best < 0) return false;
+  const Cand& k = cands[best];
+  c.rows = k.rows; c.npt = k.npt; c.nmb = k.nmb;
+  c.ncol = 8 * k.rows;
+  c.msplit = nblk / k.nmb;
+  c.hx = 8 * k.npt + 2; c.hy = k.rows + 2; c.np = c.hx * c.hy;
+  c.a_half = 2 * c.np * 16; c.a_stage = 2 * c.a_half;
+  c.w_half = 4096 * k.nmb; c.w_stage = 2 * c.w_half;
+  c.sa = c.a_stage <= 24 * 1024 ? 3 : 2;
+  int sw = (SMEM_BUDGET - c.sa * c.a_stage - 256) / c.w_stage;
+  c.sw = sw > 8 ? 8 : sw;
+  if (c.sw < 2) return false;
+  c.tiles_x = ceil_div(p.W, 8 * k.npt);
+  c.tiles_y = ceil_div(p.H, k.rows);
+  return true;
+}
+
 }  // namespace
 
 bool conv_tc_eligible(const ConvParams& p) {
+  TcpCfg cp;
+  if (choose_cfg_p(p, cp)) return true;
   TcCfg c;
   return choose_cfg(p, c);
 }
 
+int conv_tc_stats_chunks(const ConvParams& p) {
+  TcpCfg cp;
+  if (!choose_cfg_p(p, cp)) return 0;
+  return 2 * cp.tiles_x * cp.tiles_y;
+}
+
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
-  TcCfg c;
-  if (!choose_cfg(p, c)) return fail(-1, "conv_tc: shape not eligible");
-  const int smem = c.sa * c.a_stage + c.sw * c.w_stage + 8 * (2 * c.sa + 2 * c.sw + 1) + 16;
   static bool attr = false;
   if (!attr) {
     STORM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    STORM_CUDA_TRY(cudaFuncSetAttribute(conv_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     attr = true;
   }
+  TcpCfg cp;
+  if (choose_cfg_p(p, cp)) {
+    if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+    const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
+    dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
+    conv_tcp_kernel<<<grid, P_THREADS, smem, st>>>(p, cp);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
+  if (p.stats_out) return fail(-1, "conv_tc: GroupNorm partial sums are only emitted by mode P");
+  TcCfg c;
+  if (!choose_cfg(p, c)) return fail(-1, "conv_tc: shape not eligible");
+  const int smem = c.sa * c.a_stage + c.sw * c.w_stage + 8 * (2 * c.sa + 2 * c.sw + 1) + 16;
   dim3 grid(c.tiles_x * ceil_div(p.H, 16), c.nsplit, p.B);
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, c);
   STORM_LAUNCH_CHECK();

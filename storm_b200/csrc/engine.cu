@@ -387,8 +387,20 @@ struct Fwd {
     LAUNCH(h, launch_gn_finalize(a0, a1, g, b, *ss, st));
     return 0;
   }
-  int conv(const ConvParams& p) {
+  int conv(ConvParams& p, Act* out_act = nullptr) {
     const bool tc = h->cfg.engine == 0 && conv_tc_eligible(p);
+    if (tc && out_act && !h->taps_on) {
+      // the tcgen05 epilogue emits the GroupNorm partial sums of its output for free
+      const int nch = conv_tc_stats_chunks(p);
+      if (nch > 0) {
+        void* q;
+        STORM_TRY(h->pool.get((size_t)B * nch * p.Cout * 2 * sizeof(double), &q));
+        out_act->part = (double*)q;
+        out_act->nchunk = nch;
+        p.stats_out = out_act->part;
+        p.stats_chunks = nch;
+      }
+    }
     StormHandle::ProfRec rec{};
     if (h->profile_on) {
       for (cudaEvent_t* e : {&rec.a, &rec.b}) {
@@ -407,6 +419,7 @@ struct Fwd {
       STORM_CUDA_TRY(cudaEventRecord(rec.b, st));
       h->prof.push_back(rec);
     }
+    if (p.stats_out) out_act->part_valid = true;
     return 0;
   }
   int tap(const std::string& name, const Act& a) {
@@ -455,7 +468,7 @@ struct Fwd {
       p.temb = tembias ? tembias + r.temb_off : nullptr;
       p.temb_stride = h->dense_total;
       p.res = nullptr; p.out_scale = 1.0f; p.out = h1.p;
-      STORM_TRY(conv(p));
+      STORM_TRY(conv(p, &h1));
     }
     h->pool.put(ss0);
     if (resamp) release(hr);
@@ -481,7 +494,7 @@ struct Fwd {
       p.bias = r.b12; p.temb = nullptr; p.temb_stride = 0;
       p.out_scale = 0.70710678118654752f;   // (x + h) / sqrt(2), layerspp.py:274
       p.out = out.p;
-      STORM_TRY(conv(p));
+      STORM_TRY(conv(p, &out));
     }
     h->pool.put(ss1);
     release(h1);
@@ -517,7 +530,7 @@ struct Fwd {
       ConvSeg& s = p.seg[0];
       s.src0 = o.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; s.taps = 1; s.w = a.w[3]; s.wtc = a.tc[3];
       p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[3]; p.res = x.p; p.out_scale = 0.70710678118654752f; p.out = out.p;
-      STORM_TRY(conv(p));
+      STORM_TRY(conv(p, &out));
     }
     release(o);
     return 0;
