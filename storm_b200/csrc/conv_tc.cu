@@ -489,42 +489,87 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
 
   if (warp < 8) {
     // =================================== activation producers ==========================================
+    // Each thread owns up to 3 halo pixels per stage and handles all 16 channels (64 contiguous bytes) of each.
+    // All global loads of a stage are issued before any is consumed (memory-level parallelism), and the next
+    // chunk's lines are prefetched into L2 while this one is converted.
     int stage = 0;
     uint32_t phase = 0;
+    constexpr int MAXU = 3;                                // ceil(612 / 256)
+    int upix[MAXU];                                        // global pixel index (b, y, x) or -1 (outside / unused)
+    uint32_t uoff[MAXU];
+    bool uinterior[MAXU];
+#pragma unroll
+    for (int i = 0; i < MAXU; ++i) {
+      const int ps = tid + i * P_PRODUCERS;
+      upix[i] = -2;                                        // -2: slot not present
+      uoff[i] = (uint32_t)ps * 16u;
+      uinterior[i] = false;
+      if (ps < c.np) {
+        const int hy = ps / c.hx, hxx = ps - hy * c.hx;
+        const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
+        uinterior[i] = !(hy == 0 || hy == c.hy - 1 || hxx == 0 || hxx == c.hx - 1);
+        upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
+      }
+    }
     for (int si = 0; si < p.nseg; ++si) {
       const ConvSeg s = p.seg[si];
       const int C = s.C0 + s.C1;
       const bool full_halo = s.taps == 9;
       for (int c0 = 0; c0 < C; c0 += 16) {
+        const float* src;
+        int Cs, cl;
+        if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
+        // ---- issue all loads of this stage
+        float4 raw[MAXU][4];
+#pragma unroll
+        for (int i = 0; i < MAXU; ++i) {
+          if (upix[i] >= 0 && (full_halo || uinterior[i])) {
+            const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix[i] * Cs + cl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
+          }
+        }
+        // ---- L2 prefetch of the next chunk (same segment) or the first chunk of the next segment
+        {
+          const float* nsrc = nullptr;
+          int nCs = 0, ncl = 0;
+          bool nfull = full_halo;
+          const int n0 = c0 + 16;
+          if (n0 < C) {
+            if (n0 < s.C0) { nsrc = s.src0; nCs = s.C0; ncl = n0; } else { nsrc = s.src1; nCs = s.C1; ncl = n0 - s.C0; }
+          } else if (si + 1 < p.nseg) {
+            nsrc = p.seg[si + 1].src0; nCs = p.seg[si + 1].C0; ncl = 0; nfull = p.seg[si + 1].taps == 9;
+          }
+          if (nsrc) {
+#pragma unroll
+            for (int i = 0; i < MAXU; ++i)
+              if (upix[i] >= 0 && (nfull || uinterior[i]))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
+          }
+        }
+        float sc[16], sh[16];
+        if (s.ss) {
+          const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + c0) * 2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = __ldg(sp + j);
+            sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+          }
+        }
         mbar_wait(a_empty(stage), phase ^ 1);
         const uint32_t st_base = a_base + stage * c.a_stage;
-#pragma unroll 1
-        for (int kh = 0; kh < 2; ++kh) {
-          const int cc = c0 + kh * 8;
-          const float* src;
-          int Cs, cl;
-          if (cc < s.C0) { src = s.src0; Cs = s.C0; cl = cc; } else { src = s.src1; Cs = s.C1; cl = cc - s.C0; }
-          float sc[8], sh[8];
-          if (s.ss) {
-            const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + cc) * 2);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 v = __ldg(sp + j);
-              sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
-            }
-          }
-          for (int ps = tid; ps < c.np; ps += P_PRODUCERS) {
-            const int hy = ps / c.hx, hxx = ps - hy * c.hx;
-            if (!full_halo && (hy == 0 || hy == c.hy - 1 || hxx == 0 || hxx == c.hx - 1)) continue;
-            const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
+        for (int i = 0; i < MAXU; ++i) {
+          if (upix[i] == -2 || !(full_halo || uinterior[i])) continue;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
             uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-            if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
-              const float4* gp = reinterpret_cast<const float4*>(src + (((size_t)b * p.H + y) * p.W + x) * Cs + cl);
-              float4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
+            if (upix[i] >= 0) {
+              const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
               float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
               if (s.ss) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[kh * 8 + j], sh[kh * 8 + j]);
               }
               if (s.silu) {
 #pragma unroll
@@ -541,7 +586,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
               lo.z = pack_bf16x2(r[4], r[5], d0, d1);
               lo.w = pack_bf16x2(r[6], r[7], d0, d1);
             }
-            const uint32_t off = st_base + (uint32_t)(kh * c.np + ps) * 16u;
+            const uint32_t off = st_base + (uint32_t)(kh * c.np) * 16u + uoff[i];
             st_shared_v4(off, hi);
             st_shared_v4(off + c.a_half, lo);
           }
@@ -570,6 +615,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
       if (p.bias) add += __ldg(p.bias + cout);
       if (tembp) add += __ldg(tembp + cout);
       float fs = 0.f, fq = 0.f;
+      float rv[32];
+      if (p.res) {     // issue every residual load of the unit before consuming any
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int y = ty0 + g32 * 4 + (jj >> 3);
+          const int x = tx0 + 8 * pt + (jj & 7);
+          rv[jj] = (y < p.H && x < p.W) ? __ldg(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout) : 0.f;
+        }
+      }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
         const int y = ty0 + g32 * 4 + (jj >> 3);
@@ -577,7 +631,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
         if (y < p.H && x < p.W) {
           const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
           float v = __uint_as_float(r[jj]) + add;
-          if (p.res) v += __ldg(p.res + o);
+          if (p.res) v += rv[jj];
           v *= p.out_scale;
           p.out[o] = v;
           fs += v;
