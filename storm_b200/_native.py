@@ -77,6 +77,9 @@ _PROTOS = {
     "storm_debug_conv": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "storm_debug_conv_timed": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
+                                         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "storm_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "storm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -358,8 +361,9 @@ def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad:
     return spec
 
 
-def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=None, bias=None, res=None, out_scale=1.0):
-    """Test hook around storm_debug_conv: NHWC fp32 CUDA tensors, w OIHW [Cout, Cin, k, k]."""
+def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=None, bias=None, res=None, out_scale=1.0, timed=False):
+    """Test hook around storm_debug_conv: NHWC fp32 CUDA tensors, w OIHW [Cout, Cin, k, k].
+    timed=True -> (out, ms, counters) from storm_debug_conv_timed."""
     x0 = _cf(x0, "x0")
     B, H, W, C0 = x0.shape
     Cout = w.shape[0]
@@ -367,6 +371,13 @@ def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=Non
     out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x0.device)
     cont = lambda t: None if t is None else _cf(t, "arg")   # noqa: E731
     x1, ss, x2, w2, bias, res, w = cont(x1), cont(ss), cont(x2), cont(w2), cont(bias), cont(res), cont(w)
+    if timed:
+        dbg = torch.zeros(8, dtype=torch.int64, device=x0.device)
+        ms = C.c_float()
+        _check(lib().storm_debug_conv_timed(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu),
+                                            taps, w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias),
+                                            _ptr(res), float(out_scale), out.data_ptr(), B, H, W, dbg.data_ptr(), C.byref(ms), _stream()))
+        return out, float(ms.value), dbg.cpu().tolist()
     _check(lib().storm_debug_conv(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu), taps,
                                   w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias), _ptr(res),
                                   float(out_scale), out.data_ptr(), B, H, W, _stream()))

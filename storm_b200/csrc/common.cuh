@@ -71,6 +71,7 @@ struct ConvParams {
   float* out;              // NHWC [B][H][W][Cout]
   double* stats_out;       // optional GroupNorm partial sums of `out`: [B][stats_chunks][Cout][2] (tcgen05 mode P only)
   int stats_chunks;
+  long long* dbg;          // optional [8] cycle counters written by CTA 0 (tools/conv_timeline.py)
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);

@@ -24,6 +24,8 @@
 //   warp 5 TMEM allocator + single-thread MMA issuer.  One CTA per SM (smem ~150 KB, all 512 TMEM columns).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 
 namespace storm {
@@ -453,9 +455,84 @@ struct TcpCfg {
   int sa, sw;
   int a_half, a_stage, w_half, w_stage;
   int tiles_x, tiles_y;
+  int per_sm;          // CTAs per SM this config is built for (1 or 2)
 };
 
-__global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+// Single-thread MMA issue loop of mode P.  The tensor core needs one tcgen05.mma every N/2 cycles, so the
+// loop is kept lean: descriptor high words are per-CTA constants, the low words are (address >> 4) sums, and
+// the (pixel tile, M block, hi/lo) combinations are unrolled at compile time.
+template <int NPT, int NMB>
+__device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
+                                           uint32_t tmem_base) {
+  const uint32_t idesc = make_idesc(c.ncol);
+  const uint64_t pd_const = make_desc(0, (uint32_t)c.np * 16u, (uint32_t)c.hx * 16u);   // pixel operand (B)
+  const uint64_t wd_const = make_desc(0, 128, 256);                                      // weight operand (A)
+  const uint32_t a_half16 = (uint32_t)c.a_half >> 4, w_half16 = (uint32_t)c.w_half >> 4;
+  const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
+  const uint32_t a_base16 = a_base >> 4, w_base16 = w_base >> 4;
+  const uint32_t ncol = (uint32_t)c.ncol;
+  const int sa_n = c.sa, sw_n = c.sw;
+  int sa = 0, sw = 0;
+  uint32_t pa = 0, pw = 0;
+  uint32_t acc = 0;
+  const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long t_wa = 0, t_ww = 0, t_start = dbg ? clock64() : 0;
+  for (int si = 0; si < p.nseg; ++si) {
+    const int nch = (p.seg[si].C0 + p.seg[si].C1) >> 4;
+    const bool k3 = p.seg[si].taps == 9;
+    for (int ch = 0; ch < nch; ++ch) {
+      long long t0 = dbg ? clock64() : 0;
+      mbar_wait(bar_base + 8u * sa, pa);                                   // a_full
+      if (dbg) t_wa += clock64() - t0;
+      tc_fence_after();
+      const uint32_t a16 = a_base16 + sa * a_stage16;
+      const int ntap = k3 ? 9 : 1;
+      uint32_t toff = k3 ? 0u : (uint32_t)(c.hx + 1);                      // (dy * hx + dx), dy = dx = 1 for 1x1
+      int dx = 0;
+      for (int tap = 0; tap < ntap; ++tap) {
+        long long t1 = dbg ? clock64() : 0;
+        mbar_wait(bar_base + 8u * (2 * sa_n + sw), pw);                    // w_full
+        if (dbg) t_ww += clock64() - t1;
+        tc_fence_after();
+        const uint32_t w16 = w_base16 + sw * w_stage16;
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) {
+          const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff + 8u * pt);
+          const uint64_t p_lo = p_hi + a_half16;
+#pragma unroll
+          for (int mb = 0; mb < NMB; ++mb) {
+            const uint64_t w_hi = wd_const + (uint64_t)(w16 + 256u * mb);   // 4096 B per 128-channel block
+            const uint64_t w_lo = w_hi + w_half16;
+            const uint32_t d = tmem_base + (uint32_t)(pt * NMB + mb) * ncol;
+            umma_bf16(d, w_hi, p_hi, idesc, acc);
+            umma_bf16(d, w_hi, p_lo, idesc, 1u);
+            umma_bf16(d, w_lo, p_hi, idesc, 1u);
+          }
+        }
+        acc = 1u;
+        umma_commit(bar_base + 8u * (2 * sa_n + sw_n + sw));               // w_empty: frees the weight stage
+        if (++sw == sw_n) { sw = 0; pw ^= 1; }
+        if (++dx == 3) { dx = 0; toff += (uint32_t)c.hx - 2u; } else { toff += 1u; }
+      }
+      umma_commit(bar_base + 8u * (sa_n + sa));                            // a_empty: frees the activation stage
+      if (++sa == sa_n) { sa = 0; pa ^= 1; }
+    }
+  }
+  umma_commit(bar_base + 8u * (2 * sa_n + 2 * sw_n));                      // acc_full
+  if (dbg) {
+    p.dbg[0] = clock64() - t_start;   // issue loop duration
+    p.dbg[1] = t_wa;                  // cycles waiting for activation stages
+    p.dbg[2] = t_ww;                  // cycles waiting for weight stages
+    mbar_wait(bar_base + 8u * (2 * sa_n + 2 * sw_n), 0);
+    p.dbg[3] = clock64() - t_start;   // until the last MMA retired
+  }
+}
+
+// MAXU = halo pixels per producer thread (ceil(np / 256)); MINB = CTAs per SM.  <3,1>: one CTA per SM owning all
+// 512 TMEM columns; <2,2>: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
+// global stores) overlaps the other's MMA main loop on the shared tensor pipe.
+template <int MAXU, int MINB>
+__global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = smem_u32(smem);
@@ -480,7 +557,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  constexpr uint32_t TMEM_COLS = MINB == 1 ? 512 : 256;
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -494,7 +572,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
     // chunk's lines are prefetched into L2 while this one is converted.
     int stage = 0;
     uint32_t phase = 0;
-    constexpr int MAXU = 3;                                // ceil(612 / 256)
     int upix[MAXU];                                        // global pixel index (b, y, x) or -1 (outside / unused)
     uint32_t uoff[MAXU];
     bool uinterior[MAXU];
@@ -597,7 +674,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
       }
     }
     // =================================== epilogue ======================================================
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    const long long t_e0 = dbg ? clock64() : 0;
     mbar_wait(acc_full, 0);
+    const long long t_e1 = dbg ? clock64() : 0;
     tc_fence_after();
     const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which half of the work units
     const int nacc = c.npt * c.nmb;
@@ -651,6 +731,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
         o[1] = s_sq[mb];
       }
     }
+    if (dbg) {
+      p.dbg[4] = t_e1 - t_e0;          // producer warp 0 idle between its last stage and the accumulators being ready
+      p.dbg[5] = clock64() - t_e1;     // epilogue duration (thread 0)
+    }
   } else if (warp == 8) {
     // =================================== weight producer ================================================
     if (lane == 0) {
@@ -674,51 +758,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tcp_kernel(ConvParams p, Tc
   } else {
     // =================================== MMA issuer =====================================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(c.ncol);
-      const uint32_t lbo_p = (uint32_t)c.np * 16u, sbo_p = (uint32_t)c.hx * 16u;
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0;
-      bool first = true;
-      for (int si = 0; si < p.nseg; ++si) {
-        const ConvSeg s = p.seg[si];
-        const int nch = (s.C0 + s.C1) >> 4;
-        for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(a_full(sa), pa);
-          tc_fence_after();
-          const uint32_t a_st = a_base + sa * c.a_stage;
-          for (int tap = 0; tap < s.taps; ++tap) {
-            const int dy = s.taps == 9 ? tap / 3 : 1, dx = s.taps == 9 ? tap - 3 * (tap / 3) : 1;
-            mbar_wait(w_full(sw), pw);
-            tc_fence_after();
-            const uint32_t w_st = w_base + sw * c.w_stage;
-            for (int pt = 0; pt < c.npt; ++pt) {
-              const uint32_t px_addr = a_st + (uint32_t)(dy * c.hx + dx + 8 * pt) * 16u;
-              const uint64_t p_hi = make_desc(px_addr, lbo_p, sbo_p);
-              const uint64_t p_lo = make_desc(px_addr + c.a_half, lbo_p, sbo_p);
-              for (int mb = 0; mb < c.nmb; ++mb) {
-                const uint64_t w_hi = make_desc(w_st + mb * 4096, 128, 256);
-                const uint64_t w_lo = make_desc(w_st + c.w_half + mb * 4096, 128, 256);
-                const uint32_t d = tmem_base + (uint32_t)((pt * c.nmb + mb) * c.ncol);
-                umma_bf16(d, w_hi, p_hi, idesc, first ? 0u : 1u);
-                umma_bf16(d, w_hi, p_lo, idesc, 1u);
-                umma_bf16(d, w_lo, p_hi, idesc, 1u);
-              }
-            }
-            first = false;
-            umma_commit(w_empty(sw));
-            if (++sw == c.sw) { sw = 0; pw ^= 1; }
-          }
-          umma_commit(a_empty(sa));
-          if (++sa == c.sa) { sa = 0; pa ^= 1; }
-        }
-      }
-      umma_commit(acc_full);
+      if (c.npt == 1 && c.nmb == 1) issue_mmas<1, 1>(p, c, a_base, w_base, bar_base, tmem_base);
+      else if (c.npt == 2 && c.nmb == 1) issue_mmas<2, 1>(p, c, a_base, w_base, bar_base, tmem_base);
+      else if (c.npt == 1 && c.nmb == 2) issue_mmas<1, 2>(p, c, a_base, w_base, bar_base, tmem_base);
+      else issue_mmas<2, 2>(p, c, a_base, w_base, bar_base, tmem_base);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
+
+int g_tc_force_per_sm = 0;   // 0 = heuristic, 1 / 2 = force (STORM_B200_TC_PER_SM, tools only)
 
 bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   if (p.Cout % 128 != 0 || p.Cout < 128 || p.Cout > 256) return false;
@@ -726,37 +777,50 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     const ConvSeg& s = p.seg[i];
     if (!s.wtc || s.C0 % 16 != 0 || s.C1 % 16 != 0 || s.C0 < 16 || (s.taps != 9 && s.taps != 1)) return false;
   }
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("STORM_B200_TC_PER_SM");
+    if (e) g_tc_force_per_sm = atoi(e);
+    env_read = true;
+  }
   const int nblk = p.Cout / 128;
-  // candidates (rows, pixel tiles, M blocks per CTA), largest CTA tile first; take the first that fills the
-  // chip, else the one with the most CTAs
-  struct Cand { int rows, npt, nmb; };
-  const Cand cands1[] = {{32, 2, 1}, {32, 1, 1}, {16, 2, 1}, {16, 1, 1}};              // Cout = 128
-  const Cand cands2[] = {{32, 1, 2}, {16, 2, 2}, {32, 1, 1}, {16, 1, 2}, {16, 1, 1}};  // Cout = 256
-  const Cand* cands = nblk == 1 ? cands1 : cands2;
+  // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
+  // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).
+  struct Cand { int rows, npt, nmb, per_sm; };
+  const Cand cands1[] = {{32, 1, 1, 2}, {32, 2, 1, 1}, {16, 2, 1, 2}, {16, 1, 1, 2}};                         // Cout = 128
+  const Cand cands2[] = {{32, 1, 1, 2}, {32, 1, 2, 1}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};           // Cout = 256
+  // with a 1x1 skip segment the activation producers are the limiter: share each staged halo across both
+  // 128-channel blocks (measured: tools/conv_timeline.py, b31.conv1)
+  const Cand cands2s[] = {{32, 1, 2, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};
+  const Cand* cands = nblk == 1 ? cands1 : (p.nseg == 2 ? cands2s : cands2);
   const int ncand = nblk == 1 ? 4 : 5;
   int best = -1;
   long best_ctas = -1;
   for (int i = 0; i < ncand; ++i) {
     const Cand& k = cands[i];
-    if (k.npt * k.nmb * 8 * k.rows > 512) continue;
+    if (g_tc_force_per_sm && k.per_sm != g_tc_force_per_sm && !(g_tc_force_per_sm == 1 && k.rows == 16)) continue;
+    if (k.npt * k.nmb * 8 * k.rows > (k.per_sm == 2 ? 256 : 512)) continue;
     if (k.npt == 2 && p.W <= 8) continue;
     if (k.rows == 32 && p.H <= 16) continue;
     const long ctas = (long)ceil_div(p.H, k.rows) * ceil_div(p.W, 8 * k.npt) * (nblk / k.nmb) * p.B;
-    if (ctas >= 132) { best = i; break; }
+    if (ctas >= 132L * k.per_sm) { best = i; break; }
     if (ctas > best_ctas) { best_ctas = ctas; best = i; }
   }
   if (best < 0) return false;
   const Cand& k = cands[best];
   c.rows = k.rows; c.npt = k.npt; c.nmb = k.nmb;
+  c.per_sm = (g_tc_force_per_sm == 1) ? 1 : k.per_sm;
   c.ncol = 8 * k.rows;
   c.msplit = nblk / k.nmb;
   c.hx = 8 * k.npt + 2; c.hy = k.rows + 2; c.np = c.hx * c.hy;
   c.a_half = 2 * c.np * 16; c.a_stage = 2 * c.a_half;
   c.w_half = 4096 * k.nmb; c.w_stage = 2 * c.w_half;
-  c.sa = c.a_stage <= 24 * 1024 ? 3 : 2;
-  int sw = (SMEM_BUDGET - c.sa * c.a_stage - 256) / c.w_stage;
+  const int budget = c.per_sm == 2 ? 108 * 1024 : SMEM_BUDGET;
+  c.sa = (c.per_sm == 1 && c.a_stage <= 24 * 1024) ? 3 : 2;
+  int sw = (budget - c.sa * c.a_stage - 256) / c.w_stage;
   c.sw = sw > 8 ? 8 : sw;
   if (c.sw < 2) return false;
+  if (c.per_sm == 2 && c.np > 2 * P_PRODUCERS) return false;
   c.tiles_x = ceil_div(p.W, 8 * k.npt);
   c.tiles_y = ceil_div(p.H, k.rows);
   return true;
@@ -781,7 +845,8 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     STORM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    STORM_CUDA_TRY(cudaFuncSetAttribute(conv_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
     attr = true;
   }
   TcpCfg cp;
@@ -789,7 +854,8 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
     const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
     dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-    conv_tcp_kernel<<<grid, P_THREADS, smem, st>>>(p, cp);
+    if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
+    else conv_tcp_kernel<3, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
     STORM_LAUNCH_CHECK();
     return 0;
   }

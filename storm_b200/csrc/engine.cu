@@ -116,6 +116,11 @@ struct StormHandle {
   int64_t launches = 0;
   bool taps_on = false;
   std::map<std::string, Act> taps;
+  // per-step cache of the time-embedding biases: corrector and predictor of one PC step share t
+  float* temb_cache = nullptr;
+  int temb_cache_B = 0;
+  float temb_cache_t = -1.f;
+  bool temb_cache_valid = false;
   bool profile_on = false;
   struct ProfRec { cudaEvent_t a, b; int eng; double flops; };
   std::vector<ProfRec> prof;
@@ -344,6 +349,7 @@ static int repack(StormHandle* h, cudaStream_t st) {
     }
   }
   h->weights_loaded = true;
+  h->temb_cache_valid = false;
   return 0;
 }
 
@@ -537,7 +543,10 @@ struct Fwd {
   }
 };
 
-static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out, int B, int F, int T, cudaStream_t st) {
+// t_uniform: when non-null, every batch element has this time value (the PC sampler's vec_t) and the
+// time-embedding biases are reused across calls with the same value
+static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out, int B, int F, int T, cudaStream_t st,
+                       const float* t_uniform = nullptr) {
   if (!h->weights_loaded) return fail(STORM_E_STATE, "weights not loaded: call storm_load_weights first");
   const StormNetConfig& c = h->cfg;
   const int nres = c.num_levels;
@@ -561,13 +570,31 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
   // ---- time embedding -> per-block biases --------------------------------------------------------------
   float* tembias = nullptr;
   float* act = nullptr;
+  bool tembias_pooled = false;
   if (h->conditional()) {
     void* p;
-    STORM_TRY(h->pool.get((size_t)B * 4 * nf * sizeof(float), &p)); act = (float*)p;
-    STORM_TRY(h->pool.get((size_t)B * h->dense_total * sizeof(float), &p)); tembias = (float*)p;
-    LAUNCH(h, launch_temb_mlp(t, h->P("all_modules.0.W"), h->W1t, h->P("all_modules.1.bias"), h->W2t,
-                              h->P("all_modules.2.bias"), act, B, nf, st));
-    LAUNCH(h, launch_dense_all(act, h->denseWt, h->denseB, tembias, B, 4 * nf, h->dense_total, st));
+    bool hit = false;
+    if (t_uniform) {
+      if (h->temb_cache_B < B) {
+        if (h->temb_cache) cudaFree(h->temb_cache);
+        h->temb_cache = nullptr;
+        STORM_CUDA_TRY(cudaMalloc((void**)&h->temb_cache, (size_t)B * h->dense_total * sizeof(float)));
+        h->temb_cache_B = B;
+        h->temb_cache_valid = false;
+      }
+      tembias = h->temb_cache;
+      hit = h->temb_cache_valid && h->temb_cache_t == *t_uniform;
+    } else {
+      STORM_TRY(h->pool.get((size_t)B * h->dense_total * sizeof(float), &p)); tembias = (float*)p;
+      tembias_pooled = true;
+    }
+    if (!hit) {
+      STORM_TRY(h->pool.get((size_t)B * 4 * nf * sizeof(float), &p)); act = (float*)p;
+      LAUNCH(h, launch_temb_mlp(t, h->P("all_modules.0.W"), h->W1t, h->P("all_modules.1.bias"), h->W2t,
+                                h->P("all_modules.2.bias"), act, B, nf, st));
+      LAUNCH(h, launch_dense_all(act, h->denseWt, h->denseB, tembias, B, 4 * nf, h->dense_total, st));
+      if (t_uniform) { h->temb_cache_valid = true; h->temb_cache_t = *t_uniform; }
+    }
   }
 
   // ---- input ---------------------------------------------------------------------------------------------
@@ -701,7 +728,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
                         F * T, inch, st));
   f.release(pyr);
   if (act) h->pool.put(act);
-  if (tembias) h->pool.put(tembias);
+  if (tembias_pooled) h->pool.put(tembias);
   return 0;
 }
 
@@ -763,7 +790,7 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond, float* X
     src.p[0] = xt; src.bstride[0] = n;
     src.p[1] = Y; src.bstride[1] = n;
     if (ncplx == 3) { src.p[2] = cond; src.bstride[2] = n; }
-    return net_forward(h, src, tdev, d, B, F, T, st);
+    return net_forward(h, src, tdev, d, B, F, T, st, &tval);
   };
   // prior: x_T = y + randn * std(T=1) (sdes.py:233-237); StoRM uses the same form around its mean
   {
@@ -860,6 +887,7 @@ int storm_destroy(StormHandle* h) {
   for (auto& kv : h->taps) cudaFree(kv.second.p);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_free) cudaEventDestroy(e);
+  if (h->temb_cache) cudaFree(h->temb_cache);
   h->pool.destroy();
   cudaFree(h->raw);
   delete h;
@@ -1001,6 +1029,14 @@ int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double 
 int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
                      int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
                      const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  return storm_debug_conv_timed(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, out_scale, out, B, H, W, nullptr,
+                                nullptr, stream);
+}
+
+int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                           int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
+                           const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, long long* dbg_dev,
+                           float* ms_out, void* stream) {
   if (!x0 || !w || !out) return fail(STORM_E_INVALID, "storm_debug_conv: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<void*> owned;
@@ -1019,6 +1055,17 @@ int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C
     p.seg[0].wtc = t0; p.seg[1].wtc = t1;
     if (rc == 0 && !conv_tc_eligible(p)) rc = fail(STORM_E_INVALID, "storm_debug_conv: shape not eligible for the tcgen05 kernel");
     if (rc == 0) rc = launch_conv_tc(p, st);
+    if (rc == 0 && ms_out) {     // timed repeat (warm weights), optionally with the CTA-0 cycle counters
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      p.dbg = dbg_dev;
+      cudaEventRecord(e0, st);
+      rc = launch_conv_tc(p, st);
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(ms_out, e0, e1);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
   } else {
     float *s0 = nullptr, *s1 = nullptr;
     if (cudaMalloc((void**)&s0, (size_t)taps * Cin * Cout * 4) != cudaSuccess) return fail(STORM_E_NOMEM, "debug conv alloc");

@@ -83,48 +83,73 @@ __global__ void temb_mlp_kernel(const float* __restrict__ t, const float* __rest
     e[nf + i] = (float)cos((double)p);
   }
   __syncthreads();
+  // weights are streamed from HBM once per call: keep 8 independent loads in flight per thread
   for (int o = threadIdx.x; o < D; o += blockDim.x) {
     float s = b1[o];
-    for (int i = 0; i < E; ++i) s = fmaf(e[i], W1t[(size_t)i * D + o], s);
+    for (int i = 0; i < E; i += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = __ldg(W1t + (size_t)(i + j) * D + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(e[i + j], wv[j], s);
+    }
     h[o] = silu_f(s);
   }
   __syncthreads();
   for (int o = threadIdx.x; o < D; o += blockDim.x) {
     float s = b2[o];
-    for (int i = 0; i < D; ++i) s = fmaf(h[i], W2t[(size_t)i * D + o], s);
+    for (int i = 0; i < D; i += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = __ldg(W2t + (size_t)(i + j) * D + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(h[i + j], wv[j], s);
+    }
     act[(size_t)b * D + o] = silu_f(s);   // every consumer applies act(temb) first (layerspp.py:263)
   }
 }
 int launch_temb_mlp(const float* t, const float* Wf, const float* W1t, const float* b1, const float* W2t, const float* b2,
                     float* act, int B, int nf, cudaStream_t st) {
-  temb_mlp_kernel<<<B, 256, 6 * nf * sizeof(float), st>>>(t, Wf, W1t, b1, W2t, b2, act, nf);
+  if (nf % 4 != 0) return fail(-1, "temb_mlp: nf must be a multiple of 4");
+  temb_mlp_kernel<<<B, 512, 6 * nf * sizeof(float), st>>>(t, Wf, W1t, b1, W2t, b2, act, nf);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
-__global__ void dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt, const float* __restrict__ bias,
-                                 float* __restrict__ out, int B, int in_dim, int out_dim) {
+__global__ void __launch_bounds__(64) dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B, int in_dim,
+                                                       int out_dim) {
+  extern __shared__ float s_act[];   // [8][in_dim]
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= out_dim) return;
   for (int b0 = 0; b0 < B; b0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[o];
     const int nb = min(8, B - b0);
-    for (int i = 0; i < in_dim; ++i) {
-      float w = Wt[(size_t)i * out_dim + o];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 8 * in_dim; e += blockDim.x)
+      s_act[e] = (e / in_dim < nb) ? act[(size_t)b0 * in_dim + e] : 0.f;
+    __syncthreads();
+    if (o < out_dim) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bias[o];
+      for (int i = 0; i < in_dim; i += 8) {
+        float wv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wv[k] = __ldg(Wt + (size_t)(i + k) * out_dim + o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv[k], s_act[j * in_dim + i + k], acc[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (j < nb) acc[j] = fmaf(w, __ldg(act + (size_t)(b0 + j) * in_dim + i), acc[j]);
+        if (j < nb) out[(size_t)(b0 + j) * out_dim + o] = acc[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nb) out[(size_t)(b0 + j) * out_dim + o] = acc[j];
   }
 }
 int launch_dense_all(const float* act, const float* Wt, const float* bias, float* out, int B, int in_dim, int out_dim,
                      cudaStream_t st) {
-  dense_all_kernel<<<ceil_div(out_dim, 128), 128, 0, st>>>(act, Wt, bias, out, B, in_dim, out_dim);
+  if (in_dim % 8 != 0 || in_dim > 1024) return fail(-1, "dense_all: in_dim must be a multiple of 8 and <= 1024");
+  dense_all_kernel<<<ceil_div(out_dim, 64), 64, 8 * in_dim * sizeof(float), st>>>(act, Wt, bias, out, B, in_dim, out_dim);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -307,9 +332,111 @@ __global__ void resample_kernel(const float* __restrict__ x, const float* __rest
     if (h_out) reinterpret_cast<float4*>(h_out)[o] = ah;
   }
 }
+// Tiled variants: every input element is loaded and activated exactly once per CTA (shared memory), then
+// both outputs (FIR of the activated tensor and FIR of the raw tensor) are produced from the staged tile.
+// UP:   8x8 input pixels (+1 halo) x 32 channels -> 16x16 output pixels.   smem 2 x 10x10x32 floats
+// DOWN: 8x8 output pixels <- 18x18 input pixels x 16 channels.             smem 2 x 18x18x20 floats (padded)
+template <int MODE>
+__global__ void __launch_bounds__(256) resample_tiled_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+                                                             float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  constexpr int CG = MODE == 1 ? 32 : 16;            // channels per CTA
+  constexpr int C4 = CG / 4;
+  constexpr int TI = MODE == 1 ? 10 : 18;            // staged input tile edge
+  constexpr int PS = MODE == 1 ? 32 : 20;            // floats per staged pixel (padded for DOWN)
+  extern __shared__ __align__(16) float rs_smem[];
+  float* sAct = rs_smem;
+  float* sRaw = rs_smem + TI * TI * PS;
+  const int OH = MODE == 1 ? 2 * H : H / 2, OW = MODE == 1 ? 2 * W : W / 2;
+  const int tiles_x = MODE == 1 ? (W + 7) / 8 : (OW + 7) / 8;
+  const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x % tiles_x;
+  const int c0 = blockIdx.y * CG;
+  const int b = blockIdx.z;
+  // first staged input pixel
+  const int iy0 = MODE == 1 ? tyi * 8 - 1 : tyi * 16 - 1;
+  const int ix0 = MODE == 1 ? txi * 8 - 1 : txi * 16 - 1;
+  for (int e = threadIdx.x; e < TI * TI * C4; e += 256) {
+    const int c4 = e % C4, pix = e / C4;
+    const int py = pix / TI, px = pix - py * TI;
+    const int y = iy0 + py, xx = ix0 + px;
+    float4 raw = make_float4(0, 0, 0, 0), act = make_float4(0, 0, 0, 0);
+    if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) {
+      raw = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + y) * W + xx) * C + c0) + c4);
+      act = raw;
+      if (ss) {
+        const float4* sp = reinterpret_cast<const float4*>(ss + ((size_t)b * C + c0 + c4 * 4) * 2);
+        const float4 a = __ldg(sp), d = __ldg(sp + 1);
+        act.x = silu_fast(fmaf(raw.x, a.x, a.y));
+        act.y = silu_fast(fmaf(raw.y, a.z, a.w));
+        act.z = silu_fast(fmaf(raw.z, d.x, d.y));
+        act.w = silu_fast(fmaf(raw.w, d.z, d.w));
+      }
+    }
+    *reinterpret_cast<float4*>(sAct + pix * PS + c4 * 4) = act;
+    *reinterpret_cast<float4*>(sRaw + pix * PS + c4 * 4) = raw;
+  }
+  __syncthreads();
+  constexpr int TO = MODE == 1 ? 16 : 8;             // output tile edge
+  for (int e = threadIdx.x; e < TO * TO * C4; e += 256) {
+    const int c4 = e % C4, op = e / C4;
+    const int oyl = op / TO, oxl = op - oyl * TO;
+    const int oy = tyi * TO + oyl, ox = txi * TO + oxl;
+    if (oy >= OH || ox >= OW) continue;
+    float4 ah = make_float4(0, 0, 0, 0), ax = make_float4(0, 0, 0, 0);
+    if (MODE == 1) {
+      // o[2i] = x[i-1]/4 + 3x[i]/4 ; o[2i+1] = 3x[i]/4 + x[i+1]/4   (staged tile starts at input pixel i0 - 1)
+      const int ly = (oyl >> 1) + ((oyl & 1) ? 1 : 0), lx = (oxl >> 1) + ((oxl & 1) ? 1 : 0);   // first tap, staged coords
+      const float wy0 = (oyl & 1) ? 0.75f : 0.25f, wx0 = (oxl & 1) ? 0.75f : 0.25f;
+#pragma unroll
+      for (int jy = 0; jy < 2; ++jy)
+#pragma unroll
+        for (int jx = 0; jx < 2; ++jx) {
+          const float wgt = (jy ? 1.0f - wy0 : wy0) * (jx ? 1.0f - wx0 : wx0);
+          const int pix = (ly + jy) * TI + lx + jx;
+          const float4 va = *reinterpret_cast<const float4*>(sAct + pix * PS + c4 * 4);
+          const float4 vr = *reinterpret_cast<const float4*>(sRaw + pix * PS + c4 * 4);
+          ah.x = fmaf(wgt, va.x, ah.x); ah.y = fmaf(wgt, va.y, ah.y); ah.z = fmaf(wgt, va.z, ah.z); ah.w = fmaf(wgt, va.w, ah.w);
+          ax.x = fmaf(wgt, vr.x, ax.x); ax.y = fmaf(wgt, vr.y, ax.y); ax.z = fmaf(wgt, vr.z, ax.z); ax.w = fmaf(wgt, vr.w, ax.w);
+        }
+    } else {
+      const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+      for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) {
+          const float wgt = k[jy] * k[jx];
+          const int pix = (2 * oyl + jy) * TI + 2 * oxl + jx;
+          const float4 va = *reinterpret_cast<const float4*>(sAct + pix * PS + c4 * 4);
+          const float4 vr = *reinterpret_cast<const float4*>(sRaw + pix * PS + c4 * 4);
+          ah.x = fmaf(wgt, va.x, ah.x); ah.y = fmaf(wgt, va.y, ah.y); ah.z = fmaf(wgt, va.z, ah.z); ah.w = fmaf(wgt, va.w, ah.w);
+          ax.x = fmaf(wgt, vr.x, ax.x); ax.y = fmaf(wgt, vr.y, ax.y); ax.z = fmaf(wgt, vr.z, ax.z); ax.w = fmaf(wgt, vr.w, ax.w);
+        }
+    }
+    const size_t o = ((((size_t)b * OH + oy) * OW + ox) * C + c0) / 4 + c4;
+    if (h_out) reinterpret_cast<float4*>(h_out)[o] = ah;
+    if (x_out) reinterpret_cast<float4*>(x_out)[o] = ax;
+  }
+}
+
 int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, int mode, cudaStream_t st) {
   if (x.C % 4 != 0) return fail(-1, "resample: C must be a multiple of 4");
   if (mode == 2 && ((x.H | x.W) & 1)) return fail(-1, "resample: downsampling needs even extents");
+  if (mode == 1 && x.C % 32 == 0) {
+    dim3 grid(ceil_div(x.H, 8) * ceil_div(x.W, 8), x.C / 32, x.B);
+    resample_tiled_kernel<1><<<grid, 256, 2 * 10 * 10 * 32 * sizeof(float), st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
+  if (mode == 2 && x.C % 16 == 0) {
+    static bool attr = false;
+    if (!attr) {
+      STORM_CUDA_TRY(cudaFuncSetAttribute(resample_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    dim3 grid(ceil_div(x.H / 2, 8) * ceil_div(x.W / 2, 8), x.C / 16, x.B);
+    resample_tiled_kernel<2><<<grid, 256, 2 * 18 * 18 * 20 * sizeof(float), st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
   const int OH = mode == 1 ? 2 * x.H : x.H / 2, OW = mode == 1 ? 2 * x.W : x.W / 2;
   size_t total = (size_t)x.B * OH * OW * (x.C / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
@@ -412,93 +539,121 @@ int launch_combine(const float* h, const float* pyr, const float* w, const float
 }
 
 // ---- progressive output branch: conv3x3 C -> Co<=8 with GN+SiLU prologue ------------------------------
+// CTA = 16 x 32 output pixels, 128 threads, each thread a 2x2 pixel block x NCO output channels (register
+// blocking: 16 activations + 9 weight vectors feed 36*NCO FMAs per input channel).
 namespace {
-constexpr int OT = 16;            // 16x16 output pixels per CTA
-constexpr int OKC = 8;
-constexpr int OHL = OT + 2;
-constexpr int OHP = OHL + 1;      // padded row pitch
+constexpr int OTH = 16, OTW = 32;       // output tile
+constexpr int OKC = 8;                  // channels per staged chunk
+constexpr int OHH = OTH + 2, OHW = OTW + 2;
+constexpr int OHP = OHW + 2;            // padded row pitch (even -> float2 loads stay aligned)
 }
-__global__ void __launch_bounds__(256) conv_out_small_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+template <int NCO>
+__global__ void __launch_bounds__(128) conv_out_small_kernel(const float* __restrict__ x, const float* __restrict__ ss,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              const float* __restrict__ prev, float* __restrict__ out,
                                                              int H, int W, int C, int Co) {
-  __shared__ float sA[OKC][OHL][OHP];
+  __shared__ __align__(16) float sA[OKC][OHH][OHP];
   __shared__ __align__(16) float sW[9][OKC][8];
-  const int tiles_x = (W + OT - 1) / OT;
-  const int ty0 = (blockIdx.x / tiles_x) * OT, tx0 = (blockIdx.x % tiles_x) * OT;
+  const int tiles_x = (W + OTW - 1) / OTW;
+  const int ty0 = (blockIdx.x / tiles_x) * OTH, tx0 = (blockIdx.x % tiles_x) * OTW;
   const int b = blockIdx.y;
-  const int py = threadIdx.x / OT, px = threadIdx.x % OT;
-  float acc[8];
+  const int bx = threadIdx.x & 15, by = threadIdx.x >> 4;    // 2x2 block coordinates inside the tile
+  float acc[4][NCO];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NCO; ++j) acc[i][j] = 0.f;
   for (int c0 = 0; c0 < C; c0 += OKC) {
-    for (int e = threadIdx.x; e < OKC * OHL * OHL; e += 256) {
-      int ch = e % OKC;
-      int pix = e / OKC;
-      int hy = pix / OHL, hx = pix % OHL;
-      int y = ty0 + hy - 1, xx = tx0 + hx - 1;
+    for (int e = threadIdx.x; e < OKC * OHH * OHW; e += 128) {
+      const int ch = e % OKC;
+      const int pix = e / OKC;
+      const int hy = pix / OHW, hx = pix - hy * OHW;
+      const int y = ty0 + hy - 1, xx = tx0 + hx - 1;
       float v = 0.f;
       if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W && c0 + ch < C) {
         v = __ldg(x + (((size_t)b * H + y) * W + xx) * C + c0 + ch);
         if (ss) {
           const float* s2 = ss + ((size_t)b * C + c0 + ch) * 2;
-          v = silu_f(fmaf(v, __ldg(s2), __ldg(s2 + 1)));
+          v = silu_fast(fmaf(v, __ldg(s2), __ldg(s2 + 1)));
         }
       }
       sA[ch][hy][hx] = v;
     }
-    for (int e = threadIdx.x; e < 9 * OKC * 8; e += 256) {
-      int j = e % 8;
-      int ch = (e / 8) % OKC;
-      int tap = e / (8 * OKC);
+    for (int e = threadIdx.x; e < 9 * OKC * 8; e += 128) {
+      const int j = e % 8;
+      const int ch = (e / 8) % OKC;
+      const int tap = e / (8 * OKC);
       sW[tap][ch][j] = (c0 + ch < C) ? __ldg(w + ((size_t)tap * C + c0 + ch) * 8 + j) : 0.f;
     }
     __syncthreads();
-#pragma unroll 1
+#pragma unroll 2
     for (int ch = 0; ch < OKC; ++ch) {
+      float a[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 v0 = *reinterpret_cast<const float2*>(&sA[ch][2 * by + r][2 * bx]);
+        const float2 v1 = *reinterpret_cast<const float2*>(&sA[ch][2 * by + r][2 * bx + 2]);
+        a[r][0] = v0.x; a[r][1] = v0.y; a[r][2] = v1.x; a[r][3] = v1.y;
+      }
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          float a = sA[ch][py + dy][px + dx];
-          float4 w0 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][0]);
-          float4 w1 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][4]);
-          acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
-          acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+          float wv[NCO];
+          const float4 w0 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][0]);
+          wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+          if (NCO == 8) {
+            const float4 w1 = *reinterpret_cast<const float4*>(&sW[dy * 3 + dx][ch][4]);
+            wv[NCO - 4] = w1.x; wv[NCO - 3] = w1.y; wv[NCO - 2] = w1.z; wv[NCO - 1] = w1.w;
+          }
+#pragma unroll
+          for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+              const float av = a[py + dy][px + dx];
+#pragma unroll
+              for (int j = 0; j < NCO; ++j) acc[py * 2 + px][j] = fmaf(av, wv[j], acc[py * 2 + px][j]);
+            }
         }
     }
     __syncthreads();
   }
-  const int y = ty0 + py, xx = tx0 + px;
-  if (y >= H || xx >= W) return;
-  for (int j = 0; j < Co; ++j) {
-    float v = acc[j] + bias[j];
-    if (prev) {   // + FIR_up(prev) at (y, xx): prev is [B][H/2][W/2][Co]
-      const int PH = H / 2, PW = W / 2;
-      int iy = y >> 1, ix = xx >> 1;
-      int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
-      if (y & 1) { y0 = iy; wy0 = 0.75f; y1 = iy + 1; wy1 = 0.25f; } else { y0 = iy - 1; wy0 = 0.25f; y1 = iy; wy1 = 0.75f; }
-      if (xx & 1) { x0 = ix; wx0 = 0.75f; x1 = ix + 1; wx1 = 0.25f; } else { x0 = ix - 1; wx0 = 0.25f; x1 = ix; wx1 = 0.75f; }
-      float u = 0.f;
-      const float* pb = prev + (size_t)b * PH * PW * Co + j;
-      if ((unsigned)y0 < (unsigned)PH) {
-        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy0 * wx0, __ldg(pb + ((size_t)y0 * PW + x0) * Co), u);
-        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy0 * wx1, __ldg(pb + ((size_t)y0 * PW + x1) * Co), u);
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int y = ty0 + 2 * by + py, xx = tx0 + 2 * bx + px;
+      if (y >= H || xx >= W) continue;
+      for (int j = 0; j < Co; ++j) {
+        float v = acc[py * 2 + px][j < NCO ? j : 0] + bias[j];
+        if (prev) {   // + FIR_up(prev) at (y, xx): prev is [B][H/2][W/2][Co]
+          const int PH = H / 2, PW = W / 2;
+          const int iy = y >> 1, ix = xx >> 1;
+          int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+          if (y & 1) { y0 = iy; wy0 = 0.75f; y1 = iy + 1; wy1 = 0.25f; } else { y0 = iy - 1; wy0 = 0.25f; y1 = iy; wy1 = 0.75f; }
+          if (xx & 1) { x0 = ix; wx0 = 0.75f; x1 = ix + 1; wx1 = 0.25f; } else { x0 = ix - 1; wx0 = 0.25f; x1 = ix; wx1 = 0.75f; }
+          float u = 0.f;
+          const float* pb = prev + (size_t)b * PH * PW * Co + j;
+          if ((unsigned)y0 < (unsigned)PH) {
+            if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy0 * wx0, __ldg(pb + ((size_t)y0 * PW + x0) * Co), u);
+            if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy0 * wx1, __ldg(pb + ((size_t)y0 * PW + x1) * Co), u);
+          }
+          if ((unsigned)y1 < (unsigned)PH) {
+            if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy1 * wx0, __ldg(pb + ((size_t)y1 * PW + x0) * Co), u);
+            if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy1 * wx1, __ldg(pb + ((size_t)y1 * PW + x1) * Co), u);
+          }
+          v = u + v;   // pyramid = upsample(pyramid) + pyramid_h (ncsnpp.py:405-410)
+        }
+        out[(((size_t)b * H + y) * W + xx) * Co + j] = v;
       }
-      if ((unsigned)y1 < (unsigned)PH) {
-        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy1 * wx0, __ldg(pb + ((size_t)y1 * PW + x0) * Co), u);
-        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy1 * wx1, __ldg(pb + ((size_t)y1 * PW + x1) * Co), u);
-      }
-      v = u + v;   // pyramid = upsample(pyramid) + pyramid_h (ncsnpp.py:405-410)
     }
-    out[(((size_t)b * H + y) * W + xx) * Co + j] = v;
-  }
 }
 int launch_conv_out_small(const Act& h, const float* ss, const float* w, const float* bias, const float* prev, float* out,
                           int Co, cudaStream_t st) {
   if (Co > 8) return fail(-1, "conv_out_small: Co > 8");
-  dim3 grid(ceil_div(h.W, OT) * ceil_div(h.H, OT), h.B);
-  conv_out_small_kernel<<<grid, 256, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
+  dim3 grid(ceil_div(h.W, OTW) * ceil_div(h.H, OTH), h.B);
+  if (Co <= 4) conv_out_small_kernel<4><<<grid, 128, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
+  else conv_out_small_kernel<8><<<grid, 128, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
   STORM_LAUNCH_CHECK();
   return 0;
 }
