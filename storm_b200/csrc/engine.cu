@@ -92,7 +92,7 @@ struct AttnPack {
   const float* b[4] = {nullptr, nullptr, nullptr, nullptr};
   void* tc[4] = {nullptr, nullptr, nullptr, nullptr};
 };
-struct SmallConvPack { float* w = nullptr; const float* b = nullptr; void* tc = nullptr; };
+struct SmallConvPack { float* w = nullptr; const float* b = nullptr; void* tc = nullptr; int npad = 0; };
 
 }  // namespace storm
 
@@ -340,6 +340,13 @@ static int repack(StormHandle* h, cudaStream_t st) {
       LAUNCH(h, launch_pack_conv_simt(h->P(p + ".weight"), tmp, m.out_ch, m.in_ch, 9, st));   // [9][C][Co]
       STORM_CUDA_TRY(cudaMemcpy2DAsync(s.w, 8 * sizeof(float), tmp, m.out_ch * sizeof(float), m.out_ch * sizeof(float),
                                        (size_t)9 * m.in_ch, cudaMemcpyDeviceToDevice, st));
+      if (use_tc) {   // tensor-core route: 1x1 GEMM onto 9*Co tap-partials (see launch_tap_gather)
+        s.npad = (9 * m.out_ch + 15) / 16 * 16;
+        float* wz = nullptr;
+        STORM_TRY(dev_alloc(h, (size_t)m.in_ch * s.npad, &wz));
+        LAUNCH(h, launch_pack_convout_gemm(h->P(p + ".weight"), wz, m.out_ch, m.in_ch, s.npad, st));
+        STORM_TRY(tc_pack_weights_io(wz, m.in_ch, s.npad, &s.tc, &h->packed, st));
+      }
       h->conv_out[m.index] = s;
     } else if (m.kind == M_COMBINE) {
       SmallConvPack s;
@@ -703,7 +710,23 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
       const SmallConvPack& s = h->conv_out.at(co.index);
       Act np;
       STORM_TRY(f.alloc(np, hcur.H, hcur.W, inch));
-      LAUNCH(h, launch_conv_out_small(hcur, ss, s.w, s.b, have_pyr ? pyr.p : nullptr, np.p, inch, st));
+      bool done = false;
+      if (h->cfg.engine == 0 && s.tc) {
+        ConvParams p{};
+        p.nseg = 1;
+        p.seg[0].src0 = hcur.p; p.seg[0].C0 = hcur.C; p.seg[0].ss = ss; p.seg[0].silu = 1; p.seg[0].taps = 1; p.seg[0].wtc = s.tc;
+        p.B = B; p.H = hcur.H; p.W = hcur.W; p.Cout = s.npad; p.out_scale = 1.0f;
+        if (conv_tc_eligible(p)) {
+          void* zq;
+          STORM_TRY(h->pool.get((size_t)B * hcur.H * hcur.W * s.npad * sizeof(float), &zq));
+          p.out = (float*)zq;
+          STORM_TRY(f.conv(p));
+          LAUNCH(h, launch_tap_gather(p.out, s.npad, s.b, have_pyr ? pyr.p : nullptr, np.p, B, hcur.H, hcur.W, inch, st));
+          h->pool.put(zq);
+          done = true;
+        }
+      }
+      if (!done) LAUNCH(h, launch_conv_out_small(hcur, ss, s.w, s.b, have_pyr ? pyr.p : nullptr, np.p, inch, st));
       h->pool.put(ss);
       if (have_pyr) f.release(pyr);
       pyr = np;

@@ -44,6 +44,12 @@ int launch_combine(const float* h, const float* pyr, const float* w, const float
 // w packed [9][C][8] (Co <= 8, zero padded)
 int launch_conv_out_small(const Act& h, const float* ss, const float* w, const float* bias, const float* prev,
                           float* out, int Co, cudaStream_t st);
+// Tensor-core route of the same branch: Z[b,y,x,tap*Co+co] = sum_c act(h)[b,y,x,c] * W[co][c][tap] is a 1x1 GEMM
+// (N = 9*Co padded to a multiple of 16) run by the tcgen05 kernel; this gathers the 9 shifted partial sums:
+// out = bias + sum_tap Z[y+dy-1, x+dx-1, tap*Co+co] (+ FIR_up(prev)).
+int launch_pack_convout_gemm(const float* w_oihw, float* out_io, int Co, int Cin, int Npad, cudaStream_t st);
+int launch_tap_gather(const float* Z, int Npad, const float* bias, const float* prev, float* out, int B, int H, int W, int Co,
+                      cudaStream_t st);
 // d = conv1x1_{Ci->2}(pyr / t) packed to complex (ncsnpp.py:440-449); w [2][Ci]
 int launch_head(const float* pyr, const float* t, const float* w, const float* bias, float* out_c, int B, int HW,
                 int Ci, cudaStream_t st);

@@ -658,6 +658,76 @@ int launch_conv_out_small(const Act& h, const float* ss, const float* w, const f
   return 0;
 }
 
+__global__ void pack_convout_gemm_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Cin, int Npad) {
+  const int total = Cin * Npad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % Npad, c = i / Npad;
+    float v = 0.f;
+    if (n < 9 * Co) {
+      const int tap = n / Co, co = n - tap * Co;
+      v = w[((size_t)co * Cin + c) * 9 + tap];
+    }
+    out[i] = v;
+  }
+}
+int launch_pack_convout_gemm(const float* w_oihw, float* out_io, int Co, int Cin, int Npad, cudaStream_t st) {
+  pack_convout_gemm_kernel<<<ceil_div(Cin * Npad, 256), 256, 0, st>>>(w_oihw, out_io, Co, Cin, Npad);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void tap_gather_kernel(const float* __restrict__ Z, int Npad, const float* __restrict__ bias, const float* __restrict__ prev,
+                                  float* __restrict__ out, int B, int H, int W, int Co) {
+  const size_t total = (size_t)B * H * W * Co;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = i % Co;
+    size_t r = i / Co;
+    const int xx = r % W; r /= W;
+    const int y = r % H;
+    const int b = r / H;
+    float v = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if ((unsigned)yy >= (unsigned)H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xs = xx + dx - 1;
+        if ((unsigned)xs >= (unsigned)W) continue;
+        v += __ldg(Z + (((size_t)b * H + yy) * W + xs) * Npad + (dy * 3 + dx) * Co + j);
+      }
+    }
+    v += bias[j];
+    if (prev) {
+      const int PH = H / 2, PW = W / 2;
+      const int iy = y >> 1, ix = xx >> 1;
+      int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+      if (y & 1) { y0 = iy; wy0 = 0.75f; y1 = iy + 1; wy1 = 0.25f; } else { y0 = iy - 1; wy0 = 0.25f; y1 = iy; wy1 = 0.75f; }
+      if (xx & 1) { x0 = ix; wx0 = 0.75f; x1 = ix + 1; wx1 = 0.25f; } else { x0 = ix - 1; wx0 = 0.25f; x1 = ix; wx1 = 0.75f; }
+      float u = 0.f;
+      const float* pb = prev + (size_t)b * PH * PW * Co + j;
+      if ((unsigned)y0 < (unsigned)PH) {
+        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy0 * wx0, __ldg(pb + ((size_t)y0 * PW + x0) * Co), u);
+        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy0 * wx1, __ldg(pb + ((size_t)y0 * PW + x1) * Co), u);
+      }
+      if ((unsigned)y1 < (unsigned)PH) {
+        if ((unsigned)x0 < (unsigned)PW) u = fmaf(wy1 * wx0, __ldg(pb + ((size_t)y1 * PW + x0) * Co), u);
+        if ((unsigned)x1 < (unsigned)PW) u = fmaf(wy1 * wx1, __ldg(pb + ((size_t)y1 * PW + x1) * Co), u);
+      }
+      v = u + v;
+    }
+    out[i] = v;
+  }
+}
+int launch_tap_gather(const float* Z, int Npad, const float* bias, const float* prev, float* out, int B, int H, int W, int Co,
+                      cudaStream_t st) {
+  size_t total = (size_t)B * H * W * Co;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  tap_gather_kernel<<<blocks, 256, 0, st>>>(Z, Npad, bias, prev, out, B, H, W, Co);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void head_kernel(const float* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ w,
                             const float* __restrict__ bias, float2* __restrict__ out, int B, int HW, int Ci) {
   const size_t total = (size_t)B * HW;
