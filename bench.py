@@ -75,6 +75,40 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(self.rows))
 
 
+def usable_cpus() -> int:
+    """Host cores this process may really use: affinity mask and cgroup CPU quota, not os.cpu_count()."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(-(-int(q) // int(per)))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+def pick_cpu_threads() -> int:
+    """Thread count that makes the CPU oracle fastest on this box (oversubscribing a quota-limited container
+    slows torch's conv by an order of magnitude, so 'all threads' is calibrated, not assumed)."""
+    import torch
+    import torch.nn.functional as F
+    n = usable_cpus()
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    x = torch.randn(1, 128, 128, 128)
+    w = torch.randn(128, 128, 3, 3)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def synth_batch(B, L, first_id):
     import torch
     from oracle.storm_oracle import synth_utterance
@@ -107,7 +141,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = pick_cpu_threads()
     nfe_target = WORKLOAD["N"] * 2
     rates = []
     for i in range(args.warmup + args.steps):
@@ -130,7 +164,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from storm_b200 import ScoreModel, _native, ncsnpp_spec
+    from storm_b200 import ScoreModel, _native, ncsnpp_spec, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -148,12 +182,8 @@ def run_native(args):
     if rank == 0:
         model.dnn.load_state_dict(ncsnpp_spec.random_state_dict(model.dnn.cfg, seed=0, init_scale=1.0))
     model.cuda()
+    parallel.broadcast_weights(model.dnn, src=0)      # no-op at world == 1
     eng = model.dnn.engine()
-    if world > 1:
-        blob = eng.weights_view()
-        dist.broadcast(blob, src=0)
-        torch.cuda.synchronize()
-        eng.repack()
     sc = model._sampler_cfg(W["predictor"], W["corrector"], W["N"], W["corrector_steps"], W["snr"])
     sp = model.data_module.spec_config()
     ids = list(range(rank * B, rank * B + B))
@@ -227,7 +257,7 @@ def run_native(args):
                     issued_frac=(3 * achieved / peak) if (peak and dom == "tcgen05") else None,
                     launches=dp["launches"], avg_launch_ms=dp["ms"] / max(1, dp["launches"]), conv_share_of_step=conv_share,
                     by_engine=prof)
-    threads = os.cpu_count() or 1
+    threads = pick_cpu_threads()
     cpu_rate, cpu_dt, cpu_nfe = cpu_oracle_rate(threads, W["N"] * 2)
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (bf16x3 tensor-core split, fp32 accumulate)"
