@@ -5,23 +5,22 @@
 // AttnBlockpp (layerspp.py:75-91), with the GroupNorm-apply + SiLU prologue and the
 // bias / time-embedding / residual / (1/sqrt 2) epilogue fused in.
 //
-// GEMM view       D[pixel, cout] = sum_seg sum_tap sum_cin A_seg[pixel + tap, cin] * W_seg[tap][cin][cout]
-//   M = 128 output pixels per MMA  (a 16-row x 8-column patch of the spectrogram),
-//   N = Cout (or Cout/2) accumulator columns in TMEM, K step = 16 input channels.
+// GEMM view ("pixels as N")   D[cout, pixel] = sum_seg sum_tap sum_cin W_seg[tap][cout][cin] * A_seg[pixel + tap, cin]
+//   M = 128 output channels per MMA (rows of the weight image; Cout is zero-padded to a multiple of 128),
+//   N = 256 (or 128) pixels = a 32x8 (16x8) patch of the spectrogram held as TMEM columns, K step = 16 channels.
 // fp32 accuracy on bf16 tensor cores: every operand is split x = hi + lo (two bf16), and three MMAs
-//   hi*hi + lo*hi + hi*lo accumulate in fp32 TMEM (error ~2^-16 per product, vs 2^-11 for TF32).
+//   hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM (error ~2^-16 per product, vs 2^-11 for TF32).
 //
 // Data movement
-//   A (activations): producer warps read fp32 NHWC from global (coalesced 32 B per pixel half-chunk), apply
-//     scale/shift + SiLU, split to bf16 hi/lo and store a HALO tile [2 k-cores][18 rows][8*NSUB+2 cols][8 ch]
-//     in the UMMA "no-swizzle, K-major" core-matrix layout.  The 9 filter taps are then just 9 different
-//     start addresses into the same halo tile (SBO = one halo row, LBO = one k-core plane), so each
-//     activation is staged once per 16-channel chunk, not 9 times.
-//   B (weights): pre-split bf16 hi/lo shared-memory images, one per (16-channel chunk, tap), streamed with
+//   activations (B operand): producer warps read fp32 NHWC from global (64 contiguous bytes per pixel and 16-channel
+//     chunk), apply scale/shift + SiLU, split to bf16 hi/lo and store a HALO tile [2 k-cores][R+2 rows][8*NPT+2 cols][8 ch]
+//     in the UMMA "no-swizzle, K-major" core-matrix layout.  The 9 filter taps are then just 9 different start
+//     addresses into the same halo tile (SBO = one halo row, LBO = one k-core plane), so each activation is staged
+//     once per 16-channel chunk, not 9 times.
+//   weights (A operand): pre-split bf16 hi/lo shared-memory images, one per (16-channel chunk, tap), streamed with
 //     cp.async.bulk (UBLKCP) + mbarrier complete_tx through a multi-stage ring.
-//   D: TMEM, 128 lanes x (NSUB*NT <= 512) fp32 columns; read back with tcgen05.ld in the epilogue.
-// Warp roles: warps 0-3 A-producers then epilogue (TMEM lane quadrant = warp id), warp 4 weight producer,
-//   warp 5 TMEM allocator + single-thread MMA issuer.  One CTA per SM (smem ~150 KB, all 512 TMEM columns).
+//   D: TMEM, 128 lanes (output channels) x up to 512 fp32 columns (pixels); read back with tcgen05.ld in the epilogue.
+// (The first-generation "cout as N" variant of this kernel is in git history: profiles/r1_bench_history.md.)
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -32,24 +31,7 @@ namespace storm {
 
 namespace {
 
-constexpr int TC_THREADS = 192;
-constexpr int N_PRODUCERS = 128;
-constexpr int HY = 18;             // halo rows of a 16-row tile
 constexpr int SMEM_BUDGET = 200 * 1024;
-
-struct TcCfg {
-  int nsub;            // 8-column sub-tiles per CTA (1, 2, 4): CTA tile = 16 x (8*nsub) pixels
-  int nt;              // accumulator columns per sub-tile (output channels handled by this CTA)
-  int nsplit;          // Cout / nt
-  int hx;              // halo columns = 8*nsub + 2
-  int np;              // halo pixels = HY * hx
-  int sa, sw;          // ring depths
-  int a_half;          // bytes of one (hi or lo) activation plane = 2 * np * 16
-  int a_stage;         // 2 * a_half
-  int w_half;          // 32 * nt
-  int w_stage;         // 64 * nt
-  int tiles_x;
-};
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,211 +132,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// =====================================================================================================
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvParams p, TcCfg c) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_base = smem_u32(smem);
-  const uint32_t w_base = a_base + c.sa * c.a_stage;
-  const uint32_t bar_base = w_base + c.sw * c.w_stage;
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
-  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };
-  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };
-  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 2 * c.sw);
-  const uint32_t tmem_slot = acc_full + 8;
-
-  const int ty0 = (blockIdx.x / c.tiles_x) * 16;
-  const int tx0 = (blockIdx.x % c.tiles_x) * 8 * c.nsub;
-  const int n_lo = blockIdx.y * c.nt;
-  const int b = blockIdx.z;
-
-  if (tid == 0) {
-    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), N_PRODUCERS); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
-    mbar_init(acc_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp < 4) {
-    // =================================== A producers ===================================================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int si = 0; si < p.nseg; ++si) {
-      const ConvSeg s = p.seg[si];
-      const int C = s.C0 + s.C1;
-      const bool full_halo = s.taps == 9;
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        mbar_wait(a_empty(stage), phase ^ 1);
-        const uint32_t st_base = a_base + stage * c.a_stage;
-#pragma unroll 1
-        for (int kh = 0; kh < 2; ++kh) {
-          const int cc = c0 + kh * 8;
-          const float* src;
-          int Cs, cl;
-          if (cc < s.C0) { src = s.src0; Cs = s.C0; cl = cc; } else { src = s.src1; Cs = s.C1; cl = cc - s.C0; }
-          float sc[8], sh[8];
-          if (s.ss) {
-            const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + cc) * 2);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 v = __ldg(sp + j);
-              sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
-            }
-          }
-          for (int ps = tid; ps < c.np; ps += N_PRODUCERS) {
-            const int hy = ps / c.hx, hxx = ps - hy * c.hx;
-            if (!full_halo && (hy == 0 || hy == HY - 1 || hxx == 0 || hxx == c.hx - 1)) continue;
-            const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
-            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-            if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
-              const float4* gp = reinterpret_cast<const float4*>(src + (((size_t)b * p.H + y) * p.W + x) * Cs + cl);
-              float4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
-              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-              if (s.ss) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-              }
-              if (s.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
-              }
-              float r[8];
-              hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
-              hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
-              hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
-              hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
-              float d0, d1;
-              lo.x = pack_bf16x2(r[0], r[1], d0, d1);
-              lo.y = pack_bf16x2(r[2], r[3], d0, d1);
-              lo.z = pack_bf16x2(r[4], r[5], d0, d1);
-              lo.w = pack_bf16x2(r[6], r[7], d0, d1);
-            }
-            const uint32_t off = st_base + (uint32_t)(kh * c.np + ps) * 16u;
-            st_shared_v4(off, hi);
-            st_shared_v4(off + c.a_half, lo);
-          }
-        }
-        fence_async_shared();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(a_full(stage));
-        if (++stage == c.sa) { stage = 0; phase ^= 1; }
-      }
-    }
-    // =================================== epilogue ======================================================
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int m = warp * 32 + lane;
-    const int y = ty0 + (m >> 3);
-    const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
-    for (int sub = 0; sub < c.nsub; ++sub) {
-      const int x = tx0 + 8 * sub + (m & 7);
-      const bool valid = y < p.H && x < p.W;
-      const size_t obase = (((size_t)b * p.H + y) * p.W + x) * p.Cout;
-      for (int col0 = 0; col0 < c.nt; col0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * c.nt + col0), r);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j >= c.nt) break;     // nt is a multiple of 16, not necessarily of 32
-            const int n = n_lo + col0 + j;
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
-            if (p.bias) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-            if (tembp) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(tembp + n));
-              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-            if (p.res) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(p.res + obase + n));
-              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-            v.x *= p.out_scale; v.y *= p.out_scale; v.z *= p.out_scale; v.w *= p.out_scale;
-            *reinterpret_cast<float4*>(p.out + obase + n) = v;
-          }
-        }
-      }
-    }
-  } else if (warp == 4) {
-    // =================================== weight producer ================================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int si = 0; si < p.nseg; ++si) {
-        const ConvSeg s = p.seg[si];
-        const int nq = ((s.C0 + s.C1) >> 4) * s.taps;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)n_lo * 32;
-        const size_t q_stride = (size_t)64 * p.Cout;      // hi image (32*Cout bytes) then lo image
-        for (int q = 0; q < nq; ++q) {
-          mbar_wait(w_empty(stage), phase ^ 1);
-          const uint32_t dst = w_base + stage * c.w_stage;
-          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-          bulk_g2s(dst, base + q * q_stride, (uint32_t)c.w_half, w_full(stage));
-          bulk_g2s(dst + c.w_half, base + q * q_stride + (size_t)32 * p.Cout, (uint32_t)c.w_half, w_full(stage));
-          if (++stage == c.sw) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    // =================================== MMA issuer =====================================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(c.nt);
-      const uint32_t lbo_a = (uint32_t)c.np * 16u, sbo_a = (uint32_t)c.hx * 16u;
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0;
-      bool first = true;
-      for (int si = 0; si < p.nseg; ++si) {
-        const ConvSeg s = p.seg[si];
-        const int nch = (s.C0 + s.C1) >> 4;
-        for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(a_full(sa), pa);
-          tc_fence_after();
-          const uint32_t a_st = a_base + sa * c.a_stage;
-          for (int tap = 0; tap < s.taps; ++tap) {
-            const int dy = s.taps == 9 ? tap / 3 : 1, dx = s.taps == 9 ? tap - 3 * (tap / 3) : 1;
-            mbar_wait(w_full(sw), pw);
-            tc_fence_after();
-            const uint32_t w_st = w_base + sw * c.w_stage;
-            const uint64_t b_hi = make_desc(w_st, 128, 256);
-            const uint64_t b_lo = make_desc(w_st + c.w_half, 128, 256);
-            for (int sub = 0; sub < c.nsub; ++sub) {
-              const uint32_t a_addr = a_st + (uint32_t)(dy * c.hx + dx + 8 * sub) * 16u;
-              const uint64_t a_hi = make_desc(a_addr, lbo_a, sbo_a);
-              const uint64_t a_lo = make_desc(a_addr + c.a_half, lbo_a, sbo_a);
-              const uint32_t d = tmem_base + (uint32_t)(sub * c.nt);
-              umma_bf16(d, a_hi, b_hi, idesc, first ? 0u : 1u);
-              umma_bf16(d, a_lo, b_hi, idesc, 1u);
-              umma_bf16(d, a_hi, b_lo, idesc, 1u);
-            }
-            first = false;
-            umma_commit(w_empty(sw));       // frees the weight stage when these MMAs retire
-            if (++sw == c.sw) { sw = 0; pw ^= 1; }
-          }
-          umma_commit(a_empty(sa));         // frees the activation stage
-          if (++sa == c.sa) { sa = 0; pa ^= 1; }
-        }
-      }
-      umma_commit(acc_full);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
-}
-
 // ---- weight packing ------------------------------------------------------------------------------------
-// out: for q = chunk*taps + tap: [hi image][lo image], image byte offset of element (n, k):
-//      (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
+// out: for q = chunk*taps + tap: [hi image][lo image], each image Mpad rows (Cout rounded up to a multiple of 128,
+// zero rows beyond Cout); byte offset of element (n, k) inside an image: (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
+__host__ __device__ inline int tc_mpad(int Cout) { return (Cout + 127) / 128 * 128; }
+
 __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout) {
+  const int Mpad = tc_mpad(Cout);
   const size_t total = (size_t)(Cin / 16) * taps * Cout * 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = i % 16;
@@ -367,71 +151,29 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const size_t img = (size_t)(n / 8) * 128 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);     // in 2-byte units
-    uint16_t* base = out + q * (size_t)32 * Cout;                                          // 64*Cout bytes per q
+    uint16_t* base = out + q * (size_t)32 * Mpad;                                          // 64*Mpad bytes per q
     base[img] = __bfloat16_as_ushort(hi);
-    base[(size_t)16 * Cout + img] = __bfloat16_as_ushort(lo);
+    base[(size_t)16 * Mpad + img] = __bfloat16_as_ushort(lo);
   }
 }
 
-bool shape_ok(int Cout, int Cin) { return Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && Cin % 16 == 0 && Cin >= 16; }
+bool shape_ok(int Cout, int Cin) { return Cout >= 1 && Cout <= 256 && Cin % 16 == 0 && Cin >= 16; }
 
 int pack_common(const float* w, int Cout, int Cin, int taps, int io, void** out, std::vector<void*>* owned, cudaStream_t st) {
   *out = nullptr;
   if (!shape_ok(Cout, Cin)) return 0;
-  const size_t bytes = (size_t)(Cin / 16) * taps * 64 * Cout;
+  const size_t bytes = (size_t)(Cin / 16) * taps * 64 * tc_mpad(Cout);
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) return fail(-4, std::string("tc_pack: cudaMalloc failed: ") + cudaGetErrorString(e));
   if (owned) owned->push_back(p);
+  STORM_CUDA_TRY(cudaMemsetAsync(p, 0, bytes, st));
   const size_t total = (size_t)(Cin / 16) * taps * Cout * 16;
   tc_pack_kernel<<<(unsigned)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256), 256, 0, st>>>(w, (uint16_t*)p, Cout, Cin, taps, io);
   STORM_LAUNCH_CHECK();
   *out = p;
   return 0;
 }
-
-bool choose_cfg(const ConvParams& p, TcCfg& c) {
-  if (p.Cout % 16 != 0 || p.Cout < 16 || p.Cout > 256) return false;
-  for (int i = 0; i < p.nseg; ++i) {
-    const ConvSeg& s = p.seg[i];
-    if (!s.wtc || s.C0 % 16 != 0 || s.C1 % 16 != 0 || s.C0 < 16 || (s.taps != 9 && s.taps != 1)) return false;
-  }
-  const int tiles_y = ceil_div(p.H, 16);
-  int best_ns = 0, best_split = 0;
-  long best_ctas = -1;
-  bool found_full = false;
-  // candidates from the largest tile down; take the first that fills the chip, else the one with most CTAs
-  for (int nsplit = 1; nsplit <= 2 && !found_full; ++nsplit) {
-    if (p.Cout % nsplit) continue;
-    const int nt = p.Cout / nsplit;
-    if (nt % 16 != 0 || nt < 16) continue;
-    if (nsplit == 2 && nt < 64) continue;
-    for (int ns = 4; ns >= 1; ns >>= 1) {
-      if (ns * nt > 512) continue;
-      if (ns > 1 && 8 * (ns / 2) >= p.W) continue;   // do not widen the tile beyond the image
-      const long ctas = (long)tiles_y * ceil_div(p.W, 8 * ns) * nsplit * p.B;
-      if (ctas > best_ctas) { best_ctas = ctas; best_ns = ns; best_split = nsplit; }
-      if (ctas >= 132) { best_ns = ns; best_split = nsplit; found_full = true; break; }
-    }
-  }
-  if (best_ns == 0) return false;
-  c.nsub = best_ns;
-  c.nsplit = best_split;
-  c.nt = p.Cout / best_split;
-  c.hx = 8 * c.nsub + 2;
-  c.np = HY * c.hx;
-  c.a_half = 2 * c.np * 16;
-  c.a_stage = 2 * c.a_half;
-  c.w_half = 32 * c.nt;
-  c.w_stage = 64 * c.nt;
-  c.sa = c.a_stage <= 24 * 1024 ? 3 : 2;
-  int sw = (SMEM_BUDGET - c.sa * c.a_stage - 256) / c.w_stage;
-  c.sw = sw > 8 ? 8 : sw;
-  if (c.sw < 2) return false;
-  c.tiles_x = ceil_div(p.W, 8 * c.nsub);
-  return true;
-}
-
 
 // =====================================================================================================
 // Mode P ("pixels as N"): D[cout, pixel].  A operand = weight image (M = 128 output channels),
@@ -548,7 +290,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
   const int tile = blockIdx.x;
   const int ty0 = (tile / c.tiles_x) * c.rows;
   const int tx0 = (tile % c.tiles_x) * 8 * c.npt;
-  const int m_lo = blockIdx.y * 128 * c.nmb;       // first output channel of this CTA
+  const int m_lo = blockIdx.y * 128 * c.nmb;       // first output channel (row of the padded weight image) of this CTA
+  const int Mpad = tc_mpad(p.Cout);
   const int b = blockIdx.z;
 
   if (tid == 0) {
@@ -691,9 +434,10 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
       const int cout = m_lo + mb * 128 + q * 32 + lane;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
+      const bool cok = cout < p.Cout;                // rows beyond Cout are zero padding of the weight image
       float add = 0.f;
-      if (p.bias) add += __ldg(p.bias + cout);
-      if (tembp) add += __ldg(tembp + cout);
+      if (p.bias && cok) add += __ldg(p.bias + cout);
+      if (tembp && cok) add += __ldg(tembp + cout);
       float fs = 0.f, fq = 0.f;
       float rv[32];
       if (p.res) {     // issue every residual load of the unit before consuming any
@@ -701,14 +445,14 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         for (int jj = 0; jj < 32; ++jj) {
           const int y = ty0 + g32 * 4 + (jj >> 3);
           const int x = tx0 + 8 * pt + (jj & 7);
-          rv[jj] = (y < p.H && x < p.W) ? __ldg(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout) : 0.f;
+          rv[jj] = (cok && y < p.H && x < p.W) ? __ldg(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout) : 0.f;
         }
       }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
         const int y = ty0 + g32 * 4 + (jj >> 3);
         const int x = tx0 + 8 * pt + (jj & 7);
-        if (y < p.H && x < p.W) {
+        if (cok && y < p.H && x < p.W) {
           const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
           float v = __uint_as_float(r[jj]) + add;
           if (p.res) v += rv[jj];
@@ -726,6 +470,7 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
       const int chunk = tile * 2 + grp;
       for (int mb = 0; mb < c.nmb; ++mb) {
         const int cout = m_lo + mb * 128 + q * 32 + lane;
+        if (cout >= p.Cout) continue;
         double* o = p.stats_out + (((size_t)b * p.stats_chunks + chunk) * p.Cout + cout) * 2;
         o[0] = s_sum[mb];
         o[1] = s_sq[mb];
@@ -744,13 +489,13 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         const ConvSeg s = p.seg[si];
         const int nq = ((s.C0 + s.C1) >> 4) * s.taps;
         const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32;
-        const size_t q_stride = (size_t)64 * p.Cout;
+        const size_t q_stride = (size_t)64 * Mpad;
         for (int qq = 0; qq < nq; ++qq) {
           mbar_wait(w_empty(stage), phase ^ 1);
           const uint32_t dst = w_base + stage * c.w_stage;
           mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
           bulk_g2s(dst, base + qq * q_stride, (uint32_t)c.w_half, w_full(stage));
-          bulk_g2s(dst + c.w_half, base + qq * q_stride + (size_t)32 * p.Cout, (uint32_t)c.w_half, w_full(stage));
+          bulk_g2s(dst + c.w_half, base + qq * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
           if (++stage == c.sw) { stage = 0; phase ^= 1; }
         }
       }
@@ -772,7 +517,7 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
 int g_tc_force_per_sm = 0;   // 0 = heuristic, 1 / 2 = force (STORM_B200_TC_PER_SM, tools only)
 
 bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
-  if (p.Cout % 128 != 0 || p.Cout < 128 || p.Cout > 256) return false;
+  if (p.Cout < 1 || p.Cout > 256) return false;
   for (int i = 0; i < p.nseg; ++i) {
     const ConvSeg& s = p.seg[i];
     if (!s.wtc || s.C0 % 16 != 0 || s.C1 % 16 != 0 || s.C0 < 16 || (s.taps != 9 && s.taps != 1)) return false;
@@ -783,7 +528,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     if (e) g_tc_force_per_sm = atoi(e);
     env_read = true;
   }
-  const int nblk = p.Cout / 128;
+  const int nblk = tc_mpad(p.Cout) / 128;
   // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
   // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).
   struct Cand { int rows, npt, nmb, per_sm; };
@@ -830,9 +575,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
 
 bool conv_tc_eligible(const ConvParams& p) {
   TcpCfg cp;
-  if (choose_cfg_p(p, cp)) return true;
-  TcCfg c;
-  return choose_cfg(p, c);
+  return choose_cfg_p(p, cp);
 }
 
 int conv_tc_stats_chunks(const ConvParams& p) {
@@ -844,27 +587,17 @@ int conv_tc_stats_chunks(const ConvParams& p) {
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    STORM_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
     STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
     attr = true;
   }
   TcpCfg cp;
-  if (choose_cfg_p(p, cp)) {
-    if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
-    const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
-    dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-    if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
-    else conv_tcp_kernel<3, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
-    STORM_LAUNCH_CHECK();
-    return 0;
-  }
-  if (p.stats_out) return fail(-1, "conv_tc: GroupNorm partial sums are only emitted by mode P");
-  TcCfg c;
-  if (!choose_cfg(p, c)) return fail(-1, "conv_tc: shape not eligible");
-  const int smem = c.sa * c.a_stage + c.sw * c.w_stage + 8 * (2 * c.sa + 2 * c.sw + 1) + 16;
-  dim3 grid(c.tiles_x * ceil_div(p.H, 16), c.nsplit, p.B);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, c);
+  if (!choose_cfg_p(p, cp)) return fail(-1, "conv_tc: shape not eligible");
+  if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+  const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
+  dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
+  if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
+  else conv_tcp_kernel<3, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
   STORM_LAUNCH_CHECK();
   return 0;
 }

@@ -341,7 +341,7 @@ static int repack(StormHandle* h, cudaStream_t st) {
       STORM_CUDA_TRY(cudaMemcpy2DAsync(s.w, 8 * sizeof(float), tmp, m.out_ch * sizeof(float), m.out_ch * sizeof(float),
                                        (size_t)9 * m.in_ch, cudaMemcpyDeviceToDevice, st));
       if (use_tc) {   // tensor-core route: 1x1 GEMM onto 9*Co tap-partials (see launch_tap_gather)
-        s.npad = (9 * m.out_ch + 15) / 16 * 16;
+        s.npad = 9 * m.out_ch;     // the tcgen05 kernel takes any Cout <= 256 (weight rows are zero-padded to 128)
         float* wz = nullptr;
         STORM_TRY(dev_alloc(h, (size_t)m.in_ch * s.npad, &wz));
         LAUNCH(h, launch_pack_convout_gemm(h->P(p + ".weight"), wz, m.out_ch, m.in_ch, s.npad, st));
