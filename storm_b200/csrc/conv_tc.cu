@@ -200,6 +200,29 @@ struct TcpCfg {
   int per_sm;          // CTAs per SM this config is built for (1 or 2)
 };
 
+// K-chunk schedule shared by the three roles.  With a 1x1 skip segment (seg 1) its chunks are interleaved with the
+// 3x3 chunks of seg 0: each 1x1 chunk carries 9x less MMA work per staged activation, so a contiguous run of them
+// starves the tensor core while the producers wait on memory; interleaved, their latency hides behind 3x3 MMAs.
+struct ChunkIter {
+  int n0, n1, g, k, kend;
+  bool skip_phase;
+  __device__ ChunkIter(const ConvParams& p)
+      : n0((p.seg[0].C0 + p.seg[0].C1) >> 4), n1(p.nseg == 2 ? (p.seg[1].C0 + p.seg[1].C1) >> 4 : 0), g(0), k(0), kend(0),
+        skip_phase(false) {}
+  __device__ bool next(int& si, int& ch) {
+    if (skip_phase) {
+      if (k < kend) { si = 1; ch = k++; return true; }
+      skip_phase = false;
+      ++g;
+    }
+    if (g >= n0) return false;
+    si = 0; ch = g;
+    kend = (int)(((long)(g + 1) * n1) / n0);
+    skip_phase = true;
+    return true;
+  }
+};
+
 // Single-thread MMA issue loop of mode P.  The tensor core needs one tcgen05.mma every N/2 cycles, so the
 // loop is kept lean: descriptor high words are per-CTA constants, the low words are (address >> 4) sums, and
 // the (pixel tile, M block, hi/lo) combinations are unrolled at compile time.
@@ -219,10 +242,11 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   uint32_t acc = 0;
   const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long t_wa = 0, t_ww = 0, t_start = dbg ? clock64() : 0;
-  for (int si = 0; si < p.nseg; ++si) {
-    const int nch = (p.seg[si].C0 + p.seg[si].C1) >> 4;
-    const bool k3 = p.seg[si].taps == 9;
-    for (int ch = 0; ch < nch; ++ch) {
+  ChunkIter it(p);
+  int si, ch;
+  while (it.next(si, ch)) {
+    {
+      const bool k3 = p.seg[si].taps == 9;
       long long t0 = dbg ? clock64() : 0;
       mbar_wait(bar_base + 8u * sa, pa);                                   // a_full
       if (dbg) t_wa += clock64() - t0;
@@ -331,11 +355,14 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
       }
     }
-    for (int si = 0; si < p.nseg; ++si) {
-      const ConvSeg s = p.seg[si];
+    ChunkIter it(p);
+    int si, chk;
+    while (it.next(si, chk)) {
+      const ConvSeg& s = p.seg[si];
       const int C = s.C0 + s.C1;
       const bool full_halo = s.taps == 9;
-      for (int c0 = 0; c0 < C; c0 += 16) {
+      {
+        const int c0 = chk * 16;
         const float* src;
         int Cs, cl;
         if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
@@ -349,18 +376,17 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
             for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
           }
         }
-        // ---- L2 prefetch of the next chunk (same segment) or the first chunk of the next segment
+        // ---- L2 prefetch of the next chunk in schedule order
         {
-          const float* nsrc = nullptr;
-          int nCs = 0, ncl = 0;
-          bool nfull = full_halo;
-          const int n0 = c0 + 16;
-          if (n0 < C) {
-            if (n0 < s.C0) { nsrc = s.src0; nCs = s.C0; ncl = n0; } else { nsrc = s.src1; nCs = s.C1; ncl = n0 - s.C0; }
-          } else if (si + 1 < p.nseg) {
-            nsrc = p.seg[si + 1].src0; nCs = p.seg[si + 1].C0; ncl = 0; nfull = p.seg[si + 1].taps == 9;
-          }
-          if (nsrc) {
+          ChunkIter peek = it;
+          int nsi, nch;
+          if (peek.next(nsi, nch)) {
+            const ConvSeg& ns = p.seg[nsi];
+            const int n0c = nch * 16;
+            const float* nsrc;
+            int nCs, ncl;
+            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+            const bool nfull = ns.taps == 9;
 #pragma unroll
             for (int i = 0; i < MAXU; ++i)
               if (upix[i] >= 0 && (nfull || uinterior[i]))
@@ -485,17 +511,18 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int si = 0; si < p.nseg; ++si) {
-        const ConvSeg s = p.seg[si];
-        const int nq = ((s.C0 + s.C1) >> 4) * s.taps;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32;
-        const size_t q_stride = (size_t)64 * Mpad;
-        for (int qq = 0; qq < nq; ++qq) {
+      const size_t q_stride = (size_t)64 * Mpad;
+      ChunkIter it(p);
+      int si, ch;
+      while (it.next(si, ch)) {
+        const ConvSeg& s = p.seg[si];
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32 + (size_t)ch * s.taps * q_stride;
+        for (int tap = 0; tap < s.taps; ++tap) {
           mbar_wait(w_empty(stage), phase ^ 1);
           const uint32_t dst = w_base + stage * c.w_stage;
           mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-          bulk_g2s(dst, base + qq * q_stride, (uint32_t)c.w_half, w_full(stage));
-          bulk_g2s(dst + c.w_half, base + qq * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
+          bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_half, w_full(stage));
+          bulk_g2s(dst + c.w_half, base + tap * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
           if (++stage == c.sw) { stage = 0; phase ^= 1; }
         }
       }
