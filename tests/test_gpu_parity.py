@@ -239,3 +239,76 @@ def test_full_size_properties():
     assert torch.isfinite(torch.view_as_real(y)).all()
     y_sw = m(x.flip(0), t.flip(0))
     assert torch.equal(y_sw.flip(0), y)
+
+
+def _synth_Y(B, L):
+    from storm_b200 import _native
+    y = torch.stack([O.synth_utterance(b, L) for b in range(B)]).cuda()
+    sp = _native.make_spec_config()
+    norm = _native.wave_norm(y)
+    T_pad = _native.padded_frames(_native.num_frames(L, sp))
+    return y, norm, _native.stft(y, norm, sp, T_pad).unsqueeze(1)
+
+
+def test_baseline_shape_single_nfe_vs_oracle():
+    """BASELINE configs[1] shape (32640 samples -> 256x256, full-width ncsnpp): one network evaluation and one
+    whole PC step (2 NFE, Philox noise replayed into the oracle) against the CPU oracle."""
+    from storm_b200 import _native, ncsnpp_spec
+    m = _model("ncsnpp")
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=0, init_scale=1.0, bias_std=0.05)
+    m.load_state_dict(sd)
+    _, _, Y = _synth_Y(1, 32640)
+    assert tuple(Y.shape) == (1, 1, 256, 256)
+    t = torch.tensor([0.7], device="cuda")
+    x = Y + 0.1 * torch.view_as_complex(torch.randn(1, 1, 256, 256, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)))
+    d = m(torch.cat([x, Y], dim=1), t)
+    torch.set_num_threads(min(32, len(__import__("os").sched_getaffinity(0))))
+    do = O.ncsnpp_forward(sd, O.NetCfg(), torch.cat([x, Y], dim=1).cpu(), t.cpu())
+    e1 = rel_l2(d.cpu(), do)
+    print(f"256x256 single NFE rel-L2 vs oracle = {e1:.3e}")
+    assert e1 < TOL
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 1, 1, 0.5, 0.03)
+    X, nfe = m.engine().pc_sample(Y, sc, seed=11, utt_ids=[5])
+    n = Y[0].numel()
+    it = iter([_native.philox_normal(11, 5, dr, n).reshape(1, 1, 256, 256).cpu() for dr in range(3)])
+    Xo, _ = O.pc_sample(O.make_score_fn(sd, O.NetCfg()), Y.cpu(), O.OUVE(), 1, noise=lambda z: next(it))
+    e2 = rel_l2(X.cpu(), Xo)
+    print(f"256x256 one PC step rel-L2 vs oracle = {e2:.3e}")
+    assert nfe == 2 and e2 < TOL
+
+
+def test_trajectory_vs_oracle_and_sampler_sweep():
+    """N-step trajectories (config 5 sweep at reduced size): PC vs fixed-step probability-flow, several N, against the
+    oracle with replayed Philox noise; the error must not grow with N beyond the tolerance."""
+    from storm_b200 import _native, ncsnpp_spec
+    m = _model("ncsnpp")
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=0, init_scale=1.0, bias_std=0.05)
+    m.load_state_dict(sd)
+    _, _, Y = _synth_Y(2, 8000)          # 63 frames -> padded 64: [2,1,256,64]
+    n = Y[0].numel()
+    score = O.make_score_fn(sd, O.NetCfg())
+    for N, pf, corr in [(4, False, "ald"), (8, False, "ald"), (6, True, "none")]:
+        sc = _native.make_sampler_config("reverse_diffusion", corr, N, 1, 0.5, 0.03, probability_flow=pf)
+        X, nfe = m.engine().pc_sample(Y, sc, seed=77, utt_ids=[0, 1])
+        nd = 1 + N * ((1 if corr != "none" else 0) + 1)
+        draws = [torch.stack([_native.philox_normal(77, u, dr, n).reshape(Y.shape[1:]) for u in (0, 1)]).cpu() for dr in range(nd)]
+        it = iter(draws)
+        Xo, nfeo = O.pc_sample(score, Y.cpu(), O.OUVE(), N, corrector=corr, noise=lambda z: next(it), probability_flow_discretize=pf)
+        err = rel_l2(X.cpu(), Xo)
+        print(f"N={N} pf={pf} corrector={corr}: nfe={nfe} rel-L2 vs oracle = {err:.3e}")
+        assert nfe == nfeo and err < TOL
+
+
+def test_ncsnpplarge_8s_shape_runs():
+    """Config 4 shape: 128000 samples -> 1001 frames -> padded 1024; ncsnpplarge, one PC step, finite output and
+    bit-exact independence from batch composition."""
+    from storm_b200 import _native, ncsnpp_spec
+    m = _model("ncsnpplarge")
+    m.load_state_dict(ncsnpp_spec.random_state_dict(m.cfg, seed=1, init_scale=1.0))
+    _, _, Y = _synth_Y(2, 128000)
+    assert tuple(Y.shape) == (2, 1, 256, 1024)
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 1, 1, 0.5, 0.03)
+    X, nfe = m.engine().pc_sample(Y, sc, seed=3, utt_ids=[0, 1])
+    assert nfe == 2 and torch.isfinite(torch.view_as_real(X)).all()
+    X1, _ = m.engine().pc_sample(Y[1:2], sc, seed=3, utt_ids=[1])
+    assert torch.equal(X1[0], X[1])
