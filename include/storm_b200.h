@@ -194,6 +194,12 @@ int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int
                            const float* bias, const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W,
                            long long* dbg_dev, float* ms_out, void* stream);
 
+/* Test hook: single-head attention o = softmax(q k^T / sqrt(C)) v on [B][N][C] fp32 device tensors
+ * (AttnBlockpp core, layerspp.py:82-86).  engine 0 = tcgen05 kernel (v must be given channel-major [B][C][N]),
+ * 1 = SIMT kernel (v token-major [B][N][C]). */
+int storm_debug_attention(int32_t engine, const float* q, const float* k, const float* v, float* o, int32_t B, int32_t N, int32_t C,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,8 @@ _PROTOS = {
     "storm_debug_conv_timed": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                          C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
+    "storm_debug_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p]),
     "storm_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "storm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -382,6 +384,16 @@ def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=Non
                                   w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias), _ptr(res),
                                   float(out_scale), out.data_ptr(), B, H, W, _stream()))
     return out
+
+
+def debug_attention(engine: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Test hook: q, k, v [B, N, C] fp32 CUDA; the tcgen05 kernel is handed v channel-major as the engine does."""
+    q, k, v = _cf(q, "q"), _cf(k, "k"), _cf(v, "v")
+    B, N, Cc = q.shape
+    o = torch.empty_like(q)
+    vv = v.transpose(1, 2).contiguous() if engine == 0 else v
+    _check(lib().storm_debug_attention(engine, q.data_ptr(), k.data_ptr(), vv.data_ptr(), o.data_ptr(), B, N, Cc, _stream()))
+    return o
 
 
 def philox_normal(seed: int, utt_id: int, draw: int, n: int) -> torch.Tensor:

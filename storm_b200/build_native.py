@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["engine.cu", "kernels_small.cu", "conv_simt.cu", "conv_tc.cu"]
+SOURCES = ["engine.cu", "kernels_small.cu", "conv_simt.cu", "conv_tc.cu", "attn_tc.cu"]
 LIB = os.path.join(HERE, "libstorm_b200.so")
 STAMP = os.path.join(HERE, ".libstorm_b200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

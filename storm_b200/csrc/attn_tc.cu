@@ -1,0 +1,322 @@
+// tcgen05 single-head attention for AttnBlockpp (sgmse/backbones/ncsnpp_utils/layerspp.py:75-91):
+//   O[q, :] = softmax_k( Q[q,:].K[k,:] / sqrt(C) ) V[k, :]      (the path's one dense contraction)
+// q, k: [B][N][C] fp32 (token-major), vT: [B][C][N] fp32 (channel-major, written that way by the V projection's
+// epilogue so that both GEMMs see K-major operands), o: [B][N][C] fp32.  N % 128 == 0, C % 16 == 0, C <= 256.
+//
+// One CTA = one batch element x 128 queries.  Both GEMMs run on the tensor core with the bf16x3 split
+// (fp32-grade): S = Q K^T accumulates in TMEM columns [0,128), O = P V in columns [256, 256+C).
+// Two passes over the keys instead of online rescaling of the TMEM accumulator:
+//   pass 1: S~ = Qhi Khi^T only (1/3 of the MMAs) -> per-row shift m (softmax is shift invariant, the bf16 error of
+//           m is irrelevant); pass 2: exact S, P = exp((S - m)/sqrt(C)) written as bf16 hi/lo K-major tiles to
+//           shared memory, O += P V, l += row sums; finally O / l.
+// Warp roles: 0-3 softmax + epilogue (TMEM lane = query row), 4-7 operand producers (fp32 -> bf16 hi/lo,
+// no-swizzle K-major core-matrix layout), 8 TMEM alloc + single-thread MMA issue.
+#include <cuda_bf16.h>
+
+#include "kernels.cuh"
+
+namespace storm {
+
+namespace {
+
+constexpr int A_THREADS = 288;
+constexpr int TQ = 128, TK = 128;         // queries per CTA, keys per tile
+constexpr int SQ = 4, SV = 3;             // ring depths
+constexpr int QK_STAGE = 16 * 1024;       // Q chunk hi/lo (2 x 4 KB) + K chunk hi/lo (2 x 4 KB)
+constexpr int V_STAGE_MAX = 16 * 1024;    // V chunk: C rows x 16 keys x hi/lo
+constexpr int P_BYTES = 64 * 1024;        // P tile 128 x 128, hi + lo
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 8000000000LL) __trap();     // bounded: a protocol bug traps instead of hanging the GPU
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a),
+               "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, no swizzle: 8 rows x 16 B core matrices; SBO = stride between 8-row groups, LBO = between k-cores
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {   // D f32, A/B bf16, K-major, M = 128
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, float& rb) {
+  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  ra = a - __bfloat162float(ha);
+  rb = b - __bfloat162float(hb);
+  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16 consecutive fp32 (one row of a 16-wide K chunk) -> bf16 hi/lo, written as the two k-cores of row `row` of an
+// operand block with `rows` rows: hi plane at base, lo plane at base + plane; k-core stride = rows * 16 bytes
+__device__ __forceinline__ void stage_row16(const float* __restrict__ src, uint32_t base, uint32_t plane, int rows, int row) {
+  const float4* gp = reinterpret_cast<const float4*>(src);
+  float4 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = __ldg(gp + j);
+#pragma unroll
+  for (int kh = 0; kh < 2; ++kh) {
+    const float4 a = v[2 * kh], c = v[2 * kh + 1];
+    float r[8];
+    uint4 hi, lo;
+    hi.x = pack_bf16x2(a.x, a.y, r[0], r[1]);
+    hi.y = pack_bf16x2(a.z, a.w, r[2], r[3]);
+    hi.z = pack_bf16x2(c.x, c.y, r[4], r[5]);
+    hi.w = pack_bf16x2(c.z, c.w, r[6], r[7]);
+    float d0, d1;
+    lo.x = pack_bf16x2(r[0], r[1], d0, d1);
+    lo.y = pack_bf16x2(r[2], r[3], d0, d1);
+    lo.z = pack_bf16x2(r[4], r[5], d0, d1);
+    lo.w = pack_bf16x2(r[6], r[7], d0, d1);
+    const uint32_t off = base + (uint32_t)(kh * rows + row) * 16u;
+    st_shared_v4(off, hi);
+    st_shared_v4(off + plane, lo);
+  }
+}
+
+__global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                              const float* __restrict__ vT, float* __restrict__ o, int N, int C,
+                                                              float scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int NC = C >> 4, NT = N / TK;
+  const int v_plane = C * 32;                 // bytes of one V plane (hi or lo): 2 k-cores x C rows x 16 B
+  const int v_stage = 2 * v_plane;
+  const uint32_t qk_base = smem_u32(smem);
+  const uint32_t v_base = qk_base + SQ * QK_STAGE;
+  const uint32_t p_base = v_base + SV * V_STAGE_MAX;
+  const uint32_t bar_base = p_base + P_BYTES;
+  auto qk_full = [&](int i) { return bar_base + 8u * i; };
+  auto qk_empty = [&](int i) { return bar_base + 8u * (SQ + i); };
+  auto v_full = [&](int i) { return bar_base + 8u * (2 * SQ + i); };
+  auto v_empty = [&](int i) { return bar_base + 8u * (2 * SQ + SV + i); };
+  const uint32_t s_full = bar_base + 8u * (2 * SQ + 2 * SV), s_empty = s_full + 8, p_full = s_full + 16, p_empty = s_full + 24,
+                 o_full = s_full + 32, tmem_slot = s_full + 40;
+  if (tid == 0) {
+    for (int i = 0; i < SQ; ++i) { mbar_init(qk_full(i), 128); mbar_init(qk_empty(i), 1); }
+    for (int i = 0; i < SV; ++i) { mbar_init(v_full(i), 128); mbar_init(v_empty(i), 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 128); mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+  const uint32_t tm_s = tmem, tm_o = tmem + 256;
+
+  if (warp < 4) {
+    // =================================== softmax / epilogue ============================================
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int row = warp * 32 + lane;            // query row inside the tile
+    uint32_t ns = 0, np = 0;
+    float m = -INFINITY;
+    for (int t = 0; t < NT; ++t) {               // pass 1: row shift
+      mbar_wait(s_full, ns & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < TK / 32; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tm_s + lane_addr + g * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      ++ns;
+    }
+    float l = 0.f;
+    for (int t = 0; t < NT; ++t) {               // pass 2: P tiles
+      mbar_wait(s_full, ns & 1);
+      tc_fence_after();
+      mbar_wait(p_empty, (np & 1) ^ 1);          // previous P tile consumed by its MMAs
+#pragma unroll 1
+      for (int g = 0; g < TK / 32; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tm_s + lane_addr + g * 32, r);
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = expf((__uint_as_float(r[j]) - m) * scale);
+          l += pv[j];
+        }
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {         // 8 keys = one k-core row of this query
+          float rr[8];
+          uint4 hi, lo;
+          hi.x = pack_bf16x2(pv[kg * 8 + 0], pv[kg * 8 + 1], rr[0], rr[1]);
+          hi.y = pack_bf16x2(pv[kg * 8 + 2], pv[kg * 8 + 3], rr[2], rr[3]);
+          hi.z = pack_bf16x2(pv[kg * 8 + 4], pv[kg * 8 + 5], rr[4], rr[5]);
+          hi.w = pack_bf16x2(pv[kg * 8 + 6], pv[kg * 8 + 7], rr[6], rr[7]);
+          float d0, d1;
+          lo.x = pack_bf16x2(rr[0], rr[1], d0, d1);
+          lo.y = pack_bf16x2(rr[2], rr[3], d0, d1);
+          lo.z = pack_bf16x2(rr[4], rr[5], d0, d1);
+          lo.w = pack_bf16x2(rr[6], rr[7], d0, d1);
+          const uint32_t off = p_base + (uint32_t)((g * 4 + kg) * TQ + row) * 16u;   // [k-core][row][16 B]
+          st_shared_v4(off, hi);
+          st_shared_v4(off + P_BYTES / 2, lo);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      fence_async_shared();
+      mbar_arrive(p_full);
+      ++ns; ++np;
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    float* orow = o + ((size_t)b * N + q0 + row) * C;
+    for (int g = 0; g < C / 32 + ((C % 32) ? 1 : 0); ++g) {
+      uint32_t r[32];
+      tmem_ld32(tm_o + lane_addr + g * 32, r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (g * 32 + j >= C) break;
+        *reinterpret_cast<float4*>(orow + g * 32 + j) = make_float4(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv,
+                                                                     __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+      }
+    }
+  } else if (warp < 8) {
+    // =================================== producers ======================================================
+    const int pt = tid - 128;                    // 0..127
+    int sq = 0, sv = 0;
+    uint32_t pq = 0, pvp = 0;
+    const float* qrow = q + ((size_t)b * N + q0 + pt) * C;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < NT; ++t) {
+        const float* krow = k + ((size_t)b * N + t * TK + pt) * C;
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(qk_empty(sq), pq ^ 1);
+          const uint32_t st = qk_base + sq * QK_STAGE;
+          stage_row16(qrow + c * 16, st, 4096, TQ, pt);                 // Q: hi at +0, lo at +4096
+          stage_row16(krow + c * 16, st + 8192, 4096, TK, pt);          // K: hi at +8192, lo at +12288
+          fence_async_shared();
+          mbar_arrive(qk_full(sq));
+          if (++sq == SQ) { sq = 0; pq ^= 1; }
+        }
+        if (pass == 1) {
+          for (int ks = 0; ks < TK / 16; ++ks) {
+            mbar_wait(v_empty(sv), pvp ^ 1);
+            const uint32_t st = v_base + sv * V_STAGE_MAX;
+            for (int ch = pt; ch < C; ch += 128)
+              stage_row16(vT + ((size_t)b * C + ch) * N + t * TK + ks * 16, st, (uint32_t)v_plane, C, ch);
+            fence_async_shared();
+            mbar_arrive(v_full(sv));
+            if (++sv == SV) { sv = 0; pvp ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // =================================== MMA issuer =====================================================
+    const uint32_t idesc_s = make_idesc(TK), idesc_o = make_idesc(C);
+    int sq = 0, sv = 0;
+    uint32_t pq = 0, pvp = 0, ns = 0, np = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < NT; ++t) {
+        mbar_wait(s_empty, (ns & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(qk_full(sq), pq);
+          tc_fence_after();
+          const uint32_t st = qk_base + sq * QK_STAGE;
+          const uint64_t q_hi = make_desc(st, TQ * 16, 128), q_lo = make_desc(st + 4096, TQ * 16, 128);
+          const uint64_t k_hi = make_desc(st + 8192, TK * 16, 128), k_lo = make_desc(st + 12288, TK * 16, 128);
+          umma_bf16(tm_s, q_hi, k_hi, idesc_s, c > 0);
+          if (pass == 1) {
+            umma_bf16(tm_s, q_lo, k_hi, idesc_s, 1u);
+            umma_bf16(tm_s, q_hi, k_lo, idesc_s, 1u);
+          }
+          umma_commit(qk_empty(sq));
+          if (++sq == SQ) { sq = 0; pq ^= 1; }
+        }
+        umma_commit(s_full);
+        ++ns;
+        if (pass == 1) {
+          mbar_wait(p_full, np & 1);
+          tc_fence_after();
+          for (int ks = 0; ks < TK / 16; ++ks) {
+            mbar_wait(v_full(sv), pvp);
+            tc_fence_after();
+            const uint32_t st = v_base + sv * V_STAGE_MAX;
+            const uint32_t pa = p_base + (uint32_t)(2 * ks) * TQ * 16;
+            const uint64_t p_hi = make_desc(pa, TQ * 16, 128), p_lo = make_desc(pa + P_BYTES / 2, TQ * 16, 128);
+            const uint64_t v_hi = make_desc(st, (uint32_t)C * 16, 128), v_lo = make_desc(st + v_plane, (uint32_t)C * 16, 128);
+            umma_bf16(tm_o, p_hi, v_hi, idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(tm_o, p_lo, v_hi, idesc_o, 1u);
+            umma_bf16(tm_o, p_hi, v_lo, idesc_o, 1u);
+            umma_commit(v_empty(sv));
+            if (++sv == SV) { sv = 0; pvp ^= 1; }
+          }
+          umma_commit(p_empty);
+          ++np;
+        }
+      }
+    }
+    umma_commit(o_full);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+}  // namespace
+
+bool attention_tc_eligible(int N, int C) { return N >= TK && N % TK == 0 && C % 16 == 0 && C >= 16 && C <= 256; }
+
+int launch_attention_tc(const float* q, const float* k, const float* vT, float* o, int B, int N, int C, cudaStream_t st) {
+  if (!attention_tc_eligible(N, C)) return fail(-1, "attention_tc: shape not eligible");
+  const int smem = SQ * QK_STAGE + SV * V_STAGE_MAX + P_BYTES + 8 * (2 * SQ + 2 * SV + 5) + 16;
+  static bool attr = false;
+  if (!attr) {
+    STORM_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  attn_tc_kernel<<<dim3(N / TQ, B), A_THREADS, smem, st>>>(q, k, vT, o, N, C, 1.0f / sqrtf((float)C));
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace storm

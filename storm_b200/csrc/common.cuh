@@ -72,6 +72,7 @@ struct ConvParams {
   double* stats_out;       // optional GroupNorm partial sums of `out`: [B][stats_chunks][Cout][2] (tcgen05 mode P only)
   int stats_chunks;
   long long* dbg;          // optional [8] cycle counters written by CTA 0 (tools/conv_timeline.py)
+  int out_cm;              // 1: write `out` channel-major [B][Cout][H*W] (tcgen05 kernel only; attention V operand)
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);

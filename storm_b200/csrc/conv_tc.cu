@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         const int y = ty0 + g32 * 4 + (jj >> 3);
         const int x = tx0 + 8 * pt + (jj & 7);
         if (cok && y < p.H && x < p.W) {
-          const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
+          const size_t o = p.out_cm ? ((size_t)b * p.Cout + cout) * ((size_t)p.H * p.W) + (size_t)y * p.W + x
+                                    : (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
           float v = __uint_as_float(r[jj]) + add;
           if (p.res) v += rv[jj];
           v *= p.out_scale;
@@ -620,6 +621,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   }
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return fail(-1, "conv_tc: shape not eligible");
+  if (p.out_cm && p.res) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
   if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);

@@ -524,17 +524,23 @@ struct Fwd {
     Act q, k, v, o;
     STORM_TRY(alloc(q, x.H, x.W, C)); STORM_TRY(alloc(k, x.H, x.W, C)); STORM_TRY(alloc(v, x.H, x.W, C));
     Act* qkv[3] = {&q, &k, &v};
+    bool use_tc_attn = h->cfg.engine == 0 && attention_tc_eligible(N, C);
     for (int i = 0; i < 3; ++i) {
       ConvParams p{};
       p.nseg = 1;
       ConvSeg& s = p.seg[0];
       s.src0 = x.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = ss; s.silu = 0; s.taps = 1; s.w = a.w[i]; s.wtc = a.tc[i];
       p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[i]; p.out_scale = 1.0f; p.out = qkv[i]->p;
+      if (i == 2 && use_tc_attn) {
+        if (conv_tc_eligible(p)) p.out_cm = 1;     // V channel-major: K-major operand of the P.V tensor-core GEMM
+        else use_tc_attn = false;
+      }
       STORM_TRY(conv(p));
     }
     h->pool.put(ss);
     STORM_TRY(alloc(o, x.H, x.W, C));
-    LAUNCH(h, launch_attention_simt(q.p, k.p, v.p, o.p, B, N, C, st));
+    if (use_tc_attn) { LAUNCH(h, launch_attention_tc(q.p, k.p, v.p, o.p, B, N, C, st)); }
+    else { LAUNCH(h, launch_attention_simt(q.p, k.p, v.p, o.p, B, N, C, st)); }
     release(q); release(k); release(v);
     STORM_TRY(alloc(out, x.H, x.W, C));
     {
@@ -1105,6 +1111,22 @@ int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int
   cudaError_t e = cudaStreamSynchronize(st);
   for (void* q : owned) cudaFree(q);
   if (rc == 0 && e != cudaSuccess) return fail(STORM_E_CUDA, std::string("storm_debug_conv: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int storm_debug_attention(int32_t engine, const float* q, const float* k, const float* v, float* o, int32_t B, int32_t N, int32_t C,
+                          void* stream) {
+  if (!q || !k || !v || !o) return fail(STORM_E_INVALID, "storm_debug_attention: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (engine == 0) {
+    if (!attention_tc_eligible(N, C)) return fail(STORM_E_INVALID, "storm_debug_attention: shape not eligible for the tcgen05 kernel");
+    rc = launch_attention_tc(q, k, v, o, B, N, C, st);
+  } else {
+    rc = launch_attention_simt(q, k, v, o, B, N, C, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) return fail(STORM_E_CUDA, std::string("storm_debug_attention: ") + cudaGetErrorString(e));
   return rc;
 }
 

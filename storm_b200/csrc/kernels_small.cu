@@ -215,26 +215,34 @@ int launch_gn_partial(const Act& a, cudaStream_t st) {
   return 0;
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ part0, int C0, int nchunk0, const double* __restrict__ part1,
-                                   int C1, int nchunk1, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ ss, int HW, int G) {
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restrict__ part0, int C0, int nchunk0,
+                                                          const double* __restrict__ part1, int C1, int nchunk1,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ ss, int HW, int G) {
   const int g = blockIdx.x, b = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / G;
   double s = 0, q = 0;
+  // items = (chunk, channel-in-group) pairs; loads are issued in batches of 8 before being consumed so that the
+  // ~16 dependent round trips of the naive loop collapse into 2-3
+  auto item_ptr = [&](int i) -> const double2* {
+    const int cc = g * cpg + i % cpg;
+    const int ch = i / cpg;
+    if (cc < C0) return ch < nchunk0 ? reinterpret_cast<const double2*>(part0 + (((size_t)b * nchunk0 + ch) * C0 + cc) * 2) : nullptr;
+    return ch < nchunk1 ? reinterpret_cast<const double2*>(part1 + (((size_t)b * nchunk1 + ch) * C1 + (cc - C0)) * 2) : nullptr;
+  };
   const int maxchunk = max(nchunk0, nchunk1);
-  for (int i = threadIdx.x; i < cpg * maxchunk; i += blockDim.x) {
-    int cc = g * cpg + i % cpg;
-    int ch = i / cpg;
-    if (cc < C0) {
-      if (ch < nchunk0) {
-        const double* d = part0 + (((size_t)b * nchunk0 + ch) * C0 + cc) * 2;
-        s += d[0]; q += d[1];
-      }
-    } else if (ch < nchunk1) {
-      const double* d = part1 + (((size_t)b * nchunk1 + ch) * C1 + (cc - C0)) * 2;
-      s += d[0]; q += d[1];
+  const int nitems = cpg * maxchunk;
+  for (int i0 = threadIdx.x; i0 < nitems; i0 += 8 * blockDim.x) {
+    double2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * blockDim.x;
+      const double2* pp = i < nitems ? item_ptr(i) : nullptr;
+      v[j] = pp ? __ldg(pp) : make_double2(0.0, 0.0);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += v[j].x; q += v[j].y; }
   }
   __shared__ double rs[32], rq[32];
   s = warp_sum_d(s); q = warp_sum_d(q);

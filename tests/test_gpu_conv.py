@@ -69,3 +69,17 @@ def test_fused_conv(engine, case):
     print(f"engine={engine} case={case} rel-L2={err:.3e}")
     assert torch.isfinite(out).all()
     assert err < 2e-5
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("B,N,C", [(2, 1024, 256), (1, 2048, 256), (3, 128, 192), (2, 256, 64)])
+def test_attention_core(engine, B, N, C):
+    from storm_b200 import _native
+    g = torch.Generator(device="cuda").manual_seed(N + C)
+    q, k, v = (torch.randn(B, N, C, device="cuda", generator=g) * s for s in (1.5, 1.5, 1.0))
+    w = torch.softmax(torch.einsum("bqc,bkc->bqk", q.double(), k.double()) * C ** -0.5, dim=-1)
+    ref = torch.einsum("bqk,bkc->bqc", w, v.double()).float()
+    out = _native.debug_attention(engine, q, k, v)
+    err = _rel(out, ref)
+    print(f"attention engine={engine} B={B} N={N} C={C} rel-L2={err:.3e}")
+    assert torch.isfinite(out).all() and err < 2e-5
