@@ -37,10 +37,11 @@ def shard(files, rank, world):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.mode != "score-only":
-        raise NotImplementedError(f"--mode {args.mode}: only the score-only reverse-diffusion path is built (SURVEY.md section 8f)")
     import torchaudio
-    from storm_b200 import ScoreModel
+    from storm_b200 import ScoreModel, StochasticRegenerationModel
+    if args.mode == "denoiser-only" and not args.random_init and args.ckpt is None:
+        raise SystemExit("--ckpt is required")
+    model_cls = ScoreModel if args.mode == "score-only" else StochasticRegenerationModel   # enhancement.py:47-54
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -51,18 +52,20 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.makedirs(args.enhanced_dir, exist_ok=True)
     if args.ckpt:
-        model = ScoreModel.load_from_checkpoint(args.ckpt, base_dir="", batch_size=1, num_workers=0, kwargs=dict(gpu=False))
-    elif args.random_init:
+        model = model_cls.load_from_checkpoint(args.ckpt, base_dir="", batch_size=1, num_workers=0, kwargs=dict(gpu=False))
+    elif args.random_init and args.mode == "score-only":
         model = ScoreModel(backbone=args.random_init, sde="ouve", init_scale=1.0, seed=args.seed)
+    elif args.random_init:
+        model = StochasticRegenerationModel(backbone_denoiser=args.random_init, backbone_score=args.random_init, sde="ouve",
+                                            init_scale=1.0, seed=args.seed)
     else:
         raise SystemExit("--ckpt is required (or --random-init BACKBONE)")
     model.eval(no_ema=False)
     model.cuda()
-    if world > 1:   # identical weights everywhere: one broadcast of the flat blob
-        eng = model.dnn.engine()
-        dist.broadcast(eng.weights_view(), src=0)
-        torch.cuda.synchronize()
-        eng.repack()
+    if world > 1:   # identical weights everywhere: one broadcast of the flat blob per network
+        from storm_b200 import parallel
+        for net in ([model.dnn] if args.mode == "score-only" else model._nets()):
+            parallel.broadcast_weights(net, src=0)
 
     files = sorted(glob.glob(os.path.join(args.test_dir, "*.wav")))
     mine = [(i, f) for i, f in enumerate(files)][rank::world]
@@ -74,6 +77,12 @@ def main(argv=None):
         assert sr == model_sr, "You need to make sure sample_sr matches model_sr --> resample to 16kHz"
         loaded.append((idx, f, y[:1]))
     loaded.sort(key=lambda t: t[2].shape[1])
+    if args.mode != "score-only":      # StoRM / denoiser-only: one utterance per call like the reference (enhancement.py:66-72)
+        for idx, f, y in loaded:
+            x_hat = model.enhance(y, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
+                                  denoiser_only=(args.mode == "denoiser-only"))
+            torchaudio.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().unsqueeze(0), model_sr)
+        loaded = []
     i = 0
     while i < len(loaded):
         L = loaded[i][2].shape[1]

@@ -125,14 +125,17 @@ int storm_get_tap(StormHandle* h, const char* name, float* out_nchw, int64_t cap
                   int64_t shape[4], void* stream);
 
 /* ---- sampler --------------------------------------------------------------------------------------
- * pc_sampler (sgmse/sampling/__init__.py:54-66) with score = -dnn(cat[x, y], t) (sgmse/model.py:127-136).
- *   Y, X : complex [B][F][T];  cond: optional extra condition channel (StoRM's Y_denoised), or NULL.
+ * pc_sampler (sgmse/sampling/__init__.py:54-66) with score = -dnn(cat[x, cond...], t) (sgmse/model.py:127-136).
+ *   Y, X : complex [B][F][T].  Y is the SDE's steady-state mean and the centre of the prior (sdes.py:233-237).
+ *   cond0, cond1: the conditioning channels stacked after x in the network input.  cond0 == NULL means Y
+ *          (ScoreModel: cat[x, y]).  StoRM (model.py:742-756, condition="both") passes Y = Y_denoised,
+ *          cond0 = Y_noisy, cond1 = Y_denoised and a 6-channel score network.
  *   noise: NULL -> counter-based Philox keyed by (seed, utt_ids[b], draw index, element) so results do
  *          not depend on batch composition or sharding; else injected complex draws
  *          [n_draws][B][F][T] in the reference's order (prior, then per step corrector..., predictor).
  *   utt_ids: host array [B] or NULL (-> 0..B-1).   nfe_out: host int or NULL. */
-int storm_pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int32_t B, int32_t F, int32_t T,
-                    const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids,
+int storm_pc_sample(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int32_t B, int32_t F,
+                    int32_t T, const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids,
                     const float* noise, int32_t* nfe_out, void* stream);
 int32_t storm_pc_num_draws(const StormSamplerConfig* sc);
 /* The Philox draw the sampler would use: complex normal, var 1/2 per component (torch.randn_like on

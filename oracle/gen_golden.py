@@ -269,7 +269,36 @@ def gen_enhance(ns):
          **sd_arrays(m.state_dict()))
 
 
-GENS = dict(fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
+def gen_storm(ns):
+    """StochasticRegenerationModel.enhance glue (model.py:720-780) around reference modules, condition="both"."""
+    g = torch.Generator().manual_seed(9)
+    den = _tiny_model(ns, "ncsnpp", g, nf=8, discriminative=True)
+    score = _tiny_model(ns, "ncsnpp", g, nf=8, input_channels=6)
+    dm = ns.SpecsDataModule(spec_factor=0.15, spec_abs_exponent=0.5)
+    yw = torch.randn(1, 6000, generator=g) * 0.2
+    T_orig = yw.size(1)
+    norm = yw.abs().max().item()
+    Y = ns.pad_spec(torch.unsqueeze(dm.spec_fwd(dm.stft(yw / norm)), 0))
+    with torch.no_grad():
+        Y_den = den(Y)
+    cond = [Y, Y_den]
+
+    def forward_score(x, t, score_conditioning=None, sde_input=None, **kw):       # model.py:654-661
+        return -score(torch.cat([x] + score_conditioning, dim=1), t)
+
+    N = 3
+    zs = [cplx(g, *Y.shape) * float(np.sqrt(0.5)) for _ in range(1 + N)]
+    sde = ns.OUVESDE(theta=1.5, sigma_min=0.05, sigma_max=0.5, N=N)
+    sampler = ns.sampling.get_pc_sampler("reverse_diffusion", "none", sde=sde, score_fn=forward_score, y=Y_den, eps=0.03, snr=0.5,
+                                         corrector_steps=1, conditioning=cond)
+    with patched_randn_like(NoiseQueue(zs)):
+        sample, nfe = sampler()
+    x_hat = dm.istft(dm.spec_back(sample.squeeze()), T_orig) * norm
+    save("storm", y=yw, noise=torch.stack(zs), Y=Y, Y_den=Y_den, sample=sample, x_hat=x_hat.squeeze(), nfe=nfe, N=N,
+         **sd_arrays(den.state_dict(), "den/"), **sd_arrays(score.state_dict(), "score/"))
+
+
+GENS = dict(storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
             net_full=gen_net_full, sampler=gen_sampler, stft=gen_stft, enhance=gen_enhance)
 
 if __name__ == "__main__":

@@ -482,6 +482,26 @@ def enhance(sd, cfg: NetCfg, y: Tensor, sde: OUVE = OUVE(), sc: SpecCfg = SpecCf
     return x_hat.squeeze(), nfe
 
 
+def enhance_storm(sd_den, sd_score, cfg_den: NetCfg, cfg_score: NetCfg, y: Tensor, sde: OUVE = OUVE(), sc: SpecCfg = SpecCfg(),
+                  predictor: str = "reverse_diffusion", corrector: str = "none", N: int = 30, corrector_steps: int = 1, snr: float = 0.5,
+                  t_eps: float = 3e-2, noise: NoiseFn = _default_noise, return_stft: bool = False):
+    """StochasticRegenerationModel.enhance (model.py:720-780), condition="both": the denoiser estimate is the SDE mean
+    and prior centre (:754), the score net sees cat[x, Y, Y_denoised] (:654-656,742-746)."""
+    T_orig = y.size(1)
+    norm_factor = y.abs().max().item()
+    Y = pad_spec(torch.unsqueeze(spec_fwd(stft(y / norm_factor, sc), sc), 0))
+    Y_den = ncsnpp_forward(sd_den, cfg_den, Y, None)
+
+    def score(x, t, _y):
+        return -ncsnpp_forward(sd_score, cfg_score, torch.cat([x, Y, Y_den], dim=1), t)
+
+    sample, nfe = pc_sample(score, Y_den, sde, N, predictor, corrector, corrector_steps, snr, t_eps, noise)
+    if return_stft:
+        return sample.squeeze(), Y.squeeze(), Y_den.squeeze(), T_orig, norm_factor
+    x_hat = istft(spec_back(sample.squeeze(), sc), sc, T_orig) * norm_factor
+    return x_hat.squeeze(), nfe
+
+
 def synth_utterance(b: int, L: int) -> Tensor:
     """Synthetic noisy speech of SURVEY.md section 8(d): 5 harmonics of a random f0 with a 4 Hz on/off
     envelope plus white noise; generator seeded with 1234 + b.  Returns float32 [L]."""

@@ -58,7 +58,7 @@ _PROTOS = {
     "storm_net_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "storm_set_debug_taps": (C.c_int, [C.c_void_p, C.c_int32]),
     "storm_get_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
-    "storm_pc_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+    "storm_pc_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(SamplerConfig), C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "storm_pc_num_draws": (C.c_int32, [C.POINTER(SamplerConfig)]),
     "storm_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -272,7 +272,9 @@ class Engine:
 
     # ---- sampler ------------------------------------------------------------------------------------------
     def pc_sample(self, Y: torch.Tensor, sc: SamplerConfig, seed: int = 0, utt_ids: Optional[Sequence[int]] = None,
-                  noise: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
+                  noise: Optional[torch.Tensor] = None, cond: Optional[Sequence[torch.Tensor]] = None) -> Tuple[torch.Tensor, int]:
+        """Y: SDE mean / prior centre.  cond: conditioning spectrograms stacked after x in the network input
+        (default [Y]; StoRM passes [Y_noisy, Y_denoised] with Y = Y_denoised)."""
         Y = _cf(Y, "Y")
         if Y.dtype != torch.complex64 or Y.dim() != 4 or Y.shape[1] != 1:
             raise ValueError(f"expected complex64 [B, 1, F, T], got {Y.dtype} {tuple(Y.shape)}")
@@ -288,10 +290,15 @@ class Engine:
             nd = lib().storm_pc_num_draws(C.byref(sc))
             if noise.dtype != torch.complex64 or noise.numel() != nd * Y.numel():
                 raise ValueError(f"injected noise must be complex64 with {nd} draws of shape {tuple(Y.shape)}")
+        c0 = c1 = None
         if cond is not None:
-            cond = _cf(cond, "cond")
+            cond = [_cf(c, "cond") for c in cond]
+            if len(cond) not in (1, 2) or any(c.shape != Y.shape or c.dtype != torch.complex64 for c in cond):
+                raise ValueError("cond must be one or two complex64 tensors shaped like Y")
+            c0 = cond[0]
+            c1 = cond[1] if len(cond) == 2 else None
         nfe = C.c_int32()
-        _check(lib().storm_pc_sample(self._h, Y.data_ptr(), _ptr(cond), X.data_ptr(), B, F, T, C.byref(sc), C.c_uint64(seed),
+        _check(lib().storm_pc_sample(self._h, Y.data_ptr(), _ptr(c0), _ptr(c1), X.data_ptr(), B, F, T, C.byref(sc), C.c_uint64(seed),
                                      C.cast(ids, C.c_void_p) if ids is not None else None, _ptr(noise), C.byref(nfe), _stream()))
         return X, int(nfe.value)
 

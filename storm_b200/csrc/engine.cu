@@ -788,12 +788,15 @@ static int check_sampler(const StormSamplerConfig* sc) {
   return 0;
 }
 
-static int pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int B, int F, int T, const StormSamplerConfig& sc,
-                     uint64_t seed, const uint64_t* utt_ids, const float* noise, int* nfe_out, cudaStream_t st) {
+static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int B, int F, int T,
+                     const StormSamplerConfig& sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int* nfe_out,
+                     cudaStream_t st) {
   const int64_t n = (int64_t)F * T;
   const int ncplx = h->in_ch() / 2;
-  if (ncplx == 3 && !cond) return fail(STORM_E_INVALID, "6-channel score net needs the extra condition spectrogram");
+  if (ncplx == 3 && !cond1) return fail(STORM_E_INVALID, "6-channel score net needs two conditioning spectrograms");
+  if (ncplx == 2 && cond1) return fail(STORM_E_INVALID, "4-channel score net takes one conditioning spectrogram");
   if (ncplx < 2) return fail(STORM_E_INVALID, "sampler needs a score network with (x, y) input");
+  if (!cond0) cond0 = Y;
   void* p;
   float *xt, *xm, *d, *tdev;
   uint64_t* ids_dev = nullptr;
@@ -817,8 +820,8 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond, float* X
     LAUNCH(h, launch_fill(tdev, tval, B, st));
     UnpackSrc src{};
     src.p[0] = xt; src.bstride[0] = n;
-    src.p[1] = Y; src.bstride[1] = n;
-    if (ncplx == 3) { src.p[2] = cond; src.bstride[2] = n; }
+    src.p[1] = cond0; src.bstride[1] = n;
+    if (ncplx == 3) { src.p[2] = cond1; src.bstride[2] = n; }
     return net_forward(h, src, tdev, d, B, F, T, st, &tval);
   };
   // prior: x_T = y + randn * std(T=1) (sdes.py:233-237); StoRM uses the same form around its mean
@@ -1004,12 +1007,12 @@ int32_t storm_pc_num_draws(const StormSamplerConfig* sc) {
   return 1 + sc->N * (n_corr + (sc->predictor == STORM_PRED_NONE ? 0 : 1));
 }
 
-int storm_pc_sample(StormHandle* h, const float* Y, const float* cond, float* X, int32_t B, int32_t F, int32_t T,
+int storm_pc_sample(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int32_t B, int32_t F, int32_t T,
                     const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int32_t* nfe_out,
                     void* stream) {
   if (!h || !Y || !X) return fail(STORM_E_INVALID, "storm_pc_sample: null argument");
   STORM_TRY(check_sampler(sc));
-  return pc_sample(h, Y, cond, X, B, F, T, *sc, seed, utt_ids, noise, nfe_out, (cudaStream_t)stream);
+  return pc_sample(h, Y, cond0, cond1, X, B, F, T, *sc, seed, utt_ids, noise, nfe_out, (cudaStream_t)stream);
 }
 
 int storm_philox_normal(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n, float* out, void* stream) {
@@ -1169,7 +1172,7 @@ int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B
   LAUNCH(h, launch_wave_norm(wav_in, B, L, norm, st));
   LAUNCH(h, launch_stft(wav_in, norm, B, L, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
                         sp->spec_abs_exponent, st));
-  STORM_TRY(pc_sample(h, Y, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
+  STORM_TRY(pc_sample(h, Y, nullptr, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
   STORM_TRY(storm_istft(h, X, norm, B, T_pad, wav_out, L, sp, stream));
   h->pool.put(norm); h->pool.put(Y); h->pool.put(X);
   return 0;

@@ -219,6 +219,118 @@ class ScoreModel:
         return p.device
 
 
+class StochasticRegenerationModel:
+    """StoRM inference (sgmse/model.py:392-780): a discriminative NCSN++ first estimates ``Y_denoised``; the score
+    network, conditioned on ``[Y, Y_denoised]`` (6 real input channels), then runs reverse diffusion around
+    ``Y_denoised``.  Same ctor keywords / ``enhance`` signature and defaults (corrector="none", N=30) as the
+    reference; training parts are out of scope."""
+
+    def __init__(self, backbone_denoiser: str = "ncsnpp", backbone_score: str = "ncsnpp", sde: str = "ouve", lr: float = 1e-4,
+                 ema_decay: float = 0.999, t_eps: float = 3e-2, nolog: bool = False, num_eval_files: int = 50,
+                 loss_type_denoiser: str = "none", loss_type_score: str = "mse", data_module_cls=None, mode="regen-joint-training",
+                 condition="both", seed: int = 42, **kwargs):
+        if condition not in ("noisy", "post_denoiser", "both"):
+            raise NotImplementedError(f"Don't know the conditioning you have wished for: {condition}")
+        kw_d = dict(kwargs, input_channels=2, discriminative=True)                    # model.py:416-419
+        self.denoiser_net = BackboneRegistry.get_by_name(backbone_denoiser)(**kw_d) if backbone_denoiser != "none" else None
+        kw_s = dict(kwargs, input_channels=(6 if condition == "both" else 4), discriminative=False)   # model.py:421-423
+        self.score_net = BackboneRegistry.get_by_name(backbone_score)(**kw_s) if backbone_score != "none" else None
+        self.sde = SDERegistry.get_by_name("ouve" if sde == "ouvesde" else sde)(**kwargs)
+        self.t_eps, self.condition, self.mode = t_eps, condition, mode
+        self.data_module = (data_module_cls or SpecsDataModule)(**kwargs)
+        self._seed, self._calls = seed, 0
+
+    def _nets(self):
+        return [n for n in (self.denoiser_net, self.score_net) if n is not None]
+
+    def cuda(self, device=None):
+        for n in self._nets():
+            n.cuda(device)
+        return self
+
+    def eval(self, no_ema: bool = False):
+        return self
+
+    def state_dict(self):
+        out = {}
+        for name, net in (("denoiser_net", self.denoiser_net), ("score_net", self.score_net)):
+            if net is not None:
+                out.update({f"{name}.{k}": v for k, v in net.state_dict().items()})
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        for name, net in (("denoiser_net", self.denoiser_net), ("score_net", self.score_net)):
+            if net is not None:
+                net.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=strict)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        ckpt = _load_ckpt(checkpoint_path, map_location)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.pop("data_module_cls", None)
+        hp.update({k: v for k, v in overrides.items() if k not in ("kwargs",)})
+        model = cls(**hp)
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        ema = ckpt.get("ema")
+        if ema is not None and ema.get("shadow_params") is not None:      # inference uses the EMA weights (model.py:97-108)
+            params = [p for n in model._nets() for p in n.parameters()]
+            with torch.no_grad():
+                for p, sh in zip(params, ema["shadow_params"]):
+                    p.copy_(sh)
+            for n in model._nets():
+                n.mark_weights_changed()
+        return model
+
+    def next_seed(self) -> int:
+        self._calls += 1
+        return (self._seed * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+
+    def forward_denoiser(self, y, **kwargs):
+        return self.denoiser_net(y)                                   # model.py:663-665
+
+    def forward_score(self, x, t, score_conditioning, sde_input=None, **kwargs):
+        return -self.score_net(torch.cat([x] + list(score_conditioning), dim=1), t)    # model.py:654-661
+
+    def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, scale_factor=None, conditioning=None, **kwargs):
+        sde = self.sde.copy()
+        sde.N = self.sde.N if N is None else N
+        kwargs = {"eps": self.t_eps, **kwargs}
+        return sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self.forward_score, y=y,
+                                       conditioning=conditioning, **kwargs)
+
+    def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="none", N=30, corrector_steps=1, snr=0.5,
+                timeit=False, scale_factor=None, return_stft=False, denoiser_only=False, **kwargs):
+        """model.py:720-780 for one utterance ``y`` [1, L]."""
+        start = time.time()
+        T_orig = y.size(1)
+        dev = next(self._nets()[0].parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("StochasticRegenerationModel.enhance needs the model on a CUDA device: call model.cuda() first")
+        yd = y.to(dev, torch.float32)
+        sp = self.data_module.spec_config()
+        norm = _native.wave_norm(yd)
+        T_pad = _native.padded_frames(_native.num_frames(T_orig, sp))
+        Y = _native.stft(yd, norm, sp, T_pad).unsqueeze(1)
+        nfe = 0
+        Y_den = self.forward_denoiser(Y) if self.denoiser_net is not None else None
+        if self.score_net is not None and not denoiser_only:
+            cond = {"noisy": [Y], "post_denoiser": [Y_den], "both": [Y, Y_den]}[self.condition]
+            if sampler_type != "pc":
+                raise ValueError("{} is not a valid sampler type!".format(sampler_type))
+            sampler = self.get_pc_sampler(predictor, corrector, Y_den, N=N, corrector_steps=corrector_steps, snr=snr,
+                                          conditioning=cond, **kwargs)
+            sample, nfe = sampler()
+        else:
+            sample = Y_den
+        if return_stft:
+            return sample.squeeze(), Y.squeeze(), T_orig, norm.item()
+        eng = (self.score_net or self.denoiser_net).engine()
+        x_hat = eng.istft(sample.squeeze(1), norm, T_orig, sp).squeeze().cpu()
+        if timeit:
+            return x_hat, nfe, (time.time() - start) / (len(x_hat) / 16000)
+        return x_hat
+
+
 class _Tolerant:
     """Stand-in for classes pickled into reference checkpoints whose modules are absent here
     (the pickled ``data_module_cls`` hyper-parameter, model.py:61-62)."""

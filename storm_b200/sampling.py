@@ -117,8 +117,14 @@ class NoneCorrector(Corrector):
 
 
 def _native_model(score_fn):
-    from .model import ScoreModel   # local import: model imports this module
-    return score_fn if isinstance(score_fn, ScoreModel) else None
+    """(model, backbone) when ``score_fn`` is one of this package's models (or a bound method of one)."""
+    from .model import ScoreModel, StochasticRegenerationModel   # local import: model imports this module
+    owner = getattr(score_fn, "__self__", score_fn)
+    if isinstance(owner, ScoreModel):
+        return owner, owner.dnn
+    if isinstance(owner, StochasticRegenerationModel):
+        return owner, owner.score_net
+    return None
 
 
 def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=True, eps=3e-2, snr=0.1, corrector_steps=1,
@@ -129,8 +135,9 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
     tests, ``probability_flow=True`` really selects the fixed-step PF update (a no-op in the reference)."""
     predictor_cls = PredictorRegistry.get_by_name(predictor_name)
     corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
-    model = _native_model(score_fn)
-    if model is not None:
+    nat = _native_model(score_fn)
+    if nat is not None:
+        model, dnn = nat
         if not isinstance(sde, sdes.OUVESDE):
             raise NotImplementedError(f"SDE class {sde.__class__.__name__} not yet supported.")
         sc = _native.make_sampler_config(predictor_name, corrector_name, sde.N, corrector_steps, snr, eps, sde.theta,
@@ -138,7 +145,8 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
 
         def native_pc_sampler():
             s = model.next_seed() if seed is None else seed
-            return model.dnn.engine().pc_sample(y, sc, seed=s, utt_ids=utt_ids, noise=noise)
+            # conditioning = list of spectrograms stacked after x (StoRM, model.py:742-756); default [y]
+            return dnn.engine().pc_sample(y, sc, seed=s, utt_ids=utt_ids, noise=noise, cond=conditioning)
 
         return native_pc_sampler
 
@@ -165,7 +173,8 @@ def get_ode_sampler(sde, score_fn, y, inverse_scaler=None, denoise=True, rtol=1e
     (score network + drift algebra on the GPU); the state crosses PCIe per evaluation exactly as it does there."""
     from scipy import integrate
 
-    model = _native_model(score_fn)
+    nat = _native_model(score_fn)
+    model = nat[0] if nat is not None and hasattr(nat[0], "dnn") else None      # ScoreModel only (as model.py:224-244)
     rsde = sde.reverse(score_fn, probability_flow=True)
     sc = None
     if model is not None:

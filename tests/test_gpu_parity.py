@@ -312,3 +312,23 @@ def test_ncsnpplarge_8s_shape_runs():
     assert nfe == 2 and torch.isfinite(torch.view_as_real(X)).all()
     X1, _ = m.engine().pc_sample(Y[1:2], sc, seed=3, utt_ids=[1])
     assert torch.equal(X1[0], X[1])
+
+
+def test_storm_mode_vs_reference():
+    """StochasticRegenerationModel.enhance (denoiser -> 6-channel score net around Y_denoised) vs the reference glue."""
+    from storm_b200 import StochasticRegenerationModel
+    g = load_golden("storm")
+    model = StochasticRegenerationModel(backbone_denoiser="ncsnpp", backbone_score="ncsnpp", sde="ouve", nf=8)
+    sd = {"denoiser_net." + k: v for k, v in sub_sd(g, "den/").items()}
+    sd.update({"score_net." + k: v for k, v in sub_sd(g, "score/").items()})
+    model.load_state_dict(sd)
+    model.cuda()
+    y = T(g["y"])
+    sample, Y, T_orig, norm = model.enhance(y, N=int(g["N"]), return_stft=True, noise=_noise(g["noise"]))
+    assert T_orig == y.shape[1] and rel_l2(Y.cpu(), g["Y"].squeeze()) < 1e-5
+    assert rel_l2(sample.cpu(), g["sample"].squeeze()) < TIGHT
+    den = model.enhance(y, denoiser_only=True, return_stft=True)[0]
+    assert rel_l2(den.cpu(), g["Y_den"].squeeze()) < TIGHT
+    # waveform output with Philox noise: finite, right length, on the CPU like the reference
+    x_hat, nfe, rtf = model.enhance(y, N=2, timeit=True)
+    assert x_hat.shape == (y.shape[1],) and x_hat.device.type == "cpu" and nfe == 2 and torch.isfinite(x_hat).all()

@@ -145,3 +145,15 @@ def test_param_table_matches_reference_keys():
     tabl = ncsnpp_spec.param_table(ncsnpp_spec.NCSNppConfig(nf=8, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,)))
     assert [k for k, _ in tabl] == [k[3:] for k in gl if k.startswith("sd/")]
     assert ncsnpp_spec.param_count(ncsnpp_spec.NCSNppConfig()) == 27756314
+
+
+def test_storm_enhance_end_to_end():
+    g = load_golden("storm")
+    x_hat, nfe = O.enhance_storm(sub_sd(g, "den/"), sub_sd(g, "score/"), O.NetCfg(nf=8, discriminative=True),
+                                 O.NetCfg(nf=8, input_channels=6), T(g["y"]), N=int(g["N"]), noise=_queue(g["noise"]))
+    assert nfe == int(g["nfe"]) == 3
+    assert rel_l2(x_hat, g["x_hat"]) < 5e-5
+    sample, Y, Y_den, _, _ = O.enhance_storm(sub_sd(g, "den/"), sub_sd(g, "score/"), O.NetCfg(nf=8, discriminative=True),
+                                             O.NetCfg(nf=8, input_channels=6), T(g["y"]), N=int(g["N"]), noise=_queue(g["noise"]),
+                                             return_stft=True)
+    assert rel_l2(Y_den, g["Y_den"].squeeze()) < 5e-5 and rel_l2(sample, g["sample"].squeeze()) < 5e-5
