@@ -74,10 +74,12 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {   // D f32, A/B bf16, K-
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, float& rb) {
-  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  ra = a - __bfloat162float(ha);
-  rb = b - __bfloat162float(hb);
-  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  // one packed conversion (F2FP.BF16.F32.PACK_AB, full-rate pipe) instead of two scalar F2F on the quarter-rate XU pipe
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x (low half) = a, .y (high half) = b
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  ra = a - __uint_as_float(u << 16);
+  rb = b - __uint_as_float(u & 0xFFFF0000u);
+  return u;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

@@ -123,10 +123,12 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, float& rb) {
-  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  ra = a - __bfloat162float(ha);
-  rb = b - __bfloat162float(hb);
-  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  // one packed conversion (F2FP.BF16.F32.PACK_AB, full-rate pipe) instead of two scalar F2F on the quarter-rate XU pipe
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x (low half) = a, .y (high half) = b
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  ra = a - __uint_as_float(u << 16);
+  rb = b - __uint_as_float(u & 0xFFFF0000u);
+  return u;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -589,7 +591,11 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   c.a_half = 2 * c.np * 16; c.a_stage = 2 * c.a_half;
   c.w_half = 4096 * k.nmb; c.w_stage = 2 * c.w_half;
   const int budget = c.per_sm == 2 ? 108 * 1024 : SMEM_BUDGET;
-  c.sa = (c.per_sm == 1 && c.a_stage <= 24 * 1024) ? 3 : 2;
+  c.sa = (c.a_stage <= 24 * 1024) ? 3 : 2;
+  {
+    const char* e = getenv("STORM_B200_TC_SA");
+    if (e && atoi(e) >= 2) c.sa = atoi(e);
+  }
   int sw = (budget - c.sa * c.a_stage - 256) / c.w_stage;
   c.sw = sw > 8 ? 8 : sw;
   if (c.sw < 2) return false;
