@@ -197,6 +197,14 @@ int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int
                            const float* bias, const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W,
                            long long* dbg_dev, float* ms_out, void* stream);
 
+/* Same with the fused 1x1 skip of the tcgen05 kernel: when skip_out != NULL the launch also writes
+ * skip_out = conv1x1(raw source; w2) where the raw source is x2 ([B][H][W][C0+C1], single tensor) or, if x2 == NULL,
+ * the un-normalised main input cat[x0, x1]; `out` then holds the main convolution only. */
+int storm_debug_conv_fused(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                           int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout,
+                           const float* bias, const float* res, float out_scale, float* out, float* skip_out, int32_t B,
+                           int32_t H, int32_t W, long long* dbg_dev, float* ms_out, void* stream);
+
 /* Test hook: single-head attention o = softmax(q k^T / sqrt(C)) v on [B][N][C] fp32 device tensors
  * (AttnBlockpp core, layerspp.py:82-86).  engine 0 = tcgen05 kernel (v must be given channel-major [B][C][N]),
  * 1 = SIMT kernel (v token-major [B][N][C]). */

@@ -73,6 +73,14 @@ struct ConvParams {
   int stats_chunks;
   long long* dbg;          // optional [8] cycle counters written by CTA 0 (tools/conv_timeline.py)
   int out_cm;              // 1: write `out` channel-major [B][Cout][H*W] (tcgen05 kernel only; attention V operand)
+  // Fused 1x1 skip (tcgen05 kernel only, nseg == 1): the launch ALSO computes skip_out = conv1x1(raw skip source) +
+  // skip_bias into a second TMEM accumulator, from the raw (un-normalised) values the producers already hold
+  // (skip_src0 == null: same tensors as seg[0]) - ResnetBlockBigGANpp's Conv_2 (layerspp.py:268-269) for free.
+  const void* skip_wtc;
+  const float* skip_src0;
+  const float* skip_src1;
+  const float* skip_bias;
+  float* skip_out;
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);

@@ -56,11 +56,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same with a suspend-time hint: the warp sleeps in hardware for up to `ns` before the instruction returns false
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+// Long waits of many warps (producers waiting for a free stage, the 8 epilogue warps waiting for the whole main loop):
+// sleep in hardware instead of spinning - under the 1 kW power cap every wasted issue slot costs tensor clock.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 2000)) {
     if (clock64() - t0 > 8000000000LL) __trap();
   }
 }
@@ -200,6 +221,8 @@ struct TcpCfg {
   int a_half, a_stage, w_half, w_stage;
   int tiles_x, tiles_y;
   int per_sm;          // CTAs per SM this config is built for (1 or 2)
+  int fuse;            // 1: fused 1x1 skip (4 activation planes per stage, second accumulator set)
+  int a_plane;         // bytes of one activation plane (hi or lo) = a_half
 };
 
 // K-chunk schedule shared by the three roles.  With a 1x1 skip segment (seg 1) its chunks are interleaved with the
@@ -241,7 +264,7 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   const int sa_n = c.sa, sw_n = c.sw;
   int sa = 0, sw = 0;
   uint32_t pa = 0, pw = 0;
-  uint32_t acc = 0;
+  uint32_t acc = 0, acc_skip = 0;
   const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long t_wa = 0, t_ww = 0, t_start = dbg ? clock64() : 0;
   ChunkIter it(p);
@@ -281,6 +304,30 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
         umma_commit(bar_base + 8u * (2 * sa_n + sw_n + sw));               // w_empty: frees the weight stage
         if (++sw == sw_n) { sw = 0; pw ^= 1; }
         if (++dx == 3) { dx = 0; toff += (uint32_t)c.hx - 2u; } else { toff += 1u; }
+      }
+      if (c.fuse) {
+        // fused 1x1 skip: weight stage #10 of this chunk against the RAW planes (centre tap) -> second accumulator set
+        mbar_wait(bar_base + 8u * (2 * sa_n + sw), pw);
+        tc_fence_after();
+        const uint32_t w16 = w_base16 + sw * w_stage16;
+        const uint32_t raw16 = a16 + 2u * a_half16 + (uint32_t)(c.hx + 1);
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) {
+          const uint64_t p_hi = pd_const + (uint64_t)(raw16 + 8u * pt);
+          const uint64_t p_lo = p_hi + a_half16;
+#pragma unroll
+          for (int mb = 0; mb < NMB; ++mb) {
+            const uint64_t w_hi = wd_const + (uint64_t)(w16 + 256u * mb);
+            const uint64_t w_lo = w_hi + w_half16;
+            const uint32_t d = tmem_base + (uint32_t)(NPT * NMB + pt * NMB + mb) * ncol;
+            umma_bf16(d, w_hi, p_hi, idesc, acc_skip);
+            umma_bf16(d, w_hi, p_lo, idesc, 1u);
+            umma_bf16(d, w_lo, p_hi, idesc, 1u);
+          }
+        }
+        acc_skip = 1u;
+        umma_commit(bar_base + 8u * (2 * sa_n + sw_n + sw));
+        if (++sw == sw_n) { sw = 0; pw ^= 1; }
       }
       umma_commit(bar_base + 8u * (sa_n + sa));                            // a_empty: frees the activation stage
       if (++sa == sa_n) { sa = 0; pa ^= 1; }
@@ -357,6 +404,24 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
       }
     }
+    const bool fuse = c.fuse != 0, skip_sep = fuse && p.skip_src0 != nullptr;
+    auto split_store = [&](const float (&v)[8], bool valid, uint32_t off) {   // 8 channels of one pixel -> hi plane, lo plane
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        float r[8];
+        hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
+        hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
+        hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
+        hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
+        float d0, d1;
+        lo.x = pack_bf16x2(r[0], r[1], d0, d1);
+        lo.y = pack_bf16x2(r[2], r[3], d0, d1);
+        lo.z = pack_bf16x2(r[4], r[5], d0, d1);
+        lo.w = pack_bf16x2(r[6], r[7], d0, d1);
+      }
+      st_shared_v4(off, hi);
+      st_shared_v4(off + c.a_half, lo);
+    };
     ChunkIter it(p);
     int si, chk;
     while (it.next(si, chk)) {
@@ -376,6 +441,20 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
             const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix[i] * Cs + cl);
 #pragma unroll
             for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
+          }
+        }
+        float4 sraw[MAXU][4];        // separate raw source of the fused skip (up/down blocks): interior pixels only
+        if (skip_sep) {
+          const float* ssrc;
+          int sCs, scl;
+          if (c0 < s.C0) { ssrc = p.skip_src0; sCs = s.C0; scl = c0; } else { ssrc = p.skip_src1; sCs = s.C1; scl = c0 - s.C0; }
+#pragma unroll
+          for (int i = 0; i < MAXU; ++i) {
+            if (upix[i] >= 0 && uinterior[i]) {
+              const float4* gp = reinterpret_cast<const float4*>(ssrc + (size_t)upix[i] * sCs + scl);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sraw[i][j] = __ldg(gp + j);
+            }
           }
         }
         // ---- L2 prefetch of the next chunk in schedule order
@@ -404,17 +483,27 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
             sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
           }
         }
-        mbar_wait(a_empty(stage), phase ^ 1);
+        mbar_wait_relaxed(a_empty(stage), phase ^ 1);
         const uint32_t st_base = a_base + stage * c.a_stage;
 #pragma unroll
         for (int i = 0; i < MAXU; ++i) {
           if (upix[i] == -2 || !(full_halo || uinterior[i])) continue;
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
-            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-            if (upix[i] >= 0) {
-              const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
-              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const uint32_t off = st_base + (uint32_t)(kh * c.np) * 16u + uoff[i];
+            const bool valid = upix[i] >= 0;
+            const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (fuse && uinterior[i]) {          // raw planes (centre tap only needs the interior)
+              if (skip_sep) {
+                const float4 s0 = sraw[i][2 * kh], s1 = sraw[i][2 * kh + 1];
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                split_store(sv, valid, off + 2u * c.a_half);
+              } else {
+                split_store(v, valid, off + 2u * c.a_half);
+              }
+            }
+            if (valid) {
               if (s.ss) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[kh * 8 + j], sh[kh * 8 + j]);
@@ -423,20 +512,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
               }
-              float r[8];
-              hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
-              hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
-              hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
-              hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
-              float d0, d1;
-              lo.x = pack_bf16x2(r[0], r[1], d0, d1);
-              lo.y = pack_bf16x2(r[2], r[3], d0, d1);
-              lo.z = pack_bf16x2(r[4], r[5], d0, d1);
-              lo.w = pack_bf16x2(r[6], r[7], d0, d1);
             }
-            const uint32_t off = st_base + (uint32_t)(kh * c.np) * 16u + uoff[i];
-            st_shared_v4(off, hi);
-            st_shared_v4(off + c.a_half, lo);
+            split_store(v, valid, off);
           }
         }
         fence_async_shared();
@@ -447,22 +524,35 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
     // =================================== epilogue ======================================================
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     const long long t_e0 = dbg ? clock64() : 0;
-    mbar_wait(acc_full, 0);
+    mbar_wait_relaxed(acc_full, 0);
     const long long t_e1 = dbg ? clock64() : 0;
     tc_fence_after();
     const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which half of the work units
-    const int nacc = c.npt * c.nmb;
+    const int nacc_main = c.npt * c.nmb;
+    const int nacc = c.fuse ? 2 * nacc_main : nacc_main;     // fused skip: a second accumulator set after the main one
     const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
     const int nunits = nacc * units_per_acc;
     const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
     double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
     for (int u = grp; u < nunits; u += 2) {
       const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
-      const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
+      const bool is_skip = ai >= nacc_main;
+      const int am = is_skip ? ai - nacc_main : ai;
+      const int pt = am / c.nmb, mb = am - pt * c.nmb;
       const int cout = m_lo + mb * 128 + q * 32 + lane;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
       const bool cok = cout < p.Cout;                // rows beyond Cout are zero padding of the weight image
+      if (is_skip) {                                  // skip_out = conv1x1(raw) + skip_bias, no statistics
+        const float sb = (p.skip_bias && cok) ? __ldg(p.skip_bias + cout) : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int y = ty0 + g32 * 4 + (jj >> 3);
+          const int x = tx0 + 8 * pt + (jj & 7);
+          if (cok && y < p.H && x < p.W) p.skip_out[(((size_t)b * p.H + y) * p.W + x) * p.Cout + cout] = __uint_as_float(r[jj]) + sb;
+        }
+        continue;
+      }
       float add = 0.f;
       if (p.bias && cok) add += __ldg(p.bias + cout);
       if (tembp && cok) add += __ldg(tembp + cout);
@@ -528,6 +618,15 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
           bulk_g2s(dst + c.w_half, base + tap * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
           if (++stage == c.sw) { stage = 0; phase ^= 1; }
         }
+        if (c.fuse) {      // stage #10 of the chunk: Conv_2 weights (1x1), one image per chunk
+          const uint8_t* sbase = reinterpret_cast<const uint8_t*>(p.skip_wtc) + (size_t)m_lo * 32 + (size_t)ch * q_stride;
+          mbar_wait(w_empty(stage), phase ^ 1);
+          const uint32_t dst = w_base + stage * c.w_stage;
+          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
+          bulk_g2s(dst, sbase, (uint32_t)c.w_half, w_full(stage));
+          bulk_g2s(dst + c.w_half, sbase + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
+          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -559,6 +658,24 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     env_read = true;
   }
   const int nblk = tc_mpad(p.Cout) / 128;
+  if (p.skip_wtc) {
+    // fused skip: 256-pixel (or 128-pixel) tile x one 128-channel block, main + skip accumulators = 512 (256) columns,
+    // one CTA per SM, four activation planes per stage
+    if (p.nseg != 1 || p.seg[0].taps != 9 || !p.skip_out || p.out_cm) return false;
+    c.rows = p.H > 16 ? 32 : 16; c.npt = 1; c.nmb = 1; c.per_sm = 1; c.fuse = 1;
+    c.ncol = 8 * c.rows;
+    c.msplit = nblk;
+    c.hx = 10; c.hy = c.rows + 2; c.np = c.hx * c.hy;
+    c.a_half = 2 * c.np * 16; c.a_plane = c.a_half; c.a_stage = 4 * c.a_half;
+    c.w_half = 4096; c.w_stage = 8192;
+    c.sa = 2;
+    int sw = (SMEM_BUDGET - c.sa * c.a_stage - 256) / c.w_stage;
+    c.sw = sw > 10 ? 10 : sw;
+    c.tiles_x = ceil_div(p.W, 8);
+    c.tiles_y = ceil_div(p.H, c.rows);
+    return true;
+  }
+  c.fuse = 0;
   // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
   // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).
   struct Cand { int rows, npt, nmb, per_sm; };
@@ -588,7 +705,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   c.ncol = 8 * k.rows;
   c.msplit = nblk / k.nmb;
   c.hx = 8 * k.npt + 2; c.hy = k.rows + 2; c.np = c.hx * c.hy;
-  c.a_half = 2 * c.np * 16; c.a_stage = 2 * c.a_half;
+  c.a_half = 2 * c.np * 16; c.a_plane = c.a_half; c.a_stage = 2 * c.a_half;
   c.w_half = 4096 * k.nmb; c.w_stage = 2 * c.w_half;
   const int budget = c.per_sm == 2 ? 108 * 1024 : SMEM_BUDGET;
   c.sa = (c.a_stage <= 24 * 1024) ? 3 : 2;
@@ -623,6 +740,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (!attr) {
     STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
     STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
     attr = true;
   }
   TcpCfg cp;
@@ -631,7 +749,8 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-  if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
+  if (cp.fuse) conv_tcp_kernel<2, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
+  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
   else conv_tcp_kernel<3, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
   STORM_LAUNCH_CHECK();
   return 0;

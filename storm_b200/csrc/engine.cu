@@ -3,6 +3,7 @@
 // (ncsnpp.py:281-450), PC sampler loop (sgmse/sampling/__init__.py:54-66) and the C ABI of
 // include/storm_b200.h.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,6 +81,7 @@ struct Pool {
 struct ResPack {
   const float *gn0_g = nullptr, *gn0_b = nullptr, *gn1_g = nullptr, *gn1_b = nullptr;
   const float *b0 = nullptr;        // Conv_0.bias
+  const float *b1 = nullptr, *b2 = nullptr;   // Conv_1.bias, Conv_2.bias (fused-skip path)
   float* b12 = nullptr;             // Conv_1.bias (+ Conv_2.bias)
   float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;   // SIMT layouts
   void *tc0 = nullptr, *tc1 = nullptr, *tc2 = nullptr; // tcgen05 layouts
@@ -288,6 +290,8 @@ static int repack(StormHandle* h, cudaStream_t st) {
       r.gn0_g = h->P(p + ".GroupNorm_0.weight"); r.gn0_b = h->P(p + ".GroupNorm_0.bias");
       r.gn1_g = h->P(p + ".GroupNorm_1.weight"); r.gn1_b = h->P(p + ".GroupNorm_1.bias");
       r.b0 = h->P(p + ".Conv_0.bias");
+      r.b1 = h->P(p + ".Conv_1.bias");
+      r.b2 = h->P(p + ".Conv_2.bias");
       r.has_skip_conv = h->P(p + ".Conv_2.weight") != nullptr;
       STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &r.w0));
       LAUNCH(h, launch_pack_conv_simt(h->P(p + ".Conv_0.weight"), r.w0, m.out_ch, m.in_ch, 9, st));
@@ -467,7 +471,8 @@ struct Fwd {
       STORM_TRY(alloc(xr, H, W, Cin));
       LAUNCH(h, launch_resample(x0, ss0, hr.p, xr.p, m.up ? 1 : 2, st));
     }
-    Act h1;
+    Act h1, skipS;
+    bool fused = false;
     STORM_TRY(alloc(h1, H, W, m.out_ch));
     {
       ConvParams p{};
@@ -481,6 +486,20 @@ struct Fwd {
       p.temb = tembias ? tembias + r.temb_off : nullptr;
       p.temb_stride = h->dense_total;
       p.res = nullptr; p.out_scale = 1.0f; p.out = h1.p;
+      // Measured slower than the interleaved 1x1 segment (the activation producers, not the MMAs, are the limiter:
+      // profiles/r1_bench_history.md), so it is opt-in: STORM_B200_FUSE_SKIP=1.
+      static const bool fuse_enabled = getenv("STORM_B200_FUSE_SKIP") && atoi(getenv("STORM_B200_FUSE_SKIP")) != 0;
+      if (fuse_enabled && r.has_skip_conv && h->cfg.engine == 0 && r.tc0 && r.tc2) {
+        // fused skip: this launch also produces S = Conv_2(raw x) + b2 from the values its producers already hold
+        STORM_TRY(alloc(skipS, H, W, m.out_ch));
+        p.skip_wtc = r.tc2;
+        p.skip_src0 = resamp ? xr.p : nullptr;
+        p.skip_src1 = nullptr;
+        p.skip_bias = r.b2;
+        p.skip_out = skipS.p;
+        if (conv_tc_eligible(p)) fused = true;
+        else { release(skipS); p.skip_wtc = nullptr; p.skip_src0 = nullptr; p.skip_bias = nullptr; p.skip_out = nullptr; }
+      }
       STORM_TRY(conv(p, &h1));
     }
     h->pool.put(ss0);
@@ -494,7 +513,11 @@ struct Fwd {
       s.src0 = h1.p; s.C0 = m.out_ch; s.src1 = nullptr; s.C1 = 0; s.ss = ss1; s.silu = 1; s.taps = 9; s.w = r.w1; s.wtc = r.tc1;
       p.nseg = 1;
       p.res = nullptr;
-      if (r.has_skip_conv) {
+      p.bias = r.b12;
+      if (fused) {
+        p.res = skipS.p;              // (Conv_1(h) + b1 + S) / sqrt(2)
+        p.bias = r.b1;
+      } else if (r.has_skip_conv) {
         ConvSeg& k = p.seg[1];
         if (resamp) { k.src0 = xr.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; }
         else { k.src0 = x0.p; k.C0 = x0.C; k.src1 = x1 ? x1->p : nullptr; k.C1 = x1 ? x1->C : 0; }
@@ -504,13 +527,14 @@ struct Fwd {
         p.res = x0.p;     // identity skip: in_ch == out_ch, no resampling, single source
       }
       p.B = B; p.H = H; p.W = W; p.Cout = m.out_ch;
-      p.bias = r.b12; p.temb = nullptr; p.temb_stride = 0;
+      p.temb = nullptr; p.temb_stride = 0;
       p.out_scale = 0.70710678118654752f;   // (x + h) / sqrt(2), layerspp.py:274
       p.out = out.p;
       STORM_TRY(conv(p, &out));
     }
     h->pool.put(ss1);
     release(h1);
+    if (fused) release(skipS);
     if (resamp) release(xr);
     return 0;
   }
@@ -1069,22 +1093,35 @@ int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int
                            int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
                            const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, long long* dbg_dev,
                            float* ms_out, void* stream) {
+  return storm_debug_conv_fused(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, out_scale, out, nullptr, B, H, W,
+                                dbg_dev, ms_out, stream);
+}
+
+int storm_debug_conv_fused(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                           int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
+                           const float* res, float out_scale, float* out, float* skip_out, int32_t B, int32_t H, int32_t W,
+                           long long* dbg_dev, float* ms_out, void* stream) {
   if (!x0 || !w || !out) return fail(STORM_E_INVALID, "storm_debug_conv: null argument");
+  if (skip_out && (engine != 0 || !w2)) return fail(STORM_E_INVALID, "storm_debug_conv: fused skip needs the tcgen05 engine and w2");
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<void*> owned;
   ConvParams p{};
-  p.nseg = x2 ? 2 : 1;
+  p.nseg = (x2 && !skip_out) ? 2 : 1;
   p.seg[0].src0 = x0; p.seg[0].src1 = x1; p.seg[0].C0 = C0; p.seg[0].C1 = x1 ? C1 : 0; p.seg[0].ss = ss; p.seg[0].silu = silu;
   p.seg[0].taps = taps;
-  if (x2) { p.seg[1].src0 = x2; p.seg[1].C0 = C2; p.seg[1].taps = 1; }
+  if (x2 && !skip_out) { p.seg[1].src0 = x2; p.seg[1].C0 = C2; p.seg[1].taps = 1; }
   p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.bias = bias; p.res = res; p.out_scale = out_scale; p.out = out;
   int rc = 0;
   const int Cin = C0 + (x1 ? C1 : 0);
   if (engine == 0) {
     void *t0 = nullptr, *t1 = nullptr;
     rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st);
-    if (rc == 0 && x2) rc = tc_pack_weights(w2, Cout, C2, 1, &t1, &owned, st);
+    if (rc == 0 && w2) rc = tc_pack_weights(w2, Cout, skip_out ? Cin : C2, 1, &t1, &owned, st);
     p.seg[0].wtc = t0; p.seg[1].wtc = t1;
+    if (skip_out) {      // fused: skip over x2 (separate raw source, single tensor) or over the main sources when x2 == null
+      p.skip_wtc = t1; p.skip_src0 = x2; p.skip_src1 = nullptr; p.skip_bias = nullptr; p.skip_out = skip_out;
+      p.seg[1] = ConvSeg{};
+    }
     if (rc == 0 && !conv_tc_eligible(p)) rc = fail(STORM_E_INVALID, "storm_debug_conv: shape not eligible for the tcgen05 kernel");
     if (rc == 0) rc = launch_conv_tc(p, st);
     if (rc == 0 && ms_out) {     // timed repeat (warm weights), optionally with the CTA-0 cycle counters

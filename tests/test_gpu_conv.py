@@ -83,3 +83,28 @@ def test_attention_core(engine, B, N, C):
     err = _rel(out, ref)
     print(f"attention engine={engine} B={B} N={N} C={C} rel-L2={err:.3e}")
     assert torch.isfinite(out).all() and err < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,sep", [(2, 40, 24, 128, 0, 128, False), (1, 32, 32, 256, 128, 256, False),
+                                                    (2, 16, 16, 128, 0, 128, True), (1, 64, 16, 256, 0, 256, True),
+                                                    (1, 24, 8, 96, 96, 192, False)])
+def test_fused_skip_conv(B, H, W, C0, C1, Cout, sep):
+    """conv3x3(act(cat[x0,x1])) and conv1x1(raw) from ONE launch (ResnetBlock Conv_0 + Conv_2)."""
+    from storm_b200 import _native
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cout)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)   # noqa: E731
+    Cin = C0 + C1
+    x0 = rn(B, H, W, C0)
+    x1 = rn(B, H, W, C1) if C1 else None
+    x2 = rn(B, H, W, Cin) if sep else None
+    w = rn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5
+    w2 = rn(Cout, Cin, 1, 1) / Cin ** 0.5
+    ss = torch.stack([1.0 + 0.3 * rn(B, Cin), 0.2 * rn(B, Cin)], dim=-1).contiguous()
+    bias = 0.1 * rn(Cout)
+    out, skip = _native.debug_conv_fused(x0, w, w2, x1=x1, ss=ss, silu=True, x2=x2, bias=bias)
+    ref = _ref(x0, w, x1=x1, ss=ss, silu=True, bias=bias)
+    raw = x2 if sep else (x0 if x1 is None else torch.cat([x0, x1], dim=-1))
+    ref_skip = F.conv2d(raw.double().permute(0, 3, 1, 2), w2.double()).permute(0, 2, 3, 1).float()
+    e1, e2 = _rel(out, ref), _rel(skip, ref_skip)
+    print(f"fused skip {B,H,W,C0,C1,Cout,sep}: main {e1:.3e} skip {e2:.3e}")
+    assert e1 < 2e-5 and e2 < 2e-5
