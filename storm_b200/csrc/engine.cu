@@ -27,6 +27,8 @@ int fail(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------------
+constexpr int PYR_CH = 16;   // channels of the (zero-padded) input pyramid tensors
+
 enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RES, M_ATTN, M_COMBINE, M_GN, M_CONV_OUT };
 
 struct Mod {
@@ -87,6 +89,9 @@ struct ResPack {
   void *tc0 = nullptr, *tc1 = nullptr, *tc2 = nullptr; // tcgen05 layouts
   int temb_off = 0;
   bool has_skip_conv = false;
+  // down blocks followed by a Combine: Conv_2 and sqrt(2)*Combine.Conv_0 concatenated along K (x' | padded pyramid)
+  void* tc2c = nullptr;
+  float* b12c = nullptr;
 };
 struct AttnPack {
   const float *gn_g = nullptr, *gn_b = nullptr;
@@ -328,10 +333,15 @@ static int repack(StormHandle* h, cudaStream_t st) {
       }
       h->attn[m.index] = a;
     } else if (m.kind == M_CONV_IN) {
+      // input channels are zero-padded to PYR_CH = 16 so that the 4 -> nf conv is a tensor-core K chunk
       SmallConvPack s;
       s.b = h->P(p + ".bias");
-      STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &s.w));
-      LAUNCH(h, launch_pack_conv_simt(h->P(p + ".weight"), s.w, m.out_ch, m.in_ch, 9, st));
+      float* wpad = nullptr;
+      STORM_TRY(dev_alloc(h, (size_t)9 * PYR_CH * m.out_ch, &wpad));
+      LAUNCH(h, launch_pad_cin(h->P(p + ".weight"), wpad, m.out_ch, m.in_ch, PYR_CH, 9, st));
+      STORM_TRY(dev_alloc(h, (size_t)9 * PYR_CH * m.out_ch, &s.w));
+      LAUNCH(h, launch_pack_conv_simt(wpad, s.w, m.out_ch, PYR_CH, 9, st));
+      if (use_tc) STORM_TRY(tc_pack_weights(wpad, m.out_ch, PYR_CH, 9, &s.tc, &h->packed, st));
       h->conv_in[m.index] = s;
     } else if (m.kind == M_CONV_OUT) {
       // [9][C][8] zero padded on the output-channel axis
@@ -357,6 +367,20 @@ static int repack(StormHandle* h, cudaStream_t st) {
       s.b = h->P(p + ".Conv_0.bias");
       s.w = const_cast<float*>(h->P(p + ".Conv_0.weight"));   // [C][Cin] as stored
       h->combine[m.index] = s;
+      // fold "h + Conv_0(pyramid)" into the preceding down block's Conv_1 launch:
+      //   ((W2 x' + sqrt2 Wc pyr) + Conv_1(h1) + (b1 + b2 + sqrt2 bc)) / sqrt2  =  resblock + Wc pyr + bc
+      const Mod& pm = h->mods[m.index - 1];
+      auto it = h->res.find(pm.index);
+      if (use_tc && pm.kind == M_RES && pm.down && it != h->res.end() && it->second.has_skip_conv) {
+        ResPack& r = it->second;
+        const std::string pp = "all_modules." + std::to_string(pm.index);
+        float* wcat = nullptr;
+        STORM_TRY(dev_alloc(h, (size_t)pm.out_ch * (pm.in_ch + PYR_CH), &wcat));
+        LAUNCH(h, launch_concat_1x1(h->P(pp + ".Conv_2.weight"), pm.in_ch, s.w, m.in_ch, PYR_CH, 1.41421356237309505f, wcat, pm.out_ch, st));
+        STORM_TRY(tc_pack_weights(wcat, pm.out_ch, pm.in_ch + PYR_CH, 1, &r.tc2c, &h->packed, st));
+        STORM_TRY(dev_alloc(h, (size_t)pm.out_ch, &r.b12c));
+        LAUNCH(h, launch_add_vec(r.b12, s.b, r.b12c, pm.out_ch, 1.41421356237309505f, st));
+      }
     }
   }
   h->weights_loaded = true;
@@ -454,7 +478,7 @@ struct Fwd {
   }
 
   // ResnetBlockBigGANpp.forward (layerspp.py:242-274).  x1 != null: input is cat[x0, x1] (ncsnpp.py:381).
-  int res_block(const Mod& m, Act& x0, Act* x1, const float* tembias, Act& out) {
+  int res_block(const Mod& m, Act& x0, Act* x1, const float* tembias, Act& out, const Act* pyr_fuse = nullptr) {
     const ResPack& r = h->res.at(m.index);
     const int Cin = x0.C + (x1 ? x1->C : 0);
     if (Cin != m.in_ch) return fail(STORM_E_STATE, "res_block: channel mismatch");
@@ -522,6 +546,10 @@ struct Fwd {
         if (resamp) { k.src0 = xr.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; }
         else { k.src0 = x0.p; k.C0 = x0.C; k.src1 = x1 ? x1->p : nullptr; k.C1 = x1 ? x1->C : 0; }
         k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2; k.wtc = r.tc2;
+        if (pyr_fuse) {      // Combine folded in: the padded pyramid rides along as 16 more K channels of the skip segment
+          k.src1 = pyr_fuse->p; k.C1 = PYR_CH; k.w = nullptr; k.wtc = r.tc2c;
+          p.bias = r.b12c;
+        }
         p.nseg = 2;
       } else {
         p.res = x0.p;     // identity skip: in_ch == out_ch, no resampling, single source
@@ -636,9 +664,9 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
 
   // ---- input ---------------------------------------------------------------------------------------------
   size_t mi = h->conditional() ? 3 : 1;
-  Act x0;
-  STORM_TRY(f.alloc(x0, F, T, inch));
-  LAUNCH(h, launch_unpack_input(src, x0.p, B, inch / 2, F * T, st));
+  Act x0;      // [B][F][T][PYR_CH]: 2x-1 of the real/imag channels, zero padded (also level 0 of the input pyramid)
+  STORM_TRY(f.alloc(x0, F, T, PYR_CH));
+  LAUNCH(h, launch_unpack_input(src, x0.p, B, inch / 2, PYR_CH, F * T, st));
   std::vector<Act> hs;
   {
     const Mod& m = h->mods[mi];
@@ -647,9 +675,9 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     STORM_TRY(f.alloc(a, F, T, nf));
     ConvParams p{};
     p.nseg = 1;
-    p.seg[0].src0 = x0.p; p.seg[0].C0 = inch; p.seg[0].taps = 9; p.seg[0].w = s.w;
+    p.seg[0].src0 = x0.p; p.seg[0].C0 = PYR_CH; p.seg[0].taps = 9; p.seg[0].w = s.w; p.seg[0].wtc = s.tc;
     p.B = B; p.H = F; p.W = T; p.Cout = nf; p.bias = s.b; p.out_scale = 1.0f; p.out = a.p;
-    LAUNCH(h, launch_conv_simt(p, st));
+    STORM_TRY(f.conv(p, &a));
     STORM_TRY(f.tap("conv_in", a));
     hs.push_back(a);
     ++mi;
@@ -675,23 +703,30 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
       hs.push_back(o);
     }
     if (lvl != nres - 1) {
-      Act o;
-      STORM_TRY(f.res_block(h->mods[mi], hs.back(), nullptr, tembias, o));
-      STORM_TRY(tapmod(h->mods[mi], o));
-      ++mi;
-      Act pd;
-      STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, inch));
-      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, inch, st));
+      Act pd;      // input pyramid one level down (ncsnpp.py:353)
+      STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, PYR_CH));
+      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, PYR_CH, st));
       f.release(pyr_in);
       pyr_in = pd;
-      const SmallConvPack& s = h->combine.at(h->mods[mi].index);
-      Act o2;
-      STORM_TRY(f.alloc(o2, o.H, o.W, o.C));
-      LAUNCH(h, launch_combine(o.p, pyr_in.p, s.w, s.b, o2.p, B, o.H * o.W, o.C, inch, st));
-      STORM_TRY(tapmod(h->mods[mi], o2));
+      const Mod& dm = h->mods[mi];
+      const bool fuse_combine = !h->taps_on && h->cfg.engine == 0 && h->res.at(dm.index).tc2c != nullptr;
+      Act o;
+      STORM_TRY(f.res_block(dm, hs.back(), nullptr, tembias, o, fuse_combine ? &pyr_in : nullptr));
       ++mi;
-      f.release(o);
-      hs.push_back(o2);
+      if (fuse_combine) {     // `o` already is Combine(pyramid, resblock(h)) (layerspp.py:52-57)
+        ++mi;
+        hs.push_back(o);
+      } else {
+        STORM_TRY(tapmod(dm, o));
+        const SmallConvPack& s = h->combine.at(h->mods[mi].index);
+        Act o2;
+        STORM_TRY(f.alloc(o2, o.H, o.W, o.C));
+        LAUNCH(h, launch_combine(o.p, pyr_in.p, PYR_CH, s.w, s.b, o2.p, B, o.H * o.W, o.C, inch, st));
+        STORM_TRY(tapmod(h->mods[mi], o2));
+        ++mi;
+        f.release(o);
+        hs.push_back(o2);
+      }
     }
   }
   f.release(pyr_in);

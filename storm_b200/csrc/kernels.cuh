@@ -35,11 +35,16 @@ int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C
 // complex planes -> NHWC real [B][F][T][2nc] with 2x-1 (ncsnpp.py:290-296,321-323); plane ch of sample b
 // starts at p[ch] + b * bstride[ch] complex elements
 struct UnpackSrc { const float* p[3]; long long bstride[3]; };
-int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int HW, cudaStream_t st);
+// out has CP >= 2nc channels per pixel; channels beyond 2nc are written as zeros (tensor-core K padding)
+int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int CP, int HW, cudaStream_t st);
 int launch_fill(float* p, float v, int n, cudaStream_t st);
 // out = h + bias + W(pyr): Combine 'sum' with 1x1 conv Cin->C (layerspp.py:52-57); w [C][Cin]
-int launch_combine(const float* h, const float* pyr, const float* w, const float* bias, float* out, int B, int HW,
+int launch_combine(const float* h, const float* pyr, int pyr_stride, const float* w, const float* bias, float* out, int B, int HW,
                    int C, int Cin, cudaStream_t st);
+// [Cout][Cin][taps] -> [Cout][CinPad][taps] with zero channels appended
+int launch_pad_cin(const float* w, float* out, int Cout, int Cin, int CinPad, int taps, cudaStream_t st);
+// combined 1x1 matrix [Cout][C2 + CP]: columns [0,C2) = w2 ([Cout][C2]), columns [C2, C2+Cc) = scale * wc ([Cout][Cc]), rest zero
+int launch_concat_1x1(const float* w2, int C2, const float* wc, int Cc, int CP, float scale, float* out, int Cout, cudaStream_t st);
 // progressive output branch: conv3x3_{C->Co}(SiLU(GN(h))) + bias (+ FIR_up(prev)) (ncsnpp.py:389-410);
 // w packed [9][C][8] (Co <= 8, zero padded)
 int launch_conv_out_small(const Act& h, const float* ss, const float* w, const float* bias, const float* prev,

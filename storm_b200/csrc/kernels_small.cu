@@ -53,6 +53,40 @@ int launch_transpose_into(const float* w, float* out, int rows, int cols, int ou
   return 0;
 }
 
+__global__ void pad_cin_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int CinPad, int taps) {
+  const size_t n = (size_t)Cout * CinPad * taps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = i % taps;
+    const int ci = (i / taps) % CinPad;
+    const int co = i / ((size_t)taps * CinPad);
+    out[i] = ci < Cin ? w[((size_t)co * Cin + ci) * taps + tap] : 0.f;
+  }
+}
+int launch_pad_cin(const float* w, float* out, int Cout, int Cin, int CinPad, int taps, cudaStream_t st) {
+  size_t n = (size_t)Cout * CinPad * taps;
+  pad_cin_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, CinPad, taps);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void concat_1x1_kernel(const float* __restrict__ w2, int C2, const float* __restrict__ wc, int Cc, int CP, float scale,
+                                  float* __restrict__ out, int Cout) {
+  const int K = C2 + CP;
+  const size_t n = (size_t)Cout * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K, co = i / K;
+    float v = 0.f;
+    if (k < C2) v = w2[(size_t)co * C2 + k];
+    else if (k - C2 < Cc) v = scale * wc[(size_t)co * Cc + (k - C2)];
+    out[i] = v;
+  }
+}
+int launch_concat_1x1(const float* w2, int C2, const float* wc, int Cc, int CP, float scale, float* out, int Cout, cudaStream_t st) {
+  size_t n = (size_t)Cout * (C2 + CP);
+  concat_1x1_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w2, C2, wc, Cc, CP, scale, out, Cout);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n, float sb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? sb * b[i] : 0.f);
@@ -488,23 +522,24 @@ int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C
 // =====================================================================================================
 // input / pyramid / head
 // =====================================================================================================
-__global__ void unpack_input_kernel(UnpackSrc src, float* __restrict__ out, int B, int nc, int HW) {
+__global__ void unpack_input_kernel(UnpackSrc src, float* __restrict__ out, int B, int nc, int CP, int HW) {
   const size_t total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i / HW;
     const int p = i % HW;
     for (int ch = 0; ch < nc; ++ch) {
       float2 v = __ldg(reinterpret_cast<const float2*>(src.p[ch]) + (size_t)b * src.bstride[ch] + p);
-      out[i * (2 * nc) + 2 * ch] = 2.0f * v.x - 1.0f;
-      out[i * (2 * nc) + 2 * ch + 1] = 2.0f * v.y - 1.0f;
+      out[i * CP + 2 * ch] = 2.0f * v.x - 1.0f;
+      out[i * CP + 2 * ch + 1] = 2.0f * v.y - 1.0f;
     }
+    for (int ch = 2 * nc; ch < CP; ++ch) out[i * CP + ch] = 0.f;
   }
 }
-int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int HW, cudaStream_t st) {
-  if (nc < 1 || nc > 3) return fail(-1, "unpack_input: 1..3 complex channels");
+int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int CP, int HW, cudaStream_t st) {
+  if (nc < 1 || nc > 3 || CP < 2 * nc) return fail(-1, "unpack_input: 1..3 complex channels");
   size_t total = (size_t)B * HW;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  unpack_input_kernel<<<blocks, 256, 0, st>>>(src, out, B, nc, HW);
+  unpack_input_kernel<<<blocks, 256, 0, st>>>(src, out, B, nc, CP, HW);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -518,7 +553,7 @@ int launch_fill(float* p, float v, int n, cudaStream_t st) {
   return 0;
 }
 
-__global__ void combine_kernel(const float* __restrict__ h, const float* __restrict__ pyr, const float* __restrict__ w,
+__global__ void combine_kernel(const float* __restrict__ h, const float* __restrict__ pyr, int pstride, const float* __restrict__ w,
                                const float* __restrict__ bias, float* __restrict__ out, size_t npix, int C, int Cin) {
   const int C4 = C >> 2;
   const size_t total = npix * C4;
@@ -530,18 +565,18 @@ __global__ void combine_kernel(const float* __restrict__ h, const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = bias[c4 * 4 + j];
     for (int k = 0; k < Cin; ++k) {
-      float pv = __ldg(pyr + p * Cin + k);
+      float pv = __ldg(pyr + p * pstride + k);
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = fmaf(__ldg(w + (size_t)(c4 * 4 + j) * Cin + k), pv, acc[j]);
     }
     reinterpret_cast<float4*>(out)[i] = make_float4(acc[0] + hv.x, acc[1] + hv.y, acc[2] + hv.z, acc[3] + hv.w);
   }
 }
-int launch_combine(const float* h, const float* pyr, const float* w, const float* bias, float* out, int B, int HW, int C,
+int launch_combine(const float* h, const float* pyr, int pyr_stride, const float* w, const float* bias, float* out, int B, int HW, int C,
                    int Cin, cudaStream_t st) {
   size_t total = (size_t)B * HW * (C / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  combine_kernel<<<blocks, 256, 0, st>>>(h, pyr, w, bias, out, (size_t)B * HW, C, Cin);
+  combine_kernel<<<blocks, 256, 0, st>>>(h, pyr, pyr_stride, w, bias, out, (size_t)B * HW, C, Cin);
   STORM_LAUNCH_CHECK();
   return 0;
 }

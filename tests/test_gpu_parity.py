@@ -332,3 +332,42 @@ def test_storm_mode_vs_reference():
     # waveform output with Philox noise: finite, right length, on the CPU like the reference
     x_hat, nfe, rtf = model.enhance(y, N=2, timeit=True)
     assert x_hat.shape == (y.shape[1],) and x_hat.device.type == "cpu" and nfe == 2 and torch.isfinite(x_hat).all()
+
+
+@pytest.mark.parametrize("name", ["ncsnpp12M", "ncsnpp6M"])
+def test_small_backbones_vs_oracle(name):
+    """nf = 96 variants (ncsnpp.py:479-513): channel counts 96/192 exercise zero-padded 128-row weight blocks."""
+    from storm_b200 import ncsnpp_spec
+    m = _model(name)
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=4, init_scale=1.0, bias_std=0.05)
+    m.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.complex(torch.randn(2, 2, 64, 64, generator=gen), torch.randn(2, 2, 64, 64, generator=gen)) * 0.4
+    t = torch.tensor([0.9, 0.05])
+    y = m(x.cuda(), t.cuda()).cpu()
+    yo = O.ncsnpp_forward(sd, O.named_cfg(name), x, t)
+    err = rel_l2(y, yo)
+    print(f"{name}: rel-L2 vs oracle = {err:.3e}")
+    assert err < TOL
+
+
+def test_error_behaviour_matches_reference_conventions():
+    from storm_b200 import BackboneRegistry, ScoreModel, _native
+    m = _model("ncsnpp", nf=8, init_scale=1.0)
+    with pytest.raises(ValueError):           # T not a multiple of 2^(levels-1): the reference's skip-cat would fail too
+        m(torch.zeros(1, 2, 16, 20, dtype=torch.complex64, device="cuda"), torch.ones(1, device="cuda"))
+    with pytest.raises(ValueError):           # wrong channel count
+        m(torch.zeros(1, 3, 16, 16, dtype=torch.complex64, device="cuda"), torch.ones(1, device="cuda"))
+    with pytest.raises(ValueError):           # missing time conditioning on a score network
+        m(torch.zeros(1, 2, 16, 16, dtype=torch.complex64, device="cuda"))
+    with pytest.raises(RuntimeError):         # host tensors are refused, no silent CPU path
+        m(torch.zeros(1, 2, 16, 16, dtype=torch.complex64), torch.ones(1))
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 2)
+    with pytest.raises(ValueError):           # injected noise with the wrong number of draws
+        m.engine().pc_sample(torch.zeros(1, 1, 16, 16, dtype=torch.complex64, device="cuda"), sc,
+                             noise=torch.zeros(2, 1, 1, 16, 16, dtype=torch.complex64, device="cuda"))
+    with pytest.raises(ValueError):
+        _native.make_sampler_config("reverse_diffusion", "ald", 0)._fields_ and m.engine().pc_sample(
+            torch.zeros(1, 1, 16, 16, dtype=torch.complex64, device="cuda"), _native.make_sampler_config("reverse_diffusion", "ald", 0))
+    with pytest.raises(ValueError):           # unknown backbone name through the model surface
+        ScoreModel(backbone="nope")
