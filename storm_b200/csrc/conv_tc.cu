@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
   if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-int g_tc_force_per_sm = 0;   // 0 = heuristic, 1 / 2 = force (STORM_B200_TC_PER_SM, tools only)
+int g_tc_force_per_sm = 3;   // see choose_cfg_p (STORM_B200_TC_PER_SM)
 
 bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   if (p.Cout < 1 || p.Cout > 256) return false;
@@ -679,18 +679,23 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
   // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).
   struct Cand { int rows, npt, nmb, per_sm; };
-  const Cand cands1[] = {{32, 1, 1, 2}, {32, 2, 1, 1}, {16, 2, 1, 2}, {16, 1, 1, 2}};                         // Cout = 128
-  const Cand cands2[] = {{32, 1, 1, 2}, {32, 1, 2, 1}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};           // Cout = 256
-  // with a 1x1 skip segment the activation producers are the limiter: share each staged halo across both
-  // 128-channel blocks (measured: tools/conv_timeline.py, b31.conv1)
-  const Cand cands2s[] = {{32, 1, 2, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};
-  const Cand* cands = nblk == 1 ? cands1 : (p.nseg == 2 ? cands2s : cands2);
+  // Order = preference.  Measured on the sustained (power-capped) headline benchmark, the one-CTA-per-SM 512-column
+  // tiles win (fewer redundant halo conversions per MMA -> less power -> higher tensor clock), although the
+  // two-CTA variants look better when a layer is timed in isolation; mode 3 (default) prefers the big tile whenever
+  // it still yields >= 132 CTAs.  STORM_B200_TC_PER_SM: 0 = two-CTA first (burst-tuned), 1 / 2 = force, 3 = default.
+  const Cand cands1b[] = {{32, 1, 1, 2}, {32, 2, 1, 1}, {16, 2, 1, 2}, {16, 1, 1, 2}};                        // Cout <= 128
+  const Cand cands2b[] = {{32, 1, 1, 2}, {32, 1, 2, 1}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};          // Cout <= 256
+  const Cand cands1m[] = {{32, 2, 1, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 1, 2}};
+  const Cand cands2m[] = {{32, 1, 2, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};
+  const bool big_first = g_tc_force_per_sm == 3 || p.nseg == 2;
+  const Cand* cands = nblk == 1 ? (big_first ? cands1m : cands1b) : (big_first ? cands2m : cands2b);
   const int ncand = nblk == 1 ? 4 : 5;
   int best = -1;
   long best_ctas = -1;
   for (int i = 0; i < ncand; ++i) {
     const Cand& k = cands[i];
-    if (g_tc_force_per_sm && k.per_sm != g_tc_force_per_sm && !(g_tc_force_per_sm == 1 && k.rows == 16)) continue;
+    const bool forced = g_tc_force_per_sm == 1 || g_tc_force_per_sm == 2;
+    if (forced && k.per_sm != g_tc_force_per_sm && !(g_tc_force_per_sm == 1 && k.rows == 16)) continue;
     if (k.npt * k.nmb * 8 * k.rows > (k.per_sm == 2 ? 256 : 512)) continue;
     if (k.npt == 2 && p.W <= 8) continue;
     if (k.rows == 32 && p.H <= 16) continue;

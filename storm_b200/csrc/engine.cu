@@ -677,7 +677,8 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     p.nseg = 1;
     p.seg[0].src0 = x0.p; p.seg[0].C0 = PYR_CH; p.seg[0].taps = 9; p.seg[0].w = s.w; p.seg[0].wtc = s.tc;
     p.B = B; p.H = F; p.W = T; p.Cout = nf; p.bias = s.b; p.out_scale = 1.0f; p.out = a.p;
-    STORM_TRY(f.conv(p, &a));
+    static const bool no_tc_in = getenv("STORM_B200_NO_FUSE_INPUT") && atoi(getenv("STORM_B200_NO_FUSE_INPUT")) != 0;
+    if (no_tc_in) { LAUNCH(h, launch_conv_simt(p, st)); } else { STORM_TRY(f.conv(p, &a)); }
     STORM_TRY(f.tap("conv_in", a));
     hs.push_back(a);
     ++mi;
@@ -709,7 +710,8 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
       f.release(pyr_in);
       pyr_in = pd;
       const Mod& dm = h->mods[mi];
-      const bool fuse_combine = !h->taps_on && h->cfg.engine == 0 && h->res.at(dm.index).tc2c != nullptr;
+      static const bool no_fuse_in = getenv("STORM_B200_NO_FUSE_INPUT") && atoi(getenv("STORM_B200_NO_FUSE_INPUT")) != 0;
+      const bool fuse_combine = !no_fuse_in && !h->taps_on && h->cfg.engine == 0 && h->res.at(dm.index).tc2c != nullptr;
       Act o;
       STORM_TRY(f.res_block(dm, hs.back(), nullptr, tembias, o, fuse_combine ? &pyr_in : nullptr));
       ++mi;
