@@ -346,7 +346,9 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
 // MAXU = halo pixels per producer thread (ceil(np / 256)); MINB = CTAs per SM.  <3,1>: one CTA per SM owning all
 // 512 TMEM columns; <2,2>: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
 // global stores) overlaps the other's MMA main loop on the shared tensor pipe.
-template <int MAXU, int MINB>
+// FUSE: compile the fused 1x1-skip path (extra raw planes / loads) only into the instantiation that uses it, so the
+// others keep their register budget (the <2,2> variant is capped at 102 registers).
+template <int MAXU, int MINB, bool FUSE>
 __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
       }
     }
-    const bool fuse = c.fuse != 0, skip_sep = fuse && p.skip_src0 != nullptr;
+    const bool fuse = FUSE && c.fuse != 0, skip_sep = fuse && p.skip_src0 != nullptr;
     auto split_store = [&](const float (&v)[8], bool valid, uint32_t off) {   // 8 channels of one pixel -> hi plane, lo plane
       uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
       if (valid) {
@@ -443,8 +445,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
             for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
           }
         }
-        float4 sraw[MAXU][4];        // separate raw source of the fused skip (up/down blocks): interior pixels only
-        if (skip_sep) {
+        float4 sraw[FUSE ? MAXU : 1][4];   // separate raw source of the fused skip (up/down blocks): interior pixels only
+        if constexpr (FUSE) if (skip_sep) {
           const float* ssrc;
           int sCs, scl;
           if (c0 < s.C0) { ssrc = p.skip_src0; sCs = s.C0; scl = c0; } else { ssrc = p.skip_src1; sCs = s.C1; scl = c0 - s.C0; }
@@ -494,9 +496,9 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
             const bool valid = upix[i] >= 0;
             const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
             float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            if (fuse && uinterior[i]) {          // raw planes (centre tap only needs the interior)
+            if constexpr (FUSE) if (fuse && uinterior[i]) {          // raw planes (centre tap only needs the interior)
               if (skip_sep) {
-                const float4 s0 = sraw[i][2 * kh], s1 = sraw[i][2 * kh + 1];
+                const float4 s0 = sraw[FUSE ? i : 0][2 * kh], s1 = sraw[FUSE ? i : 0][2 * kh + 1];
                 const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 split_store(sv, valid, off + 2u * c.a_half);
               } else {
@@ -743,9 +745,9 @@ int conv_tc_stats_chunks(const ConvParams& p) {
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
     attr = true;
   }
   TcpCfg cp;
@@ -754,9 +756,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-  if (cp.fuse) conv_tcp_kernel<2, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
-  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2><<<grid, P_THREADS, smem, st>>>(p, cp);
-  else conv_tcp_kernel<3, 1><<<grid, P_THREADS, smem, st>>>(p, cp);
+  if (cp.fuse) conv_tcp_kernel<2, 1, true><<<grid, P_THREADS, smem, st>>>(p, cp);
+  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, false><<<grid, P_THREADS, smem, st>>>(p, cp);
+  else conv_tcp_kernel<3, 1, false><<<grid, P_THREADS, smem, st>>>(p, cp);
   STORM_LAUNCH_CHECK();
   return 0;
 }
