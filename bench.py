@@ -240,6 +240,12 @@ def run_native(args):
         return
 
     pk = peaks()
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tp):       # from the committed ncu --set full capture of the same kernel (not measured in this run)
+        tj = json.load(open(tp))
+        traffic = tj.get("mean_dram_bytes_per_launch")
+        traffic_note = "profiles/r1_conv_traffic.json: mean dram bytes of the 4 largest conv launches (ncu --set full); " + tj.get("note", "")
     total_utts = world * B * args.steps
     value = total_utts / (ms * 1e-3)
     e2e_value = total_utts / (e2e_ms * 1e-3)
@@ -249,7 +255,7 @@ def run_native(args):
     conv_share = (prof["tcgen05"]["ms"] + prof["simt"]["ms"]) / ms
     peak = pk["bf16_sustained"]
     roofline = dict(bound="tensor", kernel=f"implicit-GEMM conv3x3/1x1 ({dom})", achieved=achieved, peak=peak, unit="TFLOP/s",
-                    frac=achieved / peak if peak else None, traffic=None,
+                    frac=achieved / peak if peak else None, traffic=traffic, traffic_note=traffic_note,
                     peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                     note=("algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernel issues 3 bf16 MMAs per algorithmic MAC "
                           "(bf16x3 split for fp32-grade accuracy), so the tensor pipe runs at 3x this rate") if dom == "tcgen05"

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libstorm_b200.so")
+_LIB_PATH = os.environ.get("STORM_B200_LIB", os.path.join(_HERE, "libstorm_b200.so"))   # override: A/B of two builds
 MAX_LEVELS = 8
 
 E_INVALID, E_CUDA, E_STATE, E_NOMEM = -1, -2, -3, -4
