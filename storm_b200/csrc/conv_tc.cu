@@ -208,8 +208,7 @@ int pack_common(const float* w, int Cout, int Cin, int taps, int io, void** out,
 // channel of the tile).  CTA = NPT pixel tiles x NMB 128-channel blocks, NPT*NMB*N <= 512 TMEM columns.
 // Warps 0-7: activation producers then epilogue; warp 8: weight producer; warp 9: TMEM alloc + MMA issue.
 // =====================================================================================================
-constexpr int P_THREADS = 320;
-constexpr int P_PRODUCERS = 256;
+constexpr int P_MAX_PRODUCERS = 384;
 
 struct TcpCfg {
   int rows;            // R: pixel-tile rows (32 or 16)
@@ -348,8 +347,11 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
 // global stores) overlaps the other's MMA main loop on the shared tensor pipe.
 // FUSE: compile the fused 1x1-skip path (extra raw planes / loads) only into the instantiation that uses it, so the
 // others keep their register budget (the <2,2> variant is capped at 102 registers).
-template <int MAXU, int MINB, bool FUSE>
-__global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+// NPW: activation-producer warps (the first 8 of them also run the epilogue); warp NPW = weight producer,
+// warp NPW + 1 = TMEM allocator + MMA issuer.
+template <int MAXU, int MINB, bool FUSE, int NPW>
+__global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+  constexpr int P_PRODUCERS = NPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = smem_u32(smem);
@@ -376,14 +378,14 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
     fence_barrier_init();
   }
   constexpr uint32_t TMEM_COLS = MINB == 1 ? 512 : 256;
-  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == NPW + 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp < 8) {
+  if (warp < NPW) {
     // =================================== activation producers ==========================================
     // Each thread owns up to 3 halo pixels per stage and handles all 16 channels (64 contiguous bytes) of each.
     // All global loads of a stage are issued before any is consumed (memory-level parallelism), and the next
@@ -523,7 +525,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
         if (++stage == c.sa) { stage = 0; phase ^= 1; }
       }
     }
-    // =================================== epilogue ======================================================
+    // =================================== epilogue (producer warps 0-7) ===================================
+    if (warp < 8) {
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     const long long t_e0 = dbg ? clock64() : 0;
     mbar_wait_relaxed(acc_full, 0);
@@ -601,7 +604,8 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
       p.dbg[4] = t_e1 - t_e0;          // producer warp 0 idle between its last stage and the accumulators being ready
       p.dbg[5] = clock64() - t_e1;     // epilogue duration (thread 0)
     }
-  } else if (warp == 8) {
+    }
+  } else if (warp == NPW) {
     // =================================== weight producer ================================================
     if (lane == 0) {
       int stage = 0;
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(P_THREADS, MINB) conv_tcp_kernel(ConvParams p,
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == NPW + 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 int g_tc_force_per_sm = 3;   // see choose_cfg_p (STORM_B200_TC_PER_SM)
@@ -723,7 +727,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   int sw = (budget - c.sa * c.a_stage - 256) / c.w_stage;
   c.sw = sw > 8 ? 8 : sw;
   if (c.sw < 2) return false;
-  if (c.per_sm == 2 && c.np > 2 * P_PRODUCERS) return false;
+  if (c.per_sm == 2 && c.np > 2 * 256) return false;
   c.tiles_x = ceil_div(p.W, 8 * k.npt);
   c.tiles_y = ceil_div(p.H, k.rows);
   return true;
@@ -745,9 +749,9 @@ int conv_tc_stats_chunks(const ConvParams& p) {
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
+    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
     attr = true;
   }
   TcpCfg cp;
@@ -756,9 +760,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-  if (cp.fuse) conv_tcp_kernel<2, 1, true><<<grid, P_THREADS, smem, st>>>(p, cp);
-  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, false><<<grid, P_THREADS, smem, st>>>(p, cp);
-  else conv_tcp_kernel<3, 1, false><<<grid, P_THREADS, smem, st>>>(p, cp);
+  if (cp.fuse) conv_tcp_kernel<2, 1, true, 8><<<grid, 320, smem, st>>>(p, cp);
+  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, false, 8><<<grid, 320, smem, st>>>(p, cp);
+  else conv_tcp_kernel<2, 1, false, 12><<<grid, 448, smem, st>>>(p, cp);      // np <= 612 <= 2 * 384
   STORM_LAUNCH_CHECK();
   return 0;
 }
