@@ -33,6 +33,16 @@ GFLOP_PER_UTT_NFE = 624.8       # algorithmic conv/NIN/a
 GB_PER_UTT_NFE = 0.879
 
 
+def workload_config(world: int, nfe: int = 60) -> dict:
+    """Same `config` object in both arms (native / --impl reference)."""
+    W = WORKLOAD
+    return dict(workload="BASELINE configs[1]: ncsnpp 27.8M, B=8/GPU, 32640 samples -> 256x256 complex STFT, N=30 PC "
+                         "(reverse_diffusion+ald x1, 60 NFE), random-init weights init_scale=1.0",
+                global_batch=world * W["B_per_gpu"], parallelism=f"dp{world} (utterance sharding, one NCCL weight broadcast)",
+                l2="working set per step (activations ~3 GB) >> 126 MB L2; no explicit flush", nfe=nfe,
+                tflop_per_step=world * W["B_per_gpu"] * nfe * GFLOP_PER_UTT_NFE / 1e3)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -153,8 +163,7 @@ def run_reference(args):
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * sum(dt for _, dt in rates) / len(rates), higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="ncsnpp 27.8M, B=8/GPU, 32640 samples -> 256x256 complex STFT, N=30 PC (reverse_diffusion+ald x1, 60 NFE)",
-                            note="CPU oracle port of the reference algorithm; bounded sample"),
+                config=workload_config(args.gpus),
                 cpu_baseline=dict(value=value, unit="utt/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit="utt/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -268,10 +277,7 @@ def run_native(args):
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (bf16x3 tensor-core split, fp32 accumulate)"
                 if dom == "tcgen05" else "f32", data="synthetic",
-                config=dict(workload="BASELINE configs[1]: ncsnpp 27.8M, B=8/GPU, 32640 samples -> 256x256 complex STFT, N=30 PC (reverse_diffusion+ald x1, 60 NFE), random-init weights init_scale=1.0",
-                            global_batch=world * B, parallelism=f"dp{world} (utterance sharding, one NCCL weight broadcast)",
-                            l2="working set per step (activations ~3 GB) >> 126 MB L2; no explicit flush", nfe=nfe,
-                            tflop_per_step=world * B * nfe * GFLOP_PER_UTT_NFE / 1e3),
+                config=workload_config(world, nfe),
                 roofline=roofline,
                 cpu_baseline=dict(value=cpu_rate, unit="utt/s", cores=threads, kind="port",
                                   sample=f"oracle port, B=1 256x256, 1 PC step ({cpu_nfe} NFE) in {cpu_dt:.1f}s, scaled linearly to 60 NFE"),
