@@ -275,8 +275,7 @@ def run_native(args):
     threads = pick_cpu_threads()
     cpu_rate, cpu_dt, cpu_nfe = cpu_oracle_rate(threads, W["N"] * 2)
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (bf16x3 tensor-core split, fp32 accumulate)"
-                if dom == "tcgen05" else "f32", data="synthetic",
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", dtype_detail="fp32 in/out; tensor-core products as bf16x3 split with fp32 accumulation (fp32-grade, ~2e-5)" if dom == "tcgen05" else "fp32 FFMA", data="synthetic",
                 config=workload_config(world, nfe),
                 roofline=roofline,
                 cpu_baseline=dict(value=cpu_rate, unit="utt/s", cores=threads, kind="port",

@@ -1111,11 +1111,15 @@ int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double 
   if (!h) return fail(STORM_E_INVALID, "null handle");
   STORM_CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 2; ++i) { launches[i] = 0; ms[i] = 0; flops[i] = 0; }
+  FILE* dump = nullptr;
+  if (const char* path = getenv("STORM_B200_PROFILE_DUMP")) dump = fopen(path, "w");   // per-launch list (tools/layer_sustained.py)
   for (auto& r : h->prof) {
     float t = 0.f;
     STORM_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
     launches[r.eng] += 1; ms[r.eng] += t; flops[r.eng] += r.flops;
+    if (dump) fprintf(dump, "%d,%.6f,%.0f\n", r.eng, t, r.flops);
   }
+  if (dump) fclose(dump);
   return 0;
 }
 
