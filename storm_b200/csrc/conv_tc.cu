@@ -525,21 +525,22 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
         if (++stage == c.sa) { stage = 0; phase ^= 1; }
       }
     }
-    // =================================== epilogue (producer warps 0-7) ===================================
-    if (warp < 8) {
+    // =================================== epilogue (every producer warp) ==================================
+    {
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     const long long t_e0 = dbg ? clock64() : 0;
     mbar_wait_relaxed(acc_full, 0);
     const long long t_e1 = dbg ? clock64() : 0;
     tc_fence_after();
-    const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which half of the work units
+    constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
+    const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
     const int nacc_main = c.npt * c.nmb;
     const int nacc = c.fuse ? 2 * nacc_main : nacc_main;     // fused skip: a second accumulator set after the main one
     const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
     const int nunits = nacc * units_per_acc;
     const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
     double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
-    for (int u = grp; u < nunits; u += 2) {
+    for (int u = grp; u < nunits; u += NGRP) {
       const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
       const bool is_skip = ai >= nacc_main;
       const int am = is_skip ? ai - nacc_main : ai;
@@ -562,36 +563,92 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
       if (p.bias && cok) add += __ldg(p.bias + cout);
       if (tembp && cok) add += __ldg(tembp + cout);
       float fs = 0.f, fq = 0.f;
-      float rv[32];
-      if (p.res) {     // issue every residual load of the unit before consuming any
+      const int uy0 = ty0 + g32 * 4, ux0 = tx0 + 8 * pt;       // the unit is a 4-row x 8-pixel patch
+      if (uy0 + 4 <= p.H && ux0 + 8 <= p.W && !(p.out_cm && (p.W & 3))) {
+        // ---- interior unit (every unit of the benchmark shapes): no per-element bounds checks, addresses are
+        // row pointer + constant multiples of the pixel stride
+        if (cok) {
+          if (p.out_cm) {                                       // channel-major: 8 contiguous floats per row
+            float* op = p.out + ((size_t)b * p.Cout + cout) * ((size_t)p.H * p.W) + (size_t)uy0 * p.W + ux0;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              float v[8];
+#pragma unroll
+              for (int xx = 0; xx < 8; ++xx) {
+                v[xx] = (__uint_as_float(r[rr * 8 + xx]) + add) * p.out_scale;
+                fs += v[xx];
+                fq = fmaf(v[xx], v[xx], fq);
+              }
+              float4* o4 = reinterpret_cast<float4*>(op + (size_t)rr * p.W);
+              o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          } else {
+            const size_t pix0 = (((size_t)b * p.H + uy0) * p.W + ux0) * p.Cout + cout;
+            const size_t rstride = (size_t)p.W * p.Cout;
+            float* op = p.out + pix0;
+            if (p.res) {
+              const float* rp = p.res + pix0;
+              float rv[32];
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int xx = 0; xx < 8; ++xx) rv[rr * 8 + xx] = __ldg(rp + rr * rstride + (size_t)xx * p.Cout);
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int xx = 0; xx < 8; ++xx) {
+                  const float v = (__uint_as_float(r[rr * 8 + xx]) + add + rv[rr * 8 + xx]) * p.out_scale;
+                  op[rr * rstride + (size_t)xx * p.Cout] = v;
+                  fs += v;
+                  fq = fmaf(v, v, fq);
+                }
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int xx = 0; xx < 8; ++xx) {
+                  const float v = (__uint_as_float(r[rr * 8 + xx]) + add) * p.out_scale;
+                  op[rr * rstride + (size_t)xx * p.Cout] = v;
+                  fs += v;
+                  fq = fmaf(v, v, fq);
+                }
+            }
+          }
+        }
+      } else {
+        float rv[32];
+        if (p.res) {     // issue every residual load of the unit before consuming any
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int y = uy0 + (jj >> 3);
+            const int x = ux0 + (jj & 7);
+            rv[jj] = (cok && y < p.H && x < p.W) ? __ldg(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout) : 0.f;
+          }
+        }
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const int y = ty0 + g32 * 4 + (jj >> 3);
-          const int x = tx0 + 8 * pt + (jj & 7);
-          rv[jj] = (cok && y < p.H && x < p.W) ? __ldg(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int y = ty0 + g32 * 4 + (jj >> 3);
-        const int x = tx0 + 8 * pt + (jj & 7);
-        if (cok && y < p.H && x < p.W) {
-          const size_t o = p.out_cm ? ((size_t)b * p.Cout + cout) * ((size_t)p.H * p.W) + (size_t)y * p.W + x
-                                    : (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
-          float v = __uint_as_float(r[jj]) + add;
-          if (p.res) v += rv[jj];
-          v *= p.out_scale;
-          p.out[o] = v;
-          fs += v;
-          fq = fmaf(v, v, fq);
+          const int y = uy0 + (jj >> 3);
+          const int x = ux0 + (jj & 7);
+          if (cok && y < p.H && x < p.W) {
+            const size_t o = p.out_cm ? ((size_t)b * p.Cout + cout) * ((size_t)p.H * p.W) + (size_t)y * p.W + x
+                                      : (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
+            float v = __uint_as_float(r[jj]) + add;
+            if (p.res) v += rv[jj];
+            v *= p.out_scale;
+            p.out[o] = v;
+            fs += v;
+            fq = fmaf(v, v, fq);
+          }
         }
       }
       s_sum[mb] += (double)fs;
       s_sq[mb] += (double)fq;
     }
     if (p.stats_out) {
-      // chunk index = (tile, grp): every (chunk, channel) slot is written exactly once per launch
-      const int chunk = tile * 2 + grp;
+      // chunk index = (tile, grp): every (chunk, channel) slot is written exactly once per launch (groups without a
+      // unit write zeros)
+      const int chunk = tile * NGRP + grp;
       for (int mb = 0; mb < c.nmb; ++mb) {
         const int cout = m_lo + mb * 128 + q * 32 + lane;
         if (cout >= p.Cout) continue;
@@ -693,6 +750,10 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   const Cand cands2b[] = {{32, 1, 1, 2}, {32, 1, 2, 1}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};          // Cout <= 256
   const Cand cands1m[] = {{32, 2, 1, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 1, 2}};
   const Cand cands2m[] = {{32, 1, 2, 1}, {32, 1, 1, 2}, {16, 2, 1, 2}, {16, 1, 2, 2}, {16, 1, 1, 2}};
+  // a candidate "fills the chip" from this many CTAs per resident slot: 120 lets the 64x64 levels of the benchmark
+  // (128 tiles of 256 pixels x 256 channels) run full-rate N=256 MMAs on 128 SMs instead of 512 smem-bound N=128 ones
+  static int min_fill = -1;
+  if (min_fill < 0) { const char* e = getenv("STORM_B200_TC_MINFILL"); min_fill = e ? atoi(e) : 120; }
   const bool big_first = g_tc_force_per_sm == 3 || p.nseg == 2;
   const Cand* cands = nblk == 1 ? (big_first ? cands1m : cands1b) : (big_first ? cands2m : cands2b);
   const int ncand = nblk == 1 ? 4 : 5;
@@ -706,7 +767,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     if (k.npt == 2 && p.W <= 8) continue;
     if (k.rows == 32 && p.H <= 16) continue;
     const long ctas = (long)ceil_div(p.H, k.rows) * ceil_div(p.W, 8 * k.npt) * (nblk / k.nmb) * p.B;
-    if (ctas >= 132L * k.per_sm) { best = i; break; }
+    if (ctas >= (long)min_fill * k.per_sm) { best = i; break; }
     if (ctas > best_ctas) { best_ctas = ctas; best = i; }
   }
   if (best < 0) return false;
@@ -735,6 +796,9 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
 
 }  // namespace
 
+// epilogue warp groups per TMEM lane quadrant (= GroupNorm partial-sum chunks per tile) of the kernel variant launched
+static int tc_ngrp(const TcpCfg& c) { return (c.per_sm == 1 && !c.fuse) ? 3 : 2; }
+
 bool conv_tc_eligible(const ConvParams& p) {
   TcpCfg cp;
   return choose_cfg_p(p, cp);
@@ -743,7 +807,7 @@ bool conv_tc_eligible(const ConvParams& p) {
 int conv_tc_stats_chunks(const ConvParams& p) {
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return 0;
-  return 2 * cp.tiles_x * cp.tiles_y;
+  return tc_ngrp(cp) * cp.tiles_x * cp.tiles_y;
 }
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
@@ -757,7 +821,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return fail(-1, "conv_tc: shape not eligible");
   if (p.out_cm && p.res) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
-  if (p.stats_out && p.stats_chunks != 2 * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+  if (p.stats_out && p.stats_chunks != tc_ngrp(cp) * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
   if (cp.fuse) conv_tcp_kernel<2, 1, true, 8><<<grid, 320, smem, st>>>(p, cp);
