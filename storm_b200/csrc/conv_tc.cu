@@ -258,7 +258,9 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   const uint64_t wd_const = make_desc(0, 128, 256);                                      // weight operand (A)
   const uint32_t a_half16 = (uint32_t)c.a_half >> 4, w_half16 = (uint32_t)c.w_half >> 4;
   const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
-  const uint32_t a_base16 = a_base >> 4, w_base16 = w_base >> 4;
+  // the descriptor start-address field is 14 bits of (address >> 4); mask explicitly (measured: in a cluster launch
+  // the shared::cta address of a CTA with rank > 0 carries bits above 256 KB that would spill into the LBO field)
+  const uint32_t a_base16 = (a_base >> 4) & 0x3FFFu, w_base16 = (w_base >> 4) & 0x3FFFu;
   const uint32_t ncol = (uint32_t)c.ncol;
   const int sa_n = c.sa, sw_n = c.sw;
   int sa = 0, sw = 0;
