@@ -4,9 +4,10 @@
     python enhancement.py --test_dir noisy/ --enhanced_dir out/ --ckpt model.ckpt --mode score-only \
         [--corrector ald] [--corrector-steps 1] [--snr 0.5] [--N 50]
 
-Extensions: --batch-size (utterances of equal padded length are enhanced together), --gpus (one process per
+Extensions: --batch-size (utterances of one padded-frame bucket are enhanced together, ragged lengths inside a batch), --gpus (one process per
 GPU via torchrun; files are sharded round-robin, one NCCL weight broadcast, no per-step collective), --seed,
---random-init BACKBONE (run without a checkpoint, for smoke tests).  wav I/O uses torchaudio like the reference.
+--random-init BACKBONE (run without a checkpoint, for smoke tests), --io-workers (wav reads / writes overlap the GPU work).
+wav I/O uses torchaudio like the reference when it has a backend, scipy.io.wavfile otherwise.
 """
 import glob
 import os
@@ -27,6 +28,7 @@ def build_parser() -> ArgumentParser:
     p.add_argument("--N", type=int, default=50, help="Number of reverse steps")
     p.add_argument("--batch-size", type=int, default=8)
     p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--io-workers", type=int, default=4, help="threads reading / writing wav files around the GPU work")
     p.add_argument("--random-init", type=str, default=None, help="backbone name: run with seeded random weights instead of --ckpt")
     return p
 
@@ -37,7 +39,6 @@ def shard(files, rank, world):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    import torchaudio
     from storm_b200 import ScoreModel, StochasticRegenerationModel
     if args.mode == "denoiser-only" and not args.random_init and args.ckpt is None:
         raise SystemExit("--ckpt is required")
@@ -67,32 +68,36 @@ def main(argv=None):
         for net in ([model.dnn] if args.mode == "score-only" else model._nets()):
             parallel.broadcast_weights(net, src=0)
 
+    from storm_b200.parallel import bucket_utterances
+    from storm_b200.util import wavio
     files = sorted(glob.glob(os.path.join(args.test_dir, "*.wav")))
     mine = [(i, f) for i, f in enumerate(files)][rank::world]
     model_sr = 16000
-    # bucket by padded length so that a batch shares one spectrogram shape
-    loaded = []
-    for idx, f in mine:
-        y, sr = torchaudio.load(f)
+
+    def load(item):
+        idx, f = item
+        y, sr = wavio.load_wav(f)
         assert sr == model_sr, "You need to make sure sample_sr matches model_sr --> resample to 16kHz"
-        loaded.append((idx, f, y[:1]))
-    loaded.sort(key=lambda t: t[2].shape[1])
-    if args.mode != "score-only":      # StoRM / denoiser-only: one utterance per call like the reference (enhancement.py:66-72)
-        for idx, f, y in loaded:
-            x_hat = model.enhance(y, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
-                                  denoiser_only=(args.mode == "denoiser-only"))
-            torchaudio.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().unsqueeze(0), model_sr)
-        loaded = []
-    i = 0
-    while i < len(loaded):
-        L = loaded[i][2].shape[1]
-        group = [t for t in loaded[i:i + args.batch_size] if t[2].shape[1] == L]
-        ys = torch.cat([t[2] for t in group], dim=0)
-        out = model.enhance_batch(ys, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
-                                  seed=args.seed, utt_ids=[t[0] for t in group])
-        for (idx, f, _), x_hat in zip(group, out):
-            torchaudio.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().unsqueeze(0), model_sr)
-        i += len(group)
+        return idx, f, y[:1]
+
+    with wavio.AsyncWriter(workers=args.io_workers) as writer:
+        if args.mode != "score-only":   # StoRM / denoiser-only: one utterance per call like the reference (enhancement.py:66-72)
+            for idx, f, y in wavio.Prefetcher(mine, load, depth=4, workers=args.io_workers):
+                x_hat = model.enhance(y, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
+                                      denoiser_only=(args.mode == "denoiser-only"))
+                writer.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().unsqueeze(0), model_sr)
+        else:
+            # lengths from the wav headers -> batches of one padded-frame bucket (ragged inside the bucket); the next
+            # batches are read by worker threads while the GPU enhances the current one, results are written behind it
+            lengths = [wavio.wav_length(f) for _, f in mine]
+            batches = [[mine[i] for i in b] for b in bucket_utterances(lengths, hop_length=model.data_module.hop_length,
+                                                                       max_batch=args.batch_size)]
+            for group in wavio.Prefetcher(batches, lambda b: [load(it) for it in b], depth=2, workers=args.io_workers):
+                outs = model.enhance_batch([t[2] for t in group], corrector=args.corrector, N=args.N,
+                                           corrector_steps=args.corrector_steps, snr=args.snr, seed=args.seed,
+                                           utt_ids=[t[0] for t in group], max_batch=args.batch_size)
+                for (idx, f, _), x_hat in zip(group, outs):
+                    writer.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().reshape(1, -1), model_sr)
     if world > 1:
         dist.destroy_process_group()
 

@@ -160,12 +160,35 @@ int storm_stft(const float* wav, const float* norm, int32_t B, int32_t L, float*
 int storm_istft(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
                 const StormSpecConfig* sp, void* stream);
 
+/* Ragged batches.  The reference enhances one file at a time (enhancement.py:66-72), so every utterance has its own
+ * length: its own reflect padding, frame count 1 + L_b/hop (data_module.py:217-219), pad_spec amount and istft
+ * length (model.py:301).  Utterances whose padded frame counts agree (same storm_padded_frames(storm_num_frames(L_b)))
+ * can share one [B][F][T_pad] batch without changing any result, because GroupNorm, attention and the sampler are
+ * per sample.  `lengths`: int32 [B] on the DEVICE, L_b <= L (the row stride), all in the frame bucket of L; NULL =
+ * every row is L samples.  Samples of a row beyond L_b are ignored on input and written as zeros on output. */
+int storm_wave_norm_ragged(const float* wav, int32_t B, int32_t L, const int32_t* lengths, float* norm, void* stream);
+int storm_stft_ragged(const float* wav, const float* norm, int32_t B, int32_t L, const int32_t* lengths, float* spec,
+                      int32_t T_pad, const StormSpecConfig* sp, void* stream);
+int storm_istft_ragged(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
+                       const int32_t* lengths, const StormSpecConfig* sp, void* stream);
+
 /* ---- one-call enhancement ---------------------------------------------------------------------------
  * ScoreModel.enhance for a batch (sgmse/model.py:273-310): normalise, STFT, transform, pad, PC-sample,
  * inverse transform, iSTFT, de-normalise.  wav_in / wav_out: float [B][L] device. */
 int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L,
                   const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed,
                   const uint64_t* utt_ids, int32_t* nfe_out, void* stream);
+/* same for a ragged batch of one frame bucket (see above); L = row stride = the longest utterance of the batch */
+int storm_enhance_ragged(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const int32_t* lengths,
+                         const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids,
+                         int32_t* nfe_out, void* stream);
+
+/* ---- evaluation metric on the device ------------------------------------------------------------------
+ * si_sdr / si_sdr_torch (sgmse/util/other.py:82-94) for a batch: s (reference) and s_hat (estimate) float [B][L]
+ * device, optional int32 lengths [B] device (ragged rows), out_db float [B] device.  eps = 0 gives the numpy form
+ * (other.py:82-86), eps = 1e-10 the torch form (other.py:88-94).  fp64 accumulation, deterministic. */
+int storm_si_sdr(const float* s, const float* s_hat, int32_t B, int32_t L, const int32_t* lengths, double eps,
+                 float* out_db, void* stream);
 
 /* Kernel-launch counter (bench.py's gpu_launches). */
 int64_t storm_launch_count(const StormHandle* h);

@@ -298,7 +298,23 @@ def gen_storm(ns):
          **sd_arrays(den.state_dict(), "den/"), **sd_arrays(score.state_dict(), "score/"))
 
 
-GENS = dict(storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
+def gen_metrics(ns):
+    """si_sdr / si_sdr_torch (util/other.py:82-94) on clean/estimate pairs at several SNRs and lengths."""
+    g = torch.Generator().manual_seed(10)
+    arrs = {}
+    for tag, L, noise in [("a", 4000, 0.5), ("b", 32640, 0.05), ("c", 16000, 0.001), ("d", 777, 2.0)]:
+        s = torch.randn(L, generator=g) * 0.1
+        s_hat = 0.7 * s + noise * 0.1 * torch.randn(L, generator=g)
+        arrs.update({f"{tag}/s": s, f"{tag}/s_hat": s_hat,
+                     f"{tag}/si_sdr": np.float64(ns.si_sdr(s.double().numpy(), s_hat.double().numpy())),
+                     f"{tag}/si_sdr_torch": ns.si_sdr_torch(s, s_hat)})
+    s = torch.randn(3000, generator=g) * 0.1
+    arrs.update({"e/s": s, "e/s_hat": s[:2500] * 1.3 + 0.01 * torch.randn(2500, generator=g)})
+    arrs["e/si_sdr_torch"] = ns.si_sdr_torch(arrs["e/s"], arrs["e/s_hat"])      # different lengths: truncation
+    save("metrics", **arrs)
+
+
+GENS = dict(metrics=gen_metrics, storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
             net_full=gen_net_full, sampler=gen_sampler, stft=gen_stft, enhance=gen_enhance)
 
 if __name__ == "__main__":

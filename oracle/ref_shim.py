@@ -54,11 +54,11 @@ def load():
     from sgmse import sampling
     from sgmse.sampling import predictors, correctors
     from sgmse.data_module import SpecsDataModule
-    from sgmse.util.other import pad_spec
+    from sgmse.util.other import pad_spec, si_sdr, si_sdr_torch
 
     ns = types.SimpleNamespace(
         BackboneRegistry=BackboneRegistry, layerspp=layerspp, up_or_down_sampling=up_or_down_sampling,
         SDERegistry=SDERegistry, OUVESDE=OUVESDE, sampling=sampling, predictors=predictors,
-        correctors=correctors, SpecsDataModule=SpecsDataModule, pad_spec=pad_spec,
+        correctors=correctors, SpecsDataModule=SpecsDataModule, pad_spec=pad_spec, si_sdr=si_sdr, si_sdr_torch=si_sdr_torch,
     )
     return ns

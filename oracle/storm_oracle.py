@@ -502,6 +502,19 @@ def enhance_storm(sd_den, sd_score, cfg_den: NetCfg, cfg_score: NetCfg, y: Tenso
     return x_hat.squeeze(), nfe
 
 
+def si_sdr(s, s_hat) -> float:                                      # util/other.py:82-86 (numpy form)
+    s, s_hat = np.asarray(s, dtype=np.float64), np.asarray(s_hat, dtype=np.float64)
+    alpha = np.dot(s_hat, s) / np.linalg.norm(s) ** 2
+    return float(10 * np.log10(np.linalg.norm(alpha * s) ** 2 / np.linalg.norm(alpha * s - s_hat) ** 2))
+
+
+def si_sdr_torch(s: Tensor, s_hat: Tensor) -> Tensor:               # util/other.py:88-94 (torch form, 1e-10 guards)
+    n = min(s.size(-1), s_hat.size(-1))
+    s, s_hat = s[..., :n], s_hat[..., :n]
+    alpha = torch.dot(s_hat, s) / torch.norm(s) ** 2
+    return 10 * torch.log10(1e-10 + torch.norm(alpha * s) ** 2 / (1e-10 + torch.norm(alpha * s - s_hat) ** 2))
+
+
 def synth_utterance(b: int, L: int) -> Tensor:
     """Synthetic noisy speech of SURVEY.md section 8(d): 5 harmonics of a random f0 with a 4 Hz on/off
     envelope plus white noise; generator seeded with 1234 + b.  Returns float32 [L]."""

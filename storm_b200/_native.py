@@ -72,6 +72,14 @@ _PROTOS = {
                               C.POINTER(SpecConfig), C.c_void_p]),
     "storm_enhance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SamplerConfig),
                                 C.POINTER(SpecConfig), C.c_uint64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "storm_wave_norm_ragged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "storm_stft_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.POINTER(SpecConfig), C.c_void_p]),
+    "storm_istft_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.POINTER(SpecConfig), C.c_void_p]),
+    "storm_enhance_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(SamplerConfig),
+                                       C.POINTER(SpecConfig), C.c_uint64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "storm_si_sdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "storm_launch_count": (C.c_int64, [C.c_void_p]),
     "storm_reset_launch_count": (C.c_int, [C.c_void_p]),
     "storm_debug_conv": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
@@ -314,26 +322,31 @@ class Engine:
         return out
 
     # ---- STFT ---------------------------------------------------------------------------------------------
-    def istft(self, spec: torch.Tensor, norm: Optional[torch.Tensor], L: int, sp: SpecConfig) -> torch.Tensor:
+    def istft(self, spec: torch.Tensor, norm: Optional[torch.Tensor], L: int, sp: SpecConfig,
+              lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """lengths: optional int32 CUDA tensor [B] (ragged batch of one frame bucket, row stride L)."""
         spec = _cf(spec, "spec")
         B, F, T = spec.shape
         if F != sp.n_fft // 2 + 1:
             raise ValueError("spectrogram does not have n_fft/2+1 bins")
         wav = torch.empty((B, L), dtype=torch.float32, device=spec.device)
-        _check(lib().storm_istft(self._h, spec.data_ptr(), _ptr(norm), B, T, wav.data_ptr(), L, C.byref(sp), _stream()))
+        _check(lib().storm_istft_ragged(self._h, spec.data_ptr(), _ptr(norm), B, T, wav.data_ptr(), L, _ptr(_lens(lengths, B, L, sp)),
+                                        C.byref(sp), _stream()))
         return wav
 
     def enhance(self, wav: torch.Tensor, sc: SamplerConfig, sp: SpecConfig, seed: int = 0,
-                utt_ids: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, int]:
+                utt_ids: Optional[Sequence[int]] = None, lengths: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
         wav = _cf(wav.to(torch.float32), "wav")
         B, L = wav.shape
+        lengths = _lens(lengths, B, L, sp)
         out = torch.empty_like(wav)
         ids = None
         if utt_ids is not None:
             ids = (C.c_uint64 * B)(*[int(u) for u in utt_ids])
         nfe = C.c_int32()
-        _check(lib().storm_enhance(self._h, wav.data_ptr(), out.data_ptr(), B, L, C.byref(sc), C.byref(sp), C.c_uint64(seed),
-                                   C.cast(ids, C.c_void_p) if ids is not None else None, C.byref(nfe), _stream()))
+        _check(lib().storm_enhance_ragged(self._h, wav.data_ptr(), out.data_ptr(), B, L, _ptr(lengths), C.byref(sc), C.byref(sp),
+                                          C.c_uint64(seed), C.cast(ids, C.c_void_p) if ids is not None else None, C.byref(nfe),
+                                          _stream()))
         return out, int(nfe.value)
 
 
@@ -348,12 +361,43 @@ class _DevView:
 
 
 # ---- handle-free entry points ------------------------------------------------------------------------------
-def wave_norm(wav: torch.Tensor) -> torch.Tensor:
+def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> Optional[torch.Tensor]:
+    """Validate per-utterance lengths of a ragged batch (host-side, the library cannot see device values): int32 CUDA
+    tensor [B], every L_b <= L, longer than the STFT reflect padding, and - when a SpecConfig is given - in the same
+    padded-frame bucket as L (otherwise the batch would not reproduce per-file results)."""
+    if lengths is None:
+        return None
+    lh = [int(v) for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+    if len(lh) != B:
+        raise ValueError(f"lengths has {len(lh)} entries for a batch of {B}")
+    for v in lh:
+        if v < 1 or v > L:
+            raise ValueError(f"utterance length {v} outside (0, {L}]")
+        if sp is not None:
+            if v <= sp.n_fft // 2:
+                raise ValueError(f"utterance of {v} samples is shorter than the STFT reflect padding ({sp.n_fft // 2})")
+            if padded_frames(num_frames(v, sp)) != padded_frames(num_frames(L, sp)):
+                raise ValueError(f"lengths {v} and {L} fall into different padded-frame buckets; batch them separately")
+    return torch.tensor(lh, dtype=torch.int32, device="cuda")
+
+
+def wave_norm(wav: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     wav = _cf(wav, "wav")
     B, L = wav.shape
     norm = torch.empty((B,), dtype=torch.float32, device=wav.device)
-    _check(lib().storm_wave_norm(wav.data_ptr(), B, L, norm.data_ptr(), _stream()))
+    _check(lib().storm_wave_norm_ragged(wav.data_ptr(), B, L, _ptr(_lens(lengths, B, L)), norm.data_ptr(), _stream()))
     return norm
+
+
+def si_sdr(s: torch.Tensor, s_hat: torch.Tensor, lengths: Optional[torch.Tensor] = None, eps: float = 0.0) -> torch.Tensor:
+    """SI-SDR in dB per row of [B, L] CUDA tensors (sgmse/util/other.py:82-94); eps=1e-10 is the si_sdr_torch form."""
+    s, s_hat = _cf(s.to(torch.float32), "s"), _cf(s_hat.to(torch.float32), "s_hat")
+    if s.shape != s_hat.shape or s.dim() != 2:
+        raise ValueError("si_sdr expects two [B, L] tensors of the same shape")
+    B, L = s.shape
+    out = torch.empty((B,), dtype=torch.float32, device=s.device)
+    _check(lib().storm_si_sdr(s.data_ptr(), s_hat.data_ptr(), B, L, _ptr(_lens(lengths, B, L)), float(eps), out.data_ptr(), _stream()))
+    return out
 
 
 def num_frames(L: int, sp: SpecConfig) -> int:
@@ -364,13 +408,15 @@ def padded_frames(frames: int) -> int:
     return lib().storm_padded_frames(frames)
 
 
-def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad: Optional[int] = None) -> torch.Tensor:
+def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad: Optional[int] = None,
+         lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     wav = _cf(wav.to(torch.float32), "wav")
     B, L = wav.shape
     frames = num_frames(L, sp)
     T_pad = frames if T_pad is None else T_pad
     spec = torch.empty((B, sp.n_fft // 2 + 1, T_pad), dtype=torch.complex64, device=wav.device)
-    _check(lib().storm_stft(wav.data_ptr(), _ptr(norm), B, L, spec.data_ptr(), T_pad, C.byref(sp), _stream()))
+    _check(lib().storm_stft_ragged(wav.data_ptr(), _ptr(norm), B, L, _ptr(_lens(lengths, B, L, sp)), spec.data_ptr(), T_pad,
+                                   C.byref(sp), _stream()))
     return spec
 
 

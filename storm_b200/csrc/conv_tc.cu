@@ -531,15 +531,28 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     {
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     const long long t_e0 = dbg ? clock64() : 0;
-    mbar_wait_relaxed(acc_full, 0);
-    const long long t_e1 = dbg ? clock64() : 0;
-    tc_fence_after();
     constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
     const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
     const int nacc_main = c.npt * c.nmb;
     const int nacc = c.fuse ? 2 * nacc_main : nacc_main;     // fused skip: a second accumulator set after the main one
     const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
     const int nunits = nacc * units_per_acc;
+    if (p.res && !p.out_cm) {
+      // the producers are idle until the accumulators are complete: pull the residual lines this warp will add
+      // into L2 now (one 128-byte line per pixel per warp), so the epilogue loads do not pay HBM latency
+      for (int u = grp; u < nunits; u += NGRP) {
+        const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
+        if (ai >= nacc_main) continue;
+        const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
+        const int y = ty0 + g32 * 4 + (lane >> 3), x = tx0 + 8 * pt + (lane & 7);
+        const int cb = m_lo + mb * 128 + q * 32;
+        if (y < p.H && x < p.W && cb < p.Cout)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cb));
+      }
+    }
+    mbar_wait_relaxed(acc_full, 0);
+    const long long t_e1 = dbg ? clock64() : 0;
+    tc_fence_after();
     const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
     double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
     for (int u = grp; u < nunits; u += NGRP) {

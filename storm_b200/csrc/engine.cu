@@ -1214,30 +1214,48 @@ int storm_debug_attention(int32_t engine, const float* q, const float* k, const 
 int32_t storm_num_frames(int32_t L, const StormSpecConfig* sp) { return sp && sp->hop_length > 0 ? 1 + L / sp->hop_length : 0; }
 int32_t storm_padded_frames(int32_t frames) { return (frames + 63) / 64 * 64; }
 
-int storm_wave_norm(const float* wav, int32_t B, int32_t L, float* norm, void* stream) {
+int storm_wave_norm_ragged(const float* wav, int32_t B, int32_t L, const int32_t* lengths, float* norm, void* stream) {
   if (!wav || !norm) return fail(STORM_E_INVALID, "storm_wave_norm: null argument");
-  return launch_wave_norm(wav, B, L, norm, (cudaStream_t)stream);
+  return launch_wave_norm(wav, B, L, lengths, norm, (cudaStream_t)stream);
+}
+int storm_wave_norm(const float* wav, int32_t B, int32_t L, float* norm, void* stream) {
+  return storm_wave_norm_ragged(wav, B, L, nullptr, norm, stream);
+}
+int storm_stft_ragged(const float* wav, const float* norm, int32_t B, int32_t L, const int32_t* lengths, float* spec, int32_t T_pad,
+                      const StormSpecConfig* sp, void* stream) {
+  if (!wav || !spec || !sp) return fail(STORM_E_INVALID, "storm_stft: null argument");
+  return launch_stft(wav, norm, B, L, lengths, spec, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+                     sp->spec_abs_exponent, (cudaStream_t)stream);
 }
 int storm_stft(const float* wav, const float* norm, int32_t B, int32_t L, float* spec, int32_t T_pad, const StormSpecConfig* sp,
                void* stream) {
-  if (!wav || !spec || !sp) return fail(STORM_E_INVALID, "storm_stft: null argument");
-  return launch_stft(wav, norm, B, L, spec, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
-                     sp->spec_abs_exponent, (cudaStream_t)stream);
+  return storm_stft_ragged(wav, norm, B, L, nullptr, spec, T_pad, sp, stream);
 }
-int storm_istft(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
-                const StormSpecConfig* sp, void* stream) {
+int storm_istft_ragged(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
+                       const int32_t* lengths, const StormSpecConfig* sp, void* stream) {
   if (!h || !spec || !wav || !sp) return fail(STORM_E_INVALID, "storm_istft: null argument");
   void* p;
   STORM_TRY(h->pool.get((size_t)B * T_pad * sp->n_fft * sizeof(float), &p));
-  int rc = launch_istft(spec, norm, B, T_pad, (float*)p, wav, L, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+  int rc = launch_istft(spec, norm, B, T_pad, (float*)p, wav, L, lengths, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
                         sp->spec_abs_exponent, (cudaStream_t)stream);
   h->launches += 2;
   h->pool.put(p);
   return rc;
 }
+int storm_istft(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
+                const StormSpecConfig* sp, void* stream) {
+  return storm_istft_ragged(h, spec, norm, B, T_pad, wav, L, nullptr, sp, stream);
+}
 
-int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const StormSamplerConfig* sc,
-                  const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids, int32_t* nfe_out, void* stream) {
+int storm_si_sdr(const float* s, const float* s_hat, int32_t B, int32_t L, const int32_t* lengths, double eps, float* out_db,
+                 void* stream) {
+  if (!s || !s_hat || !out_db || B < 1 || L < 1) return fail(STORM_E_INVALID, "storm_si_sdr: bad argument");
+  return launch_si_sdr(s, s_hat, B, L, lengths, eps, out_db, (cudaStream_t)stream);
+}
+
+int storm_enhance_ragged(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const int32_t* lengths,
+                         const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids,
+                         int32_t* nfe_out, void* stream) {
   if (!h || !wav_in || !wav_out || !sp) return fail(STORM_E_INVALID, "storm_enhance: null argument");
   STORM_TRY(check_sampler(sc));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1247,13 +1265,17 @@ int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B
   STORM_TRY(h->pool.get((size_t)B * 4, &p)); float* norm = (float*)p;
   STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* Y = (float*)p;
   STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* X = (float*)p;
-  LAUNCH(h, launch_wave_norm(wav_in, B, L, norm, st));
-  LAUNCH(h, launch_stft(wav_in, norm, B, L, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+  LAUNCH(h, launch_wave_norm(wav_in, B, L, lengths, norm, st));
+  LAUNCH(h, launch_stft(wav_in, norm, B, L, lengths, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
                         sp->spec_abs_exponent, st));
   STORM_TRY(pc_sample(h, Y, nullptr, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
-  STORM_TRY(storm_istft(h, X, norm, B, T_pad, wav_out, L, sp, stream));
+  STORM_TRY(storm_istft_ragged(h, X, norm, B, T_pad, wav_out, L, lengths, sp, stream));
   h->pool.put(norm); h->pool.put(Y); h->pool.put(X);
   return 0;
+}
+int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const StormSamplerConfig* sc,
+                  const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids, int32_t* nfe_out, void* stream) {
+  return storm_enhance_ragged(h, wav_in, wav_out, B, L, nullptr, sc, sp, seed, utt_ids, nfe_out, stream);
 }
 
 }  // extern "C"

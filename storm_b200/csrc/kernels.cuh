@@ -82,14 +82,17 @@ int launch_ode_drift(const float* x, const float* y, const float* d, float* out,
                      int64_t n_total, cudaStream_t st);
 
 // ---- STFT / iSTFT (data_module.py:182-223) -----------------------------------------------------------
-int launch_wave_norm(const float* wav, int B, int L, float* norm, cudaStream_t st);
-int launch_stft(const float* wav, const float* norm, int B, int L, float* spec, int T_pad, int n_fft, int hop,
+// lens (optional, device int[B]): per-utterance true lengths inside the L-sample rows (ragged batch of one frame bucket)
+int launch_wave_norm(const float* wav, int B, int L, const int* lens, float* norm, cudaStream_t st);
+int launch_stft(const float* wav, const float* norm, int B, int L, const int* lens, float* spec, int T_pad, int n_fft, int hop,
                 int sqrt_window, float factor, float expo, cudaStream_t st);
 // frames_buf: [B][T_pad][n_fft] scratch
-int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* frames_buf, float* wav, int L, int n_fft,
-                 int hop, int sqrt_window, float factor, float expo, cudaStream_t st);
+int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* frames_buf, float* wav, int L, const int* lens,
+                 int n_fft, int hop, int sqrt_window, float factor, float expo, cudaStream_t st);
 
 // NHWC -> NCHW (debug taps)
+// SI-SDR in dB per utterance (util/other.py:82-94); eps = 0 (numpy form) or 1e-10 (torch form)
+int launch_si_sdr(const float* s, const float* s_hat, int B, int L, const int* lens, double eps, float* out, cudaStream_t st);
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t st);
 
 }  // namespace storm

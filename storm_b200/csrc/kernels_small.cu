@@ -150,22 +150,30 @@ int launch_temb_mlp(const float* t, const float* Wf, const float* W1t, const flo
   return 0;
 }
 
-__global__ void __launch_bounds__(64) dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int B, int in_dim,
-                                                       int out_dim) {
-  extern __shared__ float s_act[];   // [8][in_dim]
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+// 64 outputs x KS k-slices per CTA: the 64 x in_dim weight panel is read once, coalesced along the outputs, with
+// KS x 8 independent loads in flight per output instead of one serial chain over in_dim (latency-bound before);
+// slice partials are summed in a fixed order through shared memory (deterministic).
+constexpr int DENSE_KS = 8;   // at most; the launcher picks the largest power of two that divides in_dim / 8
+__global__ void __launch_bounds__(64 * DENSE_KS) dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt,
+                                                                  const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                                  int in_dim, int out_dim) {
+  extern __shared__ float s_act[];   // [8][in_dim] then [DENSE_KS][64][8] partials
+  float* s_part = s_act + 8 * in_dim;
+  const int tx = threadIdx.x & 63, ks = threadIdx.x >> 6;
+  const int o = blockIdx.x * 64 + tx;
+  const int KS = blockDim.x >> 6;
+  const int kper = in_dim / KS;                       // multiple of 8 (chosen by the launcher)
   for (int b0 = 0; b0 < B; b0 += 8) {
     const int nb = min(8, B - b0);
     __syncthreads();
     for (int e = threadIdx.x; e < 8 * in_dim; e += blockDim.x)
       s_act[e] = (e / in_dim < nb) ? act[(size_t)b0 * in_dim + e] : 0.f;
     __syncthreads();
-    if (o < out_dim) {
-      float acc[8];
+    float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bias[o];
-      for (int i = 0; i < in_dim; i += 8) {
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (o < out_dim) {
+      for (int i = ks * kper; i < (ks + 1) * kper; i += 8) {
         float wv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) wv[k] = __ldg(Wt + (size_t)(i + k) * out_dim + o);
@@ -174,16 +182,28 @@ __global__ void __launch_bounds__(64) dense_all_kernel(const float* __restrict__
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv[k], s_act[j * in_dim + i + k], acc[j]);
       }
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nb) out[(size_t)(b0 + j) * out_dim + o] = acc[j];
+    for (int j = 0; j < 8; ++j) s_part[(ks * 64 + tx) * 8 + j] = acc[j];
+    __syncthreads();
+    if (ks == 0 && o < out_dim) {
+      const float bv = bias[o];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = bv;
+        for (int q = 0; q < KS; ++q) v += s_part[(q * 64 + tx) * 8 + j];
+        if (j < nb) out[(size_t)(b0 + j) * out_dim + o] = v;
+      }
     }
   }
 }
 int launch_dense_all(const float* act, const float* Wt, const float* bias, float* out, int B, int in_dim, int out_dim,
                      cudaStream_t st) {
   if (in_dim % 8 != 0 || in_dim > 1024) return fail(-1, "dense_all: in_dim must be a multiple of 8 and <= 1024");
-  dense_all_kernel<<<ceil_div(out_dim, 64), 64, 8 * in_dim * sizeof(float), st>>>(act, Wt, bias, out, B, in_dim, out_dim);
+  int ks = DENSE_KS;
+  while (ks > 1 && in_dim % (8 * ks) != 0) ks >>= 1;
+  const size_t smem = (size_t)(8 * in_dim + ks * 64 * 8) * sizeof(float);
+  dense_all_kernel<<<ceil_div(out_dim, 64), 64 * ks, smem, st>>>(act, Wt, bias, out, B, in_dim, out_dim);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1050,10 +1070,12 @@ int launch_ode_drift(const float* x, const float* y, const float* d, float* out,
 // =====================================================================================================
 // STFT / iSTFT (direct DFT of length n_fft = 510 = 2*3*5*17: not a power of two, data_module.py:143,232)
 // =====================================================================================================
-__global__ void wave_norm_kernel(const float* __restrict__ wav, int L, float* __restrict__ norm) {
+// `lens` (optional, device): true length of every utterance inside its L-sample row (ragged batches of one frame bucket)
+__global__ void wave_norm_kernel(const float* __restrict__ wav, int L, const int* __restrict__ lens, float* __restrict__ norm) {
   const int b = blockIdx.x;
+  const int Lb = lens ? min(lens[b], L) : L;
   float m = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(wav[(size_t)b * L + i]));
+  for (int i = threadIdx.x; i < Lb; i += blockDim.x) m = fmaxf(m, fabsf(wav[(size_t)b * L + i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ float r[32];
@@ -1064,8 +1086,8 @@ __global__ void wave_norm_kernel(const float* __restrict__ wav, int L, float* __
     norm[b] = m;
   }
 }
-int launch_wave_norm(const float* wav, int B, int L, float* norm, cudaStream_t st) {
-  wave_norm_kernel<<<B, 1024, 0, st>>>(wav, L, norm);
+int launch_wave_norm(const float* wav, int B, int L, const int* lens, float* norm, cudaStream_t st) {
+  wave_norm_kernel<<<B, 1024, 0, st>>>(wav, L, lens, norm);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1079,14 +1101,16 @@ __device__ __forceinline__ float window_at(int n, int n_fft, int sqrt_window) {
 }  // namespace
 
 // smem: frame[n_fft] floats, tw[n_fft] float2
-__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav, const float* __restrict__ norm, int L,
-                                                   float2* __restrict__ spec, int T_pad, int n_frames, int n_fft, int hop,
-                                                   int sqrt_window, float factor, float expo) {
+__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav, const float* __restrict__ norm, int Lrow,
+                                                   const int* __restrict__ lens, float2* __restrict__ spec, int T_pad, int n_fft,
+                                                   int hop, int sqrt_window, float factor, float expo) {
   extern __shared__ float sm[];
   float* frame = sm;
   float2* tw = reinterpret_cast<float2*>(sm + n_fft + (n_fft & 1));
   const int f = blockIdx.x, b = blockIdx.y;
   const int nb = n_fft / 2 + 1;
+  const int L = lens ? min(lens[b], Lrow) : Lrow;      // this utterance's own length: its own reflect padding and frame count
+  const int n_frames = 1 + L / hop;
   if (f >= n_frames) {   // pad_spec: zero frames up to the next multiple of 64 (util/other.py:102-109)
     for (int k = threadIdx.x; k < nb; k += blockDim.x) spec[((size_t)b * nb + k) * T_pad + f] = make_float2(0.f, 0.f);
     return;
@@ -1097,7 +1121,8 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav
     int j = f * hop + n - pad;                 // center=True, reflect padding (torch.stft)
     if (j < 0) j = -j;
     if (j >= L) j = 2 * (L - 1) - j;
-    float v = wav[(size_t)b * L + j];
+    j = max(0, min(j, L - 1));                 // only reachable for signals shorter than the padding (rejected by the callers)
+    float v = wav[(size_t)b * Lrow + j];
     if (norm) v = v / nrm;                     // y = y / norm_factor (model.py:284)
     frame[n] = v * window_at(n, n_fft, sqrt_window);
     double s, c;
@@ -1130,13 +1155,13 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav
     spec[((size_t)b * nb + k) * T_pad + f] = make_float2(re * factor, im * factor);
   }
 }
-int launch_stft(const float* wav, const float* norm, int B, int L, float* spec, int T_pad, int n_fft, int hop, int sqrt_window,
-                float factor, float expo, cudaStream_t st) {
+int launch_stft(const float* wav, const float* norm, int B, int L, const int* lens, float* spec, int T_pad, int n_fft, int hop,
+                int sqrt_window, float factor, float expo, cudaStream_t st) {
   if (L <= n_fft / 2) return fail(-1, "stft: signal shorter than the reflect padding");
   const int n_frames = 1 + L / hop;
   if (T_pad < n_frames) return fail(-1, "stft: T_pad smaller than the frame count");
   size_t smem = (size_t)(n_fft + (n_fft & 1)) * sizeof(float) + (size_t)n_fft * sizeof(float2);
-  stft_kernel<<<dim3(T_pad, B), 256, smem, st>>>(wav, norm, L, reinterpret_cast<float2*>(spec), T_pad, n_frames, n_fft, hop,
+  stft_kernel<<<dim3(T_pad, B), 256, smem, st>>>(wav, norm, L, lens, reinterpret_cast<float2*>(spec), T_pad, n_fft, hop,
                                                 sqrt_window, factor, expo);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -1191,9 +1216,11 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restr
   }
 }
 __global__ void istft_ola_kernel(const float* __restrict__ frames_buf, const float* __restrict__ norm, int T_pad,
-                                 float* __restrict__ wav, int L, int n_fft, int hop, int sqrt_window) {
+                                 float* __restrict__ wav, int L, const int* __restrict__ lens, int n_fft, int hop, int sqrt_window) {
   const int b = blockIdx.y;
+  const int Lb = lens ? min(lens[b], L) : L;           // torch.istft(length = this utterance's length); the row tail is zeroed
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < L; m += gridDim.x * blockDim.x) {
+    if (m >= Lb) { wav[(size_t)b * L + m] = 0.f; continue; }
     const int mp = m + n_fft / 2;
     int f_lo = (mp - n_fft + 1 + hop - 1) / hop;
     if (mp - n_fft + 1 < 0) f_lo = 0;
@@ -1211,16 +1238,65 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames_buf, const flo
     wav[(size_t)b * L + m] = v;
   }
 }
-int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* frames_buf, float* wav, int L, int n_fft, int hop,
-                 int sqrt_window, float factor, float expo, cudaStream_t st) {
+int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* frames_buf, float* wav, int L, const int* lens,
+                 int n_fft, int hop, int sqrt_window, float factor, float expo, cudaStream_t st) {
   if (n_fft & 1) return fail(-1, "istft: n_fft must be even");
   const int nb = n_fft / 2 + 1;
   size_t smem = (size_t)(nb + n_fft) * sizeof(float2);
   istft_frames_kernel<<<dim3(T_pad, B), 256, smem, st>>>(reinterpret_cast<const float2*>(spec), T_pad, frames_buf, n_fft, sqrt_window,
                                                         factor, expo);
   STORM_LAUNCH_CHECK();
-  istft_ola_kernel<<<dim3(ceil_div(L, 256) > 512 ? 512 : ceil_div(L, 256), B), 256, 0, st>>>(frames_buf, norm, T_pad, wav, L, n_fft, hop,
-                                                                                       sqrt_window);
+  istft_ola_kernel<<<dim3(ceil_div(L, 256) > 512 ? 512 : ceil_div(L, 256), B), 256, 0, st>>>(frames_buf, norm, T_pad, wav, L, lens, n_fft,
+                                                                                       hop, sqrt_window);
+  STORM_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// SI-SDR (sgmse/util/other.py:82-94): alpha = <s_hat, s> / |s|^2 ; 10 log10(|alpha s|^2 / |alpha s - s_hat|^2)
+// One CTA per utterance, two passes, fp64 accumulation in a fixed order (deterministic).  eps = 0 reproduces si_sdr
+// (numpy), eps = 1e-10 si_sdr_torch.
+// =====================================================================================================
+namespace {
+__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+}  // namespace
+__global__ void __launch_bounds__(1024) si_sdr_kernel(const float* __restrict__ s, const float* __restrict__ sh, int L,
+                                                      const int* __restrict__ lens, double eps, float* __restrict__ out) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const int Lb = lens ? min(lens[b], L) : L;
+  const float* sp = s + (size_t)b * L;
+  const float* hp = sh + (size_t)b * L;
+  double dot = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < Lb; i += blockDim.x) {
+    const double a = sp[i], c = hp[i];
+    dot = fma(c, a, dot);
+    ss = fma(a, a, ss);
+  }
+  dot = block_sum_1024(dot, red);
+  ss = block_sum_1024(ss, red);
+  const double alpha = dot / ss;
+  double num = 0.0, den = 0.0;
+  for (int i = threadIdx.x; i < Lb; i += blockDim.x) {
+    const double a = alpha * (double)sp[i], d = a - (double)hp[i];
+    num = fma(a, a, num);
+    den = fma(d, d, den);
+  }
+  num = block_sum_1024(num, red);
+  den = block_sum_1024(den, red);
+  if (threadIdx.x == 0) out[b] = (float)(10.0 * log10(eps + num / (eps + den)));
+}
+int launch_si_sdr(const float* s, const float* s_hat, int B, int L, const int* lens, double eps, float* out, cudaStream_t st) {
+  si_sdr_kernel<<<B, 1024, 0, st>>>(s, s_hat, L, lens, eps, out);
   STORM_LAUNCH_CHECK();
   return 0;
 }

@@ -190,20 +190,45 @@ class ScoreModel:
 
     def enhance_batch(self, ys: Union[torch.Tensor, Sequence[torch.Tensor]], predictor="reverse_diffusion", corrector="ald", N=50,
                       corrector_steps=1, snr=0.5, seed: Optional[int] = None, utt_ids: Optional[Sequence[int]] = None,
-                      return_nfe: bool = False):
-        """Batch of equal-length utterances [B, L] (or a list of [L]/[1, L]) -> [B, L] on the input's device.
-        Host tensors are staged through pinned memory; noise is keyed per utterance id, so results do not
-        depend on how a set of utterances is split into batches or across GPUs."""
-        if not torch.is_tensor(ys):
-            ys = torch.stack([y.reshape(-1) for y in ys])
-        src_dev = ys.device
+                      return_nfe: bool = False, max_batch: int = 8):
+        """Batched ``enhance`` (the reference has none: enhancement.py:66-72 loops over files).
+
+        * ``ys`` = tensor [B, L] (or a list of equal-length [L] / [1, L]) -> tensor [B, L] on the input's device;
+        * ``ys`` = list of utterances of DIFFERENT lengths -> list of [L_b] tensors: utterances are bucketed by padded
+          frame count (``parallel.bucket_utterances``), each bucket runs as ragged batches of at most ``max_batch``
+          through ``storm_enhance_ragged``; every utterance gets exactly the frames, padding and istft length the
+          reference gives it when enhanced alone.
+        Host tensors are staged through pinned memory; noise is keyed per utterance id, so results do not depend on
+        how a set of utterances is split into batches or across GPUs."""
+        sc = self._sampler_cfg(predictor, corrector, N, corrector_steps, snr)
+        sp = self.data_module.spec_config()
+        seed = self.next_seed() if seed is None else seed
         dev = self._device()
+        if not torch.is_tensor(ys):
+            ys = [y.reshape(-1) for y in ys]
+            lens = [int(y.numel()) for y in ys]
+            if len(set(lens)) > 1:
+                from .parallel import bucket_utterances
+                ids_all = list(range(len(ys))) if utt_ids is None else [int(u) for u in utt_ids]
+                outs: List[Optional[torch.Tensor]] = [None] * len(ys)
+                nfe = 0
+                for idx in bucket_utterances(lens, sp.hop_length, max_batch):
+                    Lmax = max(lens[i] for i in idx)
+                    host = torch.zeros(len(idx), Lmax, dtype=torch.float32)
+                    for r, i in enumerate(idx):
+                        host[r, :lens[i]] = ys[i].to("cpu", torch.float32)
+                    yd = host.pin_memory().to(dev, non_blocking=True)
+                    out, nfe = self.dnn.engine().enhance(yd, sc, sp, seed=seed, utt_ids=[ids_all[i] for i in idx],
+                                                         lengths=[lens[i] for i in idx])
+                    for r, i in enumerate(idx):
+                        outs[i] = out[r, :lens[i]].to(ys[i].device)
+                return (outs, nfe) if return_nfe else outs
+            ys = torch.stack(ys)
+        src_dev = ys.device
         yd = ys.to(torch.float32)
         if not yd.is_cuda:
             yd = yd.pin_memory().to(dev, non_blocking=True)
-        sc = self._sampler_cfg(predictor, corrector, N, corrector_steps, snr)
-        out, nfe = self.dnn.engine().enhance(yd, sc, self.data_module.spec_config(), seed=self.next_seed() if seed is None else seed,
-                                             utt_ids=utt_ids)
+        out, nfe = self.dnn.engine().enhance(yd, sc, sp, seed=seed, utt_ids=utt_ids)
         out = out.to(src_dev)
         return (out, nfe) if return_nfe else out
 

@@ -15,6 +15,31 @@ def shard_indices(n: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n, world))
 
 
+def padded_frame_count(L: int, hop_length: int = 128) -> int:
+    """Frames of a centred STFT, 1 + L // hop (data_module.py:217-219), padded to a multiple of 64 (util/other.py:102-109)."""
+    frames = 1 + L // hop_length
+    return (frames + 63) // 64 * 64
+
+
+def bucket_utterances(lengths: Sequence[int], hop_length: int = 128, max_batch: int = 8) -> List[List[int]]:
+    """Group utterance indices into batches that reproduce per-file results: a batch only holds utterances with the same
+    padded frame count (one [B, F, T_pad] tensor; every other per-utterance quantity - reflect padding, frame count,
+    istft length, normalisation - is handled per row by the ragged C-ABI entry points).  Buckets are ordered by frame
+    count, indices inside a bucket keep their input order, each batch has at most ``max_batch`` utterances."""
+    if max_batch < 1:
+        raise ValueError("max_batch must be >= 1")
+    by_T = {}
+    for i, L in enumerate(lengths):
+        if L < 1:
+            raise ValueError(f"utterance {i} is empty")
+        by_T.setdefault(padded_frame_count(int(L), hop_length), []).append(i)
+    batches: List[List[int]] = []
+    for T in sorted(by_T):
+        idx = by_T[T]
+        batches.extend(idx[k:k + max_batch] for k in range(0, len(idx), max_batch))
+    return batches
+
+
 def flat_params(module: torch.nn.Module) -> torch.Tensor:
     return torch.cat([p.detach().reshape(-1).to(torch.float32) for p in module.parameters()])
 

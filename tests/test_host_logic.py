@@ -137,3 +137,57 @@ def test_cli_flags_match_reference():
     a = p.parse_args(["--test_dir", "a", "--enhanced_dir", "b", "--ckpt", "c", "--mode", "score-only"])
     assert (a.corrector, a.corrector_steps, a.snr, a.N) == ("ald", 1, 0.5, 50)      # enhancement.py:33-36 defaults
     assert enhancement.shard(list(range(10)), 1, 4) == [1, 5, 9]
+
+
+def test_bucket_utterances_groups_by_padded_frames():
+    from storm_b200.parallel import bucket_utterances, padded_frame_count
+    # 32640 -> 256 frames -> 256; 32000 -> 251 -> 256; 33000 -> 258 -> 320; 8000 -> 63 -> 64; 8191 -> 64 -> 64; 8192 -> 65 -> 128
+    lens = [32640, 33000, 32000, 8000, 8192, 8191, 32100, 32200]
+    assert [padded_frame_count(L) for L in lens] == [256, 320, 256, 64, 128, 64, 256, 256]
+    b = bucket_utterances(lens, max_batch=3)
+    assert b == [[3, 5], [4], [0, 2, 6], [7], [1]]
+    assert sorted(i for g in b for i in g) == list(range(len(lens)))
+    with pytest.raises(ValueError):
+        bucket_utterances([100, 0])
+    with pytest.raises(ValueError):
+        bucket_utterances([100], max_batch=0)
+
+
+def test_bucket_matches_reference_pad_spec_rule():
+    """Frame count and padding of every length in a range equal torch.stft + pad_spec of the reference path (fixture shapes)."""
+    from conftest import load_golden
+    from storm_b200.parallel import padded_frame_count
+    g = load_golden("stft")
+    for tag in ("a", "b", "c"):
+        L = g[f"{tag}/sig"].shape[-1]
+        assert padded_frame_count(L) == int(g[f"{tag}/padded_T"])
+        assert 1 + L // 128 == g[f"{tag}/stft"].shape[-1]
+
+
+def test_wavio_roundtrip_and_pipeline(tmp_path):
+    from storm_b200.util import wavio
+    g = torch.Generator().manual_seed(0)
+    paths = []
+    for i, L in enumerate([1600, 2400, 800]):
+        x = (torch.rand(1, L, generator=g) - 0.5) * 0.8
+        p = str(tmp_path / f"u{i}.wav")
+        wavio.save_wav(p, x, 16000)
+        y, sr = wavio.load_wav(p)
+        assert sr == 16000 and y.shape == (1, L) and torch.allclose(x, y, atol=1e-6)
+        assert wavio.wav_length(p) == L
+        paths.append(p)
+    # 16-bit PCM through the header-only length probe and the scipy reader
+    from scipy.io import wavfile
+    pcm = (np.sin(np.arange(1000) * 0.05) * 20000).astype(np.int16)
+    p16 = str(tmp_path / "pcm16.wav")
+    wavfile.write(p16, 16000, pcm)
+    assert wavio.wav_length(p16) == 1000
+    y, sr = wavio._scipy_load(p16)
+    assert y.shape == (1, 1000) and abs(float(y[0, 10]) - pcm[10] / 32768.0) < 1e-7
+    # prefetcher keeps order, async writer flushes on close
+    got = list(wavio.Prefetcher(paths, lambda q: wavio.load_wav(q)[0].shape[1], depth=2, workers=2))
+    assert got == [1600, 2400, 800]
+    with wavio.AsyncWriter(workers=2) as w:
+        for i, q in enumerate(paths):
+            w.save(str(tmp_path / f"o{i}.wav"), wavio.load_wav(q)[0] * 0.5, 16000)
+    assert all((tmp_path / f"o{i}.wav").exists() for i in range(3))

@@ -157,3 +157,18 @@ def test_storm_enhance_end_to_end():
                                              O.NetCfg(nf=8, input_channels=6), T(g["y"]), N=int(g["N"]), noise=_queue(g["noise"]),
                                              return_stft=True)
     assert rel_l2(Y_den, g["Y_den"].squeeze()) < 5e-5 and rel_l2(sample, g["sample"].squeeze()) < 5e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_si_sdr(tag):
+    g = load_golden("metrics")
+    s, sh = g[f"{tag}/s"], g[f"{tag}/s_hat"]
+    assert abs(O.si_sdr(s, sh) - float(g[f"{tag}/si_sdr"])) < 1e-9
+    got = O.si_sdr_torch(torch.from_numpy(s), torch.from_numpy(sh))
+    assert abs(float(got) - float(g[f"{tag}/si_sdr_torch"])) < 1e-4
+
+
+def test_si_sdr_torch_truncates_to_common_length():
+    g = load_golden("metrics")
+    got = O.si_sdr_torch(torch.from_numpy(g["e/s"]), torch.from_numpy(g["e/s_hat"]))
+    assert abs(float(got) - float(g["e/si_sdr_torch"])) < 1e-4

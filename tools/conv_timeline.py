@@ -13,6 +13,7 @@ SHAPES = [  # name, H, W, C0, C1, Cout, prologue(ss+silu), skip C2, res
     ("b31.conv1 256->256 +skip256 @256", 256, 256, 256, 0, 256, True, 256, False),
     ("b32.conv0 384->128 @256", 256, 256, 256, 128, 128, True, 0, False),
     ("b32.conv1 128->128 +skip384 @256", 256, 256, 128, 0, 128, True, 384, False),
+    ("b4.conv0 128->128 @256", 256, 256, 128, 0, 128, True, 0, False),
     ("b4.conv1 128->128 +res @256", 256, 256, 128, 0, 128, True, 0, True),
     ("b27.conv0 512->256 @128", 128, 128, 256, 256, 256, True, 0, False),
     ("b22.conv0 512->256 @64", 64, 64, 256, 256, 256, True, 0, False),
