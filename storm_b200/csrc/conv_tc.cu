@@ -76,7 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 8000000000LL) __trap();
   }
 }
-// Long waits of many warps (producers waiting for a free stage, the 8 epilogue warps waiting for the whole main loop):
+// Long waits of many warps (producers waiting for a free stage, then all of them waiting for the whole main loop):
 // sleep in hardware instead of spinning - under the 1 kW power cap every wasted issue slot costs tensor clock.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -344,12 +344,12 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   }
 }
 
-// MAXU = halo pixels per producer thread (ceil(np / 256)); MINB = CTAs per SM.  <3,1>: one CTA per SM owning all
-// 512 TMEM columns; <2,2>: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
+// MAXU = halo pixels per producer thread (ceil(np / (32 NPW))); MINB = CTAs per SM.  MINB = 1: one CTA per SM owning
+// all 512 TMEM columns; MINB = 2: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
 // global stores) overlaps the other's MMA main loop on the shared tensor pipe.
 // FUSE: compile the fused 1x1-skip path (extra raw planes / loads) only into the instantiation that uses it, so the
 // others keep their register budget (the <2,2> variant is capped at 102 registers).
-// NPW: activation-producer warps (the first 8 of them also run the epilogue); warp NPW = weight producer,
+// NPW: activation-producer warps (all of them run the epilogue afterwards); warp NPW = weight producer,
 // warp NPW + 1 = TMEM allocator + MMA issuer.
 template <int MAXU, int MINB, bool FUSE, int NPW>
 __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
