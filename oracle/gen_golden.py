@@ -298,6 +298,34 @@ def gen_storm(ns):
          **sd_arrays(den.state_dict(), "den/"), **sd_arrays(score.state_dict(), "score/"))
 
 
+def gen_headline(ns):
+    """The headline benchmark configuration end to end through the UNMODIFIED reference modules (one utterance of
+    BASELINE configs[1]): 32 640 samples -> 256x256, full-width ncsnpp with seeded weights, N=30 reverse_diffusion +
+    ald x1 (60 network evaluations), noise from oracle.seeded_complex_noise.  Only the outputs are stored; weights,
+    waveform and noise are regenerated from their seeds at test time.  Takes a few minutes on CPU."""
+    from oracle import storm_oracle as O
+    cfg = ncsnpp_spec.NCSNppConfig()
+    sd = ncsnpp_spec.random_state_dict(cfg, seed=0, init_scale=1.0, bias_std=0.05)
+    m = ns.BackboneRegistry.get_by_name("ncsnpp")(input_channels=4, init_scale=1.0).eval()
+    m.load_state_dict(sd, strict=True)
+    dm = ns.SpecsDataModule(spec_factor=0.15, spec_abs_exponent=0.5)
+    yw = O.synth_utterance(0, 32640).reshape(1, -1)
+    T_orig = yw.size(1)
+    norm = yw.abs().max().item()
+    Y = ns.pad_spec(torch.unsqueeze(dm.spec_fwd(dm.stft(yw / norm)), 0))
+    assert tuple(Y.shape) == (1, 1, 256, 256)
+    N = 30
+    zs = O.seeded_complex_noise(2024, 1 + 2 * N, tuple(Y.shape))
+    sde = ns.OUVESDE(theta=1.5, sigma_min=0.05, sigma_max=0.5, N=N)
+    sampler = ns.sampling.get_pc_sampler("reverse_diffusion", "ald", sde=sde, score_fn=_score_fn(m), y=Y, eps=0.03,
+                                         snr=0.5, corrector_steps=1)
+    with patched_randn_like(NoiseQueue(zs)), torch.no_grad():
+        sample, nfe = sampler()
+    x_hat = dm.istft(dm.spec_back(sample.squeeze()), T_orig) * norm
+    save("headline_256x256_N30", sample=sample, x_hat=x_hat.squeeze(), nfe=nfe, N=N, noise_seed=2024, weight_seed=0,
+         init_scale=1.0, bias_std=0.05, L=T_orig)
+
+
 def gen_metrics(ns):
     """si_sdr / si_sdr_torch (util/other.py:82-94) on clean/estimate pairs at several SNRs and lengths."""
     g = torch.Generator().manual_seed(10)
@@ -314,7 +342,7 @@ def gen_metrics(ns):
     save("metrics", **arrs)
 
 
-GENS = dict(metrics=gen_metrics, storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
+GENS = dict(headline=gen_headline, metrics=gen_metrics, storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
             net_full=gen_net_full, sampler=gen_sampler, stft=gen_stft, enhance=gen_enhance)
 
 if __name__ == "__main__":

@@ -515,6 +515,13 @@ def si_sdr_torch(s: Tensor, s_hat: Tensor) -> Tensor:               # util/other
     return 10 * torch.log10(1e-10 + torch.norm(alpha * s) ** 2 / (1e-10 + torch.norm(alpha * s - s_hat) ** 2))
 
 
+def seeded_complex_noise(seed: int, count: int, shape) -> List[Tensor]:
+    """``count`` draws of torch.randn_like(complex x) (real and imaginary parts N(0, 1/2)) from a seeded CPU generator:
+    the deterministic noise source shared by the fixture generator (injected into the reference) and the tests."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.complex(torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)) * math.sqrt(0.5) for _ in range(count)]
+
+
 def synth_utterance(b: int, L: int) -> Tensor:
     """Synthetic noisy speech of SURVEY.md section 8(d): 5 harmonics of a random f0 with a 4 Hz on/off
     envelope plus white noise; generator seeded with 1234 + b.  Returns float32 [L]."""

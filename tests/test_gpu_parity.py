@@ -464,3 +464,31 @@ def test_cli_enhances_a_directory_of_ragged_files(tmp_path):
         x, _ = wavio.load_wav(str(src / f"f{i}.wav"))
         alone = model.enhance_batch(x, N=1, seed=11, utt_ids=[i])
         assert rel_l2(y, alone.cpu()) < 1e-4
+
+
+def test_headline_config_vs_reference():
+    """BASELINE configs[1] for one utterance against the UNMODIFIED reference (fixture headline_256x256_N30, generated by
+    oracle/gen_golden.py): 32 640 samples -> 256x256, full-width ncsnpp, N=30 reverse_diffusion + ald (60 network
+    evaluations) with the same injected noise; weights, waveform and noise are regenerated from their seeds."""
+    from storm_b200 import _native, ncsnpp_spec
+    g = load_golden("headline_256x256_N30")
+    m = _model("ncsnpp")
+    m.load_state_dict(ncsnpp_spec.random_state_dict(m.cfg, seed=int(g["weight_seed"]), init_scale=float(g["init_scale"]),
+                                                    bias_std=float(g["bias_std"])))
+    sp = _native.make_spec_config()
+    L, N = int(g["L"]), int(g["N"])
+    y = O.synth_utterance(0, L).reshape(1, -1).cuda()
+    norm = _native.wave_norm(y)
+    T_pad = _native.padded_frames(_native.num_frames(L, sp))
+    assert T_pad == 256                                                  # index work: exact
+    Y = _native.stft(y, norm, sp, T_pad).unsqueeze(1)
+    zs = torch.stack(O.seeded_complex_noise(int(g["noise_seed"]), 1 + 2 * N, (1, 1, 256, 256))).cuda()
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", N, 1, 0.5, 0.03)
+    X, nfe = m.engine().pc_sample(Y, sc, noise=zs)
+    assert nfe == int(g["nfe"]) == 60
+    err = rel_l2(X.cpu(), g["sample"])
+    x_hat = m.engine().istft(X.squeeze(1), norm, L, sp).squeeze().cpu()
+    err_w = rel_l2(x_hat, g["x_hat"])
+    print(f"headline config vs reference: enhanced spectrogram rel-L2 = {err:.3e}, waveform rel-L2 = {err_w:.3e}")
+    assert err < TOL and err_w < TOL
+    assert err < TIGHT                                                   # what the bf16x3 path is expected to reach
