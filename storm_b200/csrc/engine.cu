@@ -377,7 +377,9 @@ static int repack(StormHandle* h, cudaStream_t st) {
         float* wcat = nullptr;
         STORM_TRY(dev_alloc(h, (size_t)pm.out_ch * (pm.in_ch + PYR_CH), &wcat));
         LAUNCH(h, launch_concat_1x1(h->P(pp + ".Conv_2.weight"), pm.in_ch, s.w, m.in_ch, PYR_CH, 1.41421356237309505f, wcat, pm.out_ch, st));
-        STORM_TRY(tc_pack_weights(wcat, pm.out_ch, pm.in_ch + PYR_CH, 1, &r.tc2c, &h->packed, st));
+        STORM_TRY(tc_pack_weights(wcat, pm.out_ch, pm.in_ch + PYR_CH, 1, &r.tc2c, &h->packed, st, 0));
+        // the 16 pyramid channels keep this launch on 16-channel K chunks: Conv_1's image must be in the same mode
+        STORM_TRY(tc_pack_weights(h->P(pp + ".Conv_1.weight"), pm.out_ch, pm.out_ch, 9, &r.tc1, &h->packed, st, 0));
         STORM_TRY(dev_alloc(h, (size_t)pm.out_ch, &r.b12c));
         LAUNCH(h, launch_add_vec(r.b12, s.b, r.b12c, pm.out_ch, 1.41421356237309505f, st));
       }
@@ -1156,8 +1158,10 @@ int storm_debug_conv_fused(int32_t engine, const float* x0, const float* x1, int
   const int Cin = C0 + (x1 ? C1 : 0);
   if (engine == 0) {
     void *t0 = nullptr, *t1 = nullptr;
-    rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st);
-    if (rc == 0 && w2) rc = tc_pack_weights(w2, Cout, skip_out ? Cin : C2, 1, &t1, &owned, st);
+    // one operand split for the whole launch: the 32-channel mode only if every segment allows it (and never fused)
+    const int mp = (!skip_out && C0 % 32 == 0 && (!x1 || C1 % 32 == 0) && (!w2 || C2 % 32 == 0)) ? 1 : 0;
+    rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st, mp);
+    if (rc == 0 && w2) rc = tc_pack_weights(w2, Cout, skip_out ? Cin : C2, 1, &t1, &owned, st, mp);
     p.seg[0].wtc = t0; p.seg[1].wtc = t1;
     if (skip_out) {      // fused: skip over x2 (separate raw source, single tensor) or over the main sources when x2 == null
       p.skip_wtc = t1; p.skip_src0 = x2; p.skip_src1 = nullptr; p.skip_bias = nullptr; p.skip_out = skip_out;

@@ -68,7 +68,9 @@ def test_fused_conv(engine, case):
     err = _rel(out, ref)
     print(f"engine={engine} case={case} rel-L2={err:.3e}")
     assert torch.isfinite(out).all()
-    assert err < 2e-5
+    # SIMT fp32 and the bf16 x 3 tensor-core split reach ~5e-6; the "f16 + 2 x fp8" split (every segment a multiple of 32
+    # channels) ~2e-5 per layer
+    assert err < (2e-5 if engine == 1 else 8e-5)
 
 
 @pytest.mark.parametrize("engine", [1, 0])
