@@ -91,7 +91,15 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st);
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
 // fast variant for the tensor-core producers (ex2.approx + approximate division, ~1e-6 relative)
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x * sigmoid(x) with the two MUFU approximations issued directly: __expf() wraps ex2 in a denormal-range guard (a compare and
+// two predicated multiplies per element) that an activation never needs - ex2.approx.ftz returns 0 below 2^-126 and 1 + 0
+// is exact; error ~2 ulp like __fdividef(v, 1 + __expf(-v)).
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -1014,8 +1014,8 @@ int tc_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void** out
                     int max_prec) {
   return pack_common(w_oihw, Cout, Cin, taps, 0, max_prec, out, owned, st);
 }
-int tc_pack_weights_io(const float* w_io, int Cin, int Cout, void** out, std::vector<void*>* owned, cudaStream_t st) {
-  return pack_common(w_io, Cout, Cin, 1, 1, 1, out, owned, st);
+int tc_pack_weights_io(const float* w_io, int Cin, int Cout, void** out, std::vector<void*>* owned, cudaStream_t st, int max_prec) {
+  return pack_common(w_io, Cout, Cin, 1, 1, max_prec, out, owned, st);
 }
 
 }  // namespace storm

@@ -13,5 +13,6 @@ namespace storm {
 int tc_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void** out, std::vector<void*>* owned, cudaStream_t st,
                     int max_prec = 1);
 // [Cin][Cout] fp32 (NIN) -> same layout with taps = 1
-int tc_pack_weights_io(const float* w_io, int Cin, int Cout, void** out, std::vector<void*>* owned, cudaStream_t st);
+int tc_pack_weights_io(const float* w_io, int Cin, int Cout, void** out, std::vector<void*>* owned, cudaStream_t st,
+                       int max_prec = 1);
 }  // namespace storm
