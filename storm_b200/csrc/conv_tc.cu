@@ -921,8 +921,40 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   const bool big_first = g_tc_force_per_sm == 3 || p.nseg == 2;
   const Cand* cands = nblk == 1 ? (big_first ? cands1m : cands1b) : (big_first ? cands2m : cands2b);
   const int ncand = nblk == 1 ? 4 : 5;
+  // shared-memory plan of a candidate; false when it does not fit (then the next candidate is tried)
+  auto plan = [&](const Cand& k, TcpCfg& o) -> bool {
+    o.rows = k.rows; o.npt = k.npt; o.nmb = k.nmb;
+    o.per_sm = (g_tc_force_per_sm == 1) ? 1 : k.per_sm;
+    o.ncol = 8 * k.rows;
+    o.msplit = nblk / k.nmb;
+    o.hx = 8 * k.npt + 2; o.hy = k.rows + 2; o.np = o.hx * o.hy;
+    o.a_half = 2 * o.np * 16; o.a_plane = o.a_half; o.a_stage = 2 * o.a_half;
+    o.w_half = 4096 * k.nmb; o.w_stage = 2 * o.w_half;
+    o.w_plane = o.w_half;
+    int budget = o.per_sm == 2 ? 108 * 1024 : SMEM_BUDGET;
+    if (o.prec == 1) {   // a stage = one 32-channel chunk: four activation planes / four weight planes of the same sizes
+      o.a_stage = 4 * o.a_plane;
+      o.w_stage = 4 * o.w_plane;
+      budget = o.per_sm == 2 ? 112 * 1024 : 222 * 1024;
+    }
+    o.sa = (o.a_stage <= 24 * 1024) ? 3 : 2;
+    {
+      const char* e = getenv("STORM_B200_TC_SA");
+      if (e && atoi(e) >= 2) o.sa = atoi(e);
+    }
+    int sw = (budget - o.sa * o.a_stage - 256) / o.w_stage;
+    if (sw < 2 && o.sa == 3) {     // rather two activation stages than too few weight stages
+      o.sa = 2;
+      sw = (budget - o.sa * o.a_stage - 256) / o.w_stage;
+    }
+    o.sw = sw > 8 ? 8 : sw;
+    if (o.sw < 2) return false;
+    if (o.per_sm == 2 && o.np > 2 * 256) return false;      // MAXU = 2 halo pixels per producer thread
+    return true;
+  };
   int best = -1;
   long best_ctas = -1;
+  TcpCfg best_cfg = c;
   for (int i = 0; i < ncand; ++i) {
     const Cand& k = cands[i];
     const bool forced = g_tc_force_per_sm == 1 || g_tc_force_per_sm == 2;
@@ -930,40 +962,15 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     if (k.npt * k.nmb * 8 * k.rows > (k.per_sm == 2 ? 256 : 512)) continue;
     if (k.npt == 2 && p.W <= 8) continue;
     if (k.rows == 32 && p.H <= 16) continue;
+    TcpCfg t = c;
+    if (!plan(k, t)) continue;
     const long ctas = (long)ceil_div(p.H, k.rows) * ceil_div(p.W, 8 * k.npt) * (nblk / k.nmb) * p.B;
-    if (ctas >= (long)min_fill * k.per_sm) { best = i; break; }
-    if (ctas > best_ctas) { best_ctas = ctas; best = i; }
+    if (ctas >= (long)min_fill * k.per_sm) { best = i; best_cfg = t; break; }
+    if (ctas > best_ctas) { best_ctas = ctas; best = i; best_cfg = t; }
   }
   if (best < 0) return false;
   const Cand& k = cands[best];
-  c.rows = k.rows; c.npt = k.npt; c.nmb = k.nmb;
-  c.per_sm = (g_tc_force_per_sm == 1) ? 1 : k.per_sm;
-  c.ncol = 8 * k.rows;
-  c.msplit = nblk / k.nmb;
-  c.hx = 8 * k.npt + 2; c.hy = k.rows + 2; c.np = c.hx * c.hy;
-  c.a_half = 2 * c.np * 16; c.a_plane = c.a_half; c.a_stage = 2 * c.a_half;
-  c.w_half = 4096 * k.nmb; c.w_stage = 2 * c.w_half;
-  c.w_plane = c.w_half;
-  int budget = c.per_sm == 2 ? 108 * 1024 : SMEM_BUDGET;
-  if (c.prec == 1) {     // a stage = one 32-channel chunk: four activation planes / four weight planes of the same sizes
-    c.a_stage = 4 * c.a_plane;
-    c.w_stage = 4 * c.w_plane;
-    budget = c.per_sm == 2 ? 112 * 1024 : 222 * 1024;
-  }
-  c.sa = (c.a_stage <= 24 * 1024) ? 3 : 2;
-  {
-    const char* e = getenv("STORM_B200_TC_SA");
-    if (e && atoi(e) >= 2) c.sa = atoi(e);
-  }
-  int sw = (budget - c.sa * c.a_stage - 256) / c.w_stage;
-  c.sw = sw > 8 ? 8 : sw;
-  if (c.sw < 2 && c.prec == 1 && c.sa == 3) {     // rather two activation stages than too few weight stages
-    c.sa = 2;
-    sw = (budget - c.sa * c.a_stage - 256) / c.w_stage;
-    c.sw = sw > 8 ? 8 : sw;
-  }
-  if (c.sw < 2) return false;
-  if (c.per_sm == 2 && c.np > 2 * 256) return false;
+  c = best_cfg;
   c.tiles_x = ceil_div(p.W, 8 * k.npt);
   c.tiles_y = ceil_div(p.H, k.rows);
   return true;
