@@ -173,7 +173,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from storm_b200 import ScoreModel, _native, ncsnpp_spec, parallel
+    from storm_b200 import ScoreModel, ncsnpp_spec, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

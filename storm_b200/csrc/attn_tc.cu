@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __re
   const int b = blockIdx.y, q0 = blockIdx.x * TQ;
   const int NC = C >> 4, NT = N / TK;
   const int v_plane = C * 32;                 // bytes of one V plane (hi or lo): 2 k-cores x C rows x 16 B
-  const int v_stage = 2 * v_plane;
   const uint32_t qk_base = smem_u32(smem);
   const uint32_t v_base = qk_base + SQ * QK_STAGE;
   const uint32_t p_base = v_base + SV * V_STAGE_MAX;

@@ -307,7 +307,6 @@ int pack_common(const float* w, int Cout, int Cin, int taps, int io, int max_pre
 // channel of the tile).  CTA = NPT pixel tiles x NMB 128-channel blocks, NPT*NMB*N <= 512 TMEM columns.
 // Warps 0-7: activation producers then epilogue; warp 8: weight producer; warp 9: TMEM alloc + MMA issue.
 // =====================================================================================================
-constexpr int P_MAX_PRODUCERS = 384;
 
 struct TcpCfg {
   int rows;            // R: pixel-tile rows (32 or 16)

@@ -9,7 +9,6 @@ namespace storm {
 
 namespace {
 constexpr float PI_F = 3.14159274101257324f;   // float(np.pi), as torch's fp32 scalar multiply sees it
-constexpr double PI_D = 3.14159265358979323846;
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll

@@ -18,7 +18,6 @@ from . import _native, sampling
 from .backbones import BackboneRegistry
 from .data_module import SpecsDataModule
 from .sdes import SDERegistry
-from .util.other import pad_spec
 
 
 class ScoreModel:

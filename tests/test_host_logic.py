@@ -2,7 +2,6 @@
 import ctypes
 import os
 import re
-import subprocess
 import sys
 
 import numpy as np

@@ -3,7 +3,6 @@ gather, max-over-ranks timing reduction."""
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
