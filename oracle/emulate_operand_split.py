@@ -1,0 +1,82 @@
+"""Emulate tensor-core operand splits in the CPU oracle, BEFORE writing a kernel for them.
+
+TEST INFRASTRUCTURE ONLY (like everything under oracle/).  Every convolution / 1x1 / NIN product of the oracle network is
+replaced by the sum of narrow-operand products a tensor-core kernel would issue (operands rounded with torch's float16 /
+bfloat16 / float8 types, fp32 accumulation), the headline configuration (one utterance of BASELINE configs[1]: 256x256,
+N=30 reverse_diffusion + ald = 60 evaluations, noise from ``seeded_complex_noise``) is run end to end and the enhanced
+spectrogram is compared with the fixture produced by the UNMODIFIED reference (tests/golden/headline_256x256_N30.npz).
+
+    python oracle/emulate_operand_split.py MODE        # a few minutes per mode on 8 cores
+
+MODE                  tensor passes   what is multiplied                                               measured here
+exact                 -               fp32 x fp32 (the oracle itself)                                  5e-7 .. 7e-7 (thread count)
+f16_f8f8              2               wh16*h16 + e4m3(wl 2^12)*e5m2(x 2^-12) + e5m2(w 2^-6)*e4m3(l 2^6)   5.8e-5   <- conv_tc.cu mode 1
+f16_act               2               (wh16 + wl16) * h16: fp16 activations, exact weights             8.0e-4
+f16_main              1               wh16 * h16 only                                                  1.6e-3
+(bf16 x 3, conv_tc.cu mode 0, is measured on the GPU: 2.8e-5.)  The north-star tolerance is 1e-3.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import storm_oracle as O  # noqa: E402
+from storm_b200 import ncsnpp_spec  # noqa: E402
+
+E4, E5 = torch.float8_e4m3fn, torch.float8_e5m2
+
+
+def q8(x, dt, k):
+    """x * 2^k rounded to fp8 (saturating, round to nearest even), returned unscaled."""
+    s = 2.0 ** k
+    lim = 440.0 if dt is E4 else 57000.0
+    return (x * s).clamp(-lim, lim).to(dt).float() / s
+
+
+def make_lin(mode):
+    def lin(op, x, w):
+        if mode == "exact":
+            return op(x, w)
+        h = x.half().float()
+        wh = w.half().float()
+        if mode == "f16_act":
+            return op(h, w)
+        if mode == "f16_main":
+            return op(h, wh)
+        if mode == "f16_f8f8":
+            return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E4, 6), q8(w, E5, -6))
+        raise SystemExit(f"unknown mode {mode}")
+    return lin
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "f16_f8f8"
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    lin = make_lin(mode)
+    O._conv = lambda x, sd, key, pad: lin(lambda a, b: F.conv2d(a, b, None, padding=pad), x, sd[key + ".weight"]) \
+        + sd[key + ".bias"][None, :, None, None]
+    O._nin = lambda x, sd, key: lin(lambda a, b: torch.einsum("bchw,cd->bdhw", a, b), x, sd[key + ".W"]) \
+        + sd[key + ".b"][None, :, None, None]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "headline_256x256_N30.npz"))
+    sd = ncsnpp_spec.random_state_dict(ncsnpp_spec.NCSNppConfig(), seed=int(g["weight_seed"]), init_scale=float(g["init_scale"]),
+                                       bias_std=float(g["bias_std"]))
+    sc = O.SpecCfg()
+    yw = O.synth_utterance(0, int(g["L"])).reshape(1, -1)
+    Y = O.pad_spec(O.spec_fwd(O.stft(yw / yw.abs().max(), sc), sc).unsqueeze(0))
+    N = int(g["N"])
+    it = iter(O.seeded_complex_noise(int(g["noise_seed"]), 1 + 2 * N, tuple(Y.shape)))
+    t0 = time.time()
+    with torch.no_grad():
+        x, nfe = O.pc_sample(O.make_score_fn(sd, O.NetCfg()), Y, O.OUVE(), N, noise=lambda z: next(it))
+    ref = torch.from_numpy(g["sample"])
+    print(f"mode={mode}: {nfe} evaluations, enhanced spectrogram rel-L2 vs the reference = {(x - ref).norm() / ref.norm():.3e}"
+          f"  ({time.time() - t0:.0f} s)")
+
+
+if __name__ == "__main__":
+    main()
