@@ -361,12 +361,10 @@ class _DevView:
 
 
 # ---- handle-free entry points ------------------------------------------------------------------------------
-def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> Optional[torch.Tensor]:
-    """Validate per-utterance lengths of a ragged batch (host-side, the library cannot see device values): int32 CUDA
-    tensor [B], every L_b <= L, longer than the STFT reflect padding, and - when a SpecConfig is given - in the same
-    padded-frame bucket as L (otherwise the batch would not reproduce per-file results)."""
-    if lengths is None:
-        return None
+def check_lengths(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> List[int]:
+    """Host-side validation of the per-utterance lengths of a ragged batch (the library cannot see device values):
+    B entries, every L_b in (0, L], longer than the STFT reflect padding, and - when a SpecConfig is given - in the same
+    padded-frame bucket as the row stride L (otherwise the batch would not reproduce per-file results)."""
     lh = [int(v) for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
     if len(lh) != B:
         raise ValueError(f"lengths has {len(lh)} entries for a batch of {B}")
@@ -378,7 +376,14 @@ def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> Optional[
                 raise ValueError(f"utterance of {v} samples is shorter than the STFT reflect padding ({sp.n_fft // 2})")
             if padded_frames(num_frames(v, sp)) != padded_frames(num_frames(L, sp)):
                 raise ValueError(f"lengths {v} and {L} fall into different padded-frame buckets; batch them separately")
-    return torch.tensor(lh, dtype=torch.int32, device="cuda")
+    return lh
+
+
+def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> Optional[torch.Tensor]:
+    """Validated lengths as the int32 CUDA tensor the ragged entry points take (None = every row is L samples)."""
+    if lengths is None:
+        return None
+    return torch.tensor(check_lengths(lengths, B, L, sp), dtype=torch.int32, device="cuda")
 
 
 def wave_norm(wav: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:

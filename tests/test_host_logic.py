@@ -190,3 +190,19 @@ def test_wavio_roundtrip_and_pipeline(tmp_path):
         for i, q in enumerate(paths):
             w.save(str(tmp_path / f"o{i}.wav"), wavio.load_wav(q)[0] * 0.5, 16000)
     assert all((tmp_path / f"o{i}.wav").exists() for i in range(3))
+
+
+def test_ragged_length_validation_is_host_side():
+    """The checks in front of storm_*_ragged (the library cannot read device lengths) - no GPU needed."""
+    from storm_b200 import _native
+    sp = _native.make_spec_config()
+    assert _native.check_lengths([5000, 4000, 7000, 8100], 4, 8100, sp) == [5000, 4000, 7000, 8100]
+    assert _native.check_lengths(torch.tensor([32640, 32000]), 2, 32640, sp) == [32640, 32000]
+    for bad, B, L in [([5000, 4000], 3, 8000),            # wrong count
+                      ([5000, 9000], 2, 8100),            # longer than the row
+                      ([5000, 0], 2, 8100),               # empty
+                      ([5000, 200], 2, 8100),             # shorter than the reflect padding (255)
+                      ([5000, 9000], 2, 9000)]:           # 40 frames -> 64 vs 71 frames -> 128: different buckets
+        with pytest.raises(ValueError):
+            _native.check_lengths(bad, B, L, sp)
+    assert _native.check_lengths([5000, 200], 2, 8100) == [5000, 200]     # without a SpecConfig only the range is checked
