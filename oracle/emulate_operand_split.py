@@ -11,6 +11,7 @@ spectrogram is compared with the fixture produced by the UNMODIFIED reference (t
 MODE                  tensor passes   what is multiplied                                               measured here
 exact                 -               fp32 x fp32 (the oracle itself)                                  5e-7 .. 7e-7 (thread count)
 f16_f8f8              2               wh16*h16 + e4m3(wl 2^12)*e5m2(x 2^-12) + e5m2(w 2^-6)*e4m3(l 2^6)   5.8e-5   <- conv_tc.cu mode 1
+f16_f8f8_noscale_l    2               the same with e4m3(w) * e5m2(l): no scaling of the residual (one multiply less per element)   6.9e-5
 f16_act               2               (wh16 + wl16) * h16: fp16 activations, exact weights             8.0e-4
 f16_main              1               wh16 * h16 only                                                  1.6e-3
 (bf16 x 3, conv_tc.cu mode 0, is measured on the GPU: 2.8e-5.)  The north-star tolerance is 1e-3.
@@ -50,6 +51,8 @@ def make_lin(mode):
             return op(h, wh)
         if mode == "f16_f8f8":
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E4, 6), q8(w, E5, -6))
+        if mode == "f16_f8f8_noscale_l":      # residual unscaled in e5m2, weights unscaled in e4m3 (one multiply less per element)
+            return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E5, 0), q8(w, E4, 0))
         raise SystemExit(f"unknown mode {mode}")
     return lin
 
