@@ -99,14 +99,12 @@ class NCSNpp(nn.Module):
         return self.engine().net_forward(x, time_cond)
 
 
-@BackboneRegistry.register("ncsnpplarge")
+@BackboneRegistry.register("ncsnpplarge", "ncsnpp-large")     # README.md:43 of the reference spells it "ncsnpp-large"
 class NCSNppLarge(NCSNpp):
     """65.6 M parameters (ncsnpp.py:460-470)."""
     DEFAULTS = dict(nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,))
 
 
-# README.md:43 of the reference spells the large model "ncsnpp-large"; keep that name usable
-BackboneRegistry.register("ncsnpp-large")(NCSNppLarge)
 
 
 @BackboneRegistry.register("ncsnpp12M")
