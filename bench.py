@@ -265,8 +265,8 @@ def run_native(args):
     peak = pk["bf16_sustained"]
     # operand split of the tensor-core convolutions (storm_b200/csrc/conv_tc.cu): default = one fp16 pass + two fp8 correction
     # passes at twice the rate (2 passes); STORM_B200_TC_PREC=0 = bf16 hi/lo split (3 passes)
-    passes = 3 if os.environ.get("STORM_B200_TC_PREC", "1") == "0" or os.environ.get("STORM_B200_FUSE_SKIP", "0") not in ("", "0") else 2
-    split = "f16 x f16 + e4m3 x e5m2 + e5m2 x e4m3 corrections, fp32 accumulation" if passes == 2 else "bf16 hi/lo x 3, fp32 accumulation"
+    passes = 3 if os.environ.get("STORM_B200_TC_PREC", "1") == "0" else 2
+    split = "f16 x f16 + two e4m3 x e5m2 correction passes, fp32 accumulation" if passes == 2 else "bf16 hi/lo x 3, fp32 accumulation"
     roofline = dict(bound="tensor", kernel=f"implicit-GEMM conv3x3/1x1 ({dom})", achieved=achieved, peak=peak, unit="TFLOP/s",
                     frac=achieved / peak if peak else None, traffic=traffic, traffic_note=traffic_note,
                     peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",

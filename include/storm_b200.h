@@ -220,13 +220,14 @@ int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int
                            const float* bias, const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W,
                            long long* dbg_dev, float* ms_out, void* stream);
 
-/* Same with the fused 1x1 skip of the tcgen05 kernel: when skip_out != NULL the launch also writes
- * skip_out = conv1x1(raw source; w2) where the raw source is x2 ([B][H][W][C0+C1], single tensor) or, if x2 == NULL,
- * the un-normalised main input cat[x0, x1]; `out` then holds the main convolution only. */
-int storm_debug_conv_fused(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
-                           int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout,
-                           const float* bias, const float* res, float out_scale, float* out, float* skip_out, int32_t B,
-                           int32_t H, int32_t W, long long* dbg_dev, float* ms_out, void* stream);
+/* General form.  res_up: residual given at HALF resolution ([B][H/2][W/2][Cout], tcgen05 engine only); the epilogue adds
+ * its x2 FIR upsampling (taps [1,3,3,1], up_or_down_sampling.py:195-217) - how the engine runs the 1x1 skip of up blocks.
+ * max_prec: 1 = let the tcgen05 path use the two-pass "f16 + 2 x fp8" operand split when every segment is a multiple of
+ * 32 channels, 0 = force the bf16 x 3 split.  ms_out / dbg_dev as in storm_debug_conv_timed (NULL = single launch). */
+int storm_debug_conv_ex(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                        int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout,
+                        const float* bias, const float* res, const float* res_up, float out_scale, float* out, int32_t B,
+                        int32_t H, int32_t W, int32_t max_prec, long long* dbg_dev, float* ms_out, void* stream);
 
 /* Test hook: single-head attention o = softmax(q k^T / sqrt(C)) v on [B][N][C] fp32 device tensors
  * (AttnBlockpp core, layerspp.py:82-86).  engine 0 = tcgen05 kernel (v must be given channel-major [B][C][N]),

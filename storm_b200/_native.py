@@ -88,10 +88,10 @@ _PROTOS = {
     "storm_debug_conv_timed": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                          C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
-    "storm_debug_conv_fused": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
-                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float),
-                                         C.c_void_p]),
+    "storm_debug_conv_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.POINTER(C.c_float), C.c_void_p]),
     "storm_debug_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]),
     "storm_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -425,44 +425,28 @@ def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad:
     return spec
 
 
-def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=None, bias=None, res=None, out_scale=1.0, timed=False):
-    """Test hook around storm_debug_conv: NHWC fp32 CUDA tensors, w OIHW [Cout, Cin, k, k].
-    timed=True -> (out, ms, counters) from storm_debug_conv_timed."""
+def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=None, bias=None, res=None, res_up=None, out_scale=1.0,
+               timed=False, max_prec=1):
+    """Test hook around storm_debug_conv_ex: NHWC fp32 CUDA tensors, w OIHW [Cout, Cin, k, k]; res_up = residual at half
+    resolution (added FIR-upsampled); max_prec=0 forces the bf16 x 3 operand split.
+    timed=True -> (out, ms, counters)."""
     x0 = _cf(x0, "x0")
     B, H, W, C0 = x0.shape
     Cout = w.shape[0]
     taps = w.shape[2] * w.shape[3]
     out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x0.device)
     cont = lambda t: None if t is None else _cf(t, "arg")   # noqa: E731
-    x1, ss, x2, w2, bias, res, w = cont(x1), cont(ss), cont(x2), cont(w2), cont(bias), cont(res), cont(w)
-    if timed:
-        dbg = torch.zeros(8, dtype=torch.int64, device=x0.device)
-        ms = C.c_float()
-        _check(lib().storm_debug_conv_timed(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu),
-                                            taps, w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias),
-                                            _ptr(res), float(out_scale), out.data_ptr(), B, H, W, dbg.data_ptr(), C.byref(ms), _stream()))
-        return out, float(ms.value), dbg.cpu().tolist()
-    _check(lib().storm_debug_conv(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu), taps,
-                                  w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias), _ptr(res),
-                                  float(out_scale), out.data_ptr(), B, H, W, _stream()))
-    return out
-
-
-def debug_conv_fused(x0, w, w2, x1=None, ss=None, silu=False, x2=None, bias=None, out_scale=1.0):
-    """tcgen05 conv with the fused 1x1 skip: returns (main conv output, skip output), NHWC."""
-    x0 = _cf(x0, "x0")
-    B, H, W, C0 = x0.shape
-    Cout = w.shape[0]
-    out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x0.device)
-    skip = torch.empty_like(out)
-    cont = lambda t: None if t is None else _cf(t, "arg")   # noqa: E731
-    x1, ss, x2, w2, bias, w = cont(x1), cont(ss), cont(x2), cont(w2), cont(bias), cont(w)
+    x1, ss, x2, w2, bias, res, res_up, w = cont(x1), cont(ss), cont(x2), cont(w2), cont(bias), cont(res), cont(res_up), cont(w)
+    dbg = torch.zeros(8, dtype=torch.int64, device=x0.device) if timed else None
     ms = C.c_float()
-    _check(lib().storm_debug_conv_fused(0, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu),
-                                        w.shape[2] * w.shape[3], w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1],
-                                        w2.data_ptr(), Cout, _ptr(bias), None, float(out_scale), out.data_ptr(), skip.data_ptr(),
-                                        B, H, W, None, None, _stream()))
-    return out, skip
+    with torch.cuda.device(x0.device):
+        _check(lib().storm_debug_conv_ex(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu),
+                                         taps, w.data_ptr(), _ptr(x2), 0 if x2 is None else x2.shape[-1], _ptr(w2), Cout, _ptr(bias),
+                                         _ptr(res), _ptr(res_up), float(out_scale), out.data_ptr(), B, H, W, int(max_prec), _ptr(dbg),
+                                         C.byref(ms) if timed else None, _stream()))
+    if timed:
+        return out, float(ms.value), dbg.cpu().tolist()
+    return out
 
 
 def debug_attention(engine: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:

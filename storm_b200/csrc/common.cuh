@@ -56,7 +56,9 @@ struct ConvSeg {
   int silu;
   int taps;
   const float* w;     // SIMT path: [taps][C0+C1][Cout]
-  const void* wtc;    // tcgen05 path: bf16 hi/lo smem images (see conv_tc.cu)
+  const void* wtc;    // tcgen05 path: packed shared-memory operand images (TcWeights::img, see conv_tc.cuh)
+  int wprec;          // operand split the image was packed in (TcWeights::prec)
+  float wscale;       // power-of-two factor the packed weights carry (TcWeights::scale; 1 for the bf16 x 3 split)
 };
 
 struct ConvParams {
@@ -67,20 +69,16 @@ struct ConvParams {
   const float* temb;       // [B][temb_stride] per-sample bias or null
   int temb_stride;
   const float* res;        // residual NHWC [B][H][W][Cout] or null
+  // residual given at HALF resolution, NHWC [B][H/2][W/2][Cout]: the epilogue adds its x2 FIR upsampling (taps [1,3,3,1],
+  // up_or_down_sampling.py:195-217: o[2i] = x[i-1]/4 + 3x[i]/4, o[2i+1] = 3x[i]/4 + x[i+1]/4 per axis, zero outside).  Used for
+  // the 1x1 skip of up blocks, which commutes with the (linear, per-channel) resampling: Conv_2(FIR_up(x)) = FIR_up(Conv_2(x)).
+  const float* res_up;
   float out_scale;
   float* out;              // NHWC [B][H][W][Cout]
   double* stats_out;       // optional GroupNorm partial sums of `out`: [B][stats_chunks][Cout][2] (tcgen05 mode P only)
   int stats_chunks;
   long long* dbg;          // optional [8] cycle counters written by CTA 0 (tools/conv_timeline.py)
   int out_cm;              // 1: write `out` channel-major [B][Cout][H*W] (tcgen05 kernel only; attention V operand)
-  // Fused 1x1 skip (tcgen05 kernel only, nseg == 1): the launch ALSO computes skip_out = conv1x1(raw skip source) +
-  // skip_bias into a second TMEM accumulator, from the raw (un-normalised) values the producers already hold
-  // (skip_src0 == null: same tensors as seg[0]) - ResnetBlockBigGANpp's Conv_2 (layerspp.py:268-269) for free.
-  const void* skip_wtc;
-  const float* skip_src0;
-  const float* skip_src1;
-  const float* skip_bias;
-  float* skip_out;
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);

@@ -25,8 +25,10 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
+#include <cmath>
 #include <cstdlib>
-#include <unordered_map>
+#include <cstring>
+#include <mutex>
 
 #include "conv_tc.cuh"
 
@@ -161,29 +163,35 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
 }
 
 // ---- operand split of precision mode 1 ("f16 + 2 x fp8", 2 tensor passes instead of 3) -------------------------------
-//   x = h + l with h = fp16(x);   w = wh + wl with wh = fp16(w)
-//   w x = wh h  +  wl h  +  w l  (+ wl l ~ 2^-24)
-//       ~ wh16 * h16  +  e4m3(wl 2^12) * e5m2(h 2^-12)  +  e5m2(w 2^-6) * e4m3(l 2^6)
+//   W = beta w (beta = power of two chosen per launch from max|w| at pack time so that max|W| is in (2^13, 2^14]);
+//   x = h + l with h = fp16(x) (saturating);   W = Wh + Wl with Wh = fp16(W)
+//   W x = Wh h  +  Wl h  +  W l  (+ Wl l ~ 2^-24)
+//       ~ Wh16 * h16  +  e4m3(Wl) * e5m2(h)  +  e4m3(W 2^-10) * e5m2(l 2^10)          (the epilogue multiplies by 1 / beta)
 // The first product is exact in the fp32 accumulator; the two corrections are ~2^-12 of it, so 3..4 significant bits
 // (fp8) keep the total error near 2^-15 - the bf16 x 3 split gives 2^-16 - while an fp8 MMA covers K = 32 channels in
-// the time a 16-bit MMA covers 16: 1 + 1/2 + 1/2 = 2 passes.  Emulated in the oracle on the headline configuration
-// (60 evaluations): 5.8e-5 against the reference (bf16 x 3: 2.8e-5, fp16 activations without corrections: 8.0e-4).
-constexpr float PREC1_A8_SCALE = 1.0f / 4096.0f, PREC1_WL_SCALE = 4096.0f;    // e5m2(h 2^-12) x e4m3(wl 2^12)
-constexpr float PREC1_AL_SCALE = 64.0f, PREC1_W8_SCALE = 1.0f / 64.0f;       // e4m3(l 2^6)   x e5m2(w 2^-6)
+// the time a 16-bit MMA covers 16: 1 + 1/2 + 1/2 = 2 passes.
+// Range: e5m2 has fp16's exponent range, so e5m2(h) needs no scaling and covers every finite h; l <= 2^-11 |x| scaled by
+// 2^10 stays inside e5m2 for every fp16-normal x (2^-14 .. 65504); with max|W| pinned near 2^14 the weight planes sit in
+// the middle of e4m3 (|Wl| <= 8, |W 2^-10| <= 16, 13+ binades of headroom below).  The scheme is therefore invariant to
+// the scale of the weights (beta) and of the activations (tests/test_gpu_conv.py::test_dynamic_range_sweep: 1.6e-5 for
+// activations x 1e-3 .. 1e4 and weights x 1e-3 .. 30; round 1's fixed 2^+-12 / 2^+-6 scalings lost the corrections below
+// |x| ~ 0.06 or |w| ~ 1e-3).  Emulated in the oracle before the kernel was written (oracle/emulate_operand_split.py).
+constexpr float PREC1_AL_SCALE = 1024.0f, PREC1_W8_SCALE = 1.0f / 1024.0f;       // e5m2(l 2^10) x e4m3(W 2^-10)
+constexpr int PREC1_W_LOG2_MAX = 14;                                                // max|beta w| in (2^13, 2^14]
 
-// 8 fp32 -> 8 fp16 (16 B), 8 e5m2 of the fp16 values * 2^-12 (8 B), 8 e4m3 of the residuals * 2^6 (8 B)
+// 8 fp32 -> 8 fp16 (16 B, saturating), 8 e5m2 of the fp16 values (8 B), 8 e5m2 of the residuals * 2^10 (8 B)
 __device__ __forceinline__ void split_f16f8(const float (&v)[8], uint4& h16, uint2& a8, uint2& l8) {
   uint32_t hh[4], aa[4], ll[4];
-  const __half2 sc = __float2half2_rn(PREC1_A8_SCALE);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);              // .x (low half) = v[2j]
-    hh[j] = *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t hu;                                                                  // low half = v[2j]
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hu) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    hh[j] = hu;
+    const __half2 h = *reinterpret_cast<const __half2*>(&hu);
     const float2 f = __half22float2(h);
-    const __half2 hs = __hmul2(h, sc);
-    aa[j] = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);   // low byte = .x
+    aa[j] = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&h), __NV_SATFINITE, __NV_E5M2);   // low byte = .x
     ll[j] = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * j] - f.x) * PREC1_AL_SCALE, (v[2 * j + 1] - f.y) * PREC1_AL_SCALE),
-                                     __NV_SATFINITE, __NV_E4M3);
+                                     __NV_SATFINITE, __NV_E5M2);
   }
   h16 = make_uint4(hh[0], hh[1], hh[2], hh[3]);
   a8 = make_uint2(aa[0] | (aa[1] << 16), aa[2] | (aa[3] << 16));
@@ -227,10 +235,11 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict
   }
 }
 
-// Precision mode 1 image, per q = chunk32 * taps + tap: four planes of Mpad rows x 32 bytes:
-//   [wh fp16, channels 0-15][wh fp16, channels 16-31][e4m3(wl 2^12), 32 channels][e5m2(w 2^-6), 32 channels]
+// Precision mode 1 image, per q = chunk32 * taps + tap: four planes of Mpad rows x 32 bytes (W = beta w):
+//   [Wh fp16, channels 0-15][Wh fp16, channels 16-31][e4m3(Wl), 32 channels][e4m3(W 2^-10), 32 channels]
 // byte offset of (row n, byte kb) inside a plane: (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16  (same core-matrix layout)
-__global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout) {
+__global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout,
+                                  float beta) {
   const int Mpad = tc_mpad(Cout);
   const size_t total = (size_t)(Cin / 32) * taps * Cout * 32;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -240,7 +249,7 @@ __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restri
     const int tap = q % taps;
     const int chunk = q / taps;
     const int ci = chunk * 32 + k;
-    const float v = io_layout ? w[(size_t)ci * Cout + n] : w[((size_t)n * Cin + ci) * taps + tap];
+    const float v = beta * (io_layout ? w[(size_t)ci * Cout + n] : w[((size_t)n * Cin + ci) * taps + tap]);
     const __half wh = __float2half_rn(v);
     const float wl = v - __half2float(wh);
     const size_t plane = (size_t)32 * Mpad;
@@ -249,38 +258,51 @@ __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restri
     const int k16 = k % 16;
     *reinterpret_cast<uint16_t*>(base + (k / 16) * plane + row + (k16 / 8) * 128 + (k16 % 8) * 2) = __half_as_ushort(wh);
     const size_t o8 = row + (k / 16) * 128 + k16;
-    base[2 * plane + o8] = (uint8_t)__nv_cvt_float_to_fp8(wl * PREC1_WL_SCALE, __NV_SATFINITE, __NV_E4M3);
-    base[3 * plane + o8] = (uint8_t)__nv_cvt_float_to_fp8(v * PREC1_W8_SCALE, __NV_SATFINITE, __NV_E5M2);
+    base[2 * plane + o8] = (uint8_t)__nv_cvt_float_to_fp8(wl, __NV_SATFINITE, __NV_E4M3);
+    base[3 * plane + o8] = (uint8_t)__nv_cvt_float_to_fp8(v * PREC1_W8_SCALE, __NV_SATFINITE, __NV_E4M3);
   }
+}
+
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(w[i]);
+    if (a == a && a <= 3.0e38f) m = fmaxf(m, a);          // ignore NaN / inf
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));     // non-negative floats order like their bit patterns
 }
 
 bool shape_ok(int Cout, int Cin) { return Cout >= 1 && Cout <= 256 && Cin % 16 == 0 && Cin >= 16; }
 
 // STORM_B200_TC_PREC: 1 (default) = "f16 + 2 x fp8" operand split wherever every K segment is a multiple of 32 channels,
-// 0 = bf16 x 3 everywhere.  The fused-skip variant only exists for bf16 x 3.
+// 0 = bf16 x 3 everywhere.
 int prec_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("STORM_B200_TC_PREC");
-    v = e ? atoi(e) : 1;
-    const char* f = getenv("STORM_B200_FUSE_SKIP");
-    if (f && atoi(f)) v = 0;
-  }
+  static const int v = [] { const char* e = getenv("STORM_B200_TC_PREC"); return e ? atoi(e) : 1; }();
   return v;
 }
-std::unordered_map<const void*, int>& pack_prec() {      // packed image -> precision mode it was written in
-  static std::unordered_map<const void*, int> m;
-  return m;
-}
-int seg_prec(const ConvSeg& s) {
-  auto it = pack_prec().find(s.wtc);
-  return it == pack_prec().end() ? 0 : it->second;
+
+// beta = 2^(14 - ceil(log2 max|w|)): max|beta w| in (2^13, 2^14]
+float scale_for_absmax(float a) {
+  if (!(a > 0.f) || !(a < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(a, &e);                            // a = m 2^e, m in [0.5, 1)  ->  a <= 2^e
+  int k = PREC1_W_LOG2_MAX - e;
+  if (k > 100) k = 100;
+  if (k < -100) k = -100;
+  return ldexpf(1.0f, k);
 }
 
-int pack_common(const float* w, int Cout, int Cin, int taps, int io, int max_prec, void** out, std::vector<void*>* owned, cudaStream_t st) {
-  *out = nullptr;
+int pack_common(const float* w, int Cout, int Cin, int taps, int io, int max_prec, float absmax, TcWeights* out,
+                std::vector<void*>* owned, cudaStream_t st) {
+  *out = TcWeights();
   if (!shape_ok(Cout, Cin)) return 0;
   const int prec = (max_prec >= 1 && prec_enabled() && Cin % 32 == 0) ? 1 : 0;
+  float beta = 1.0f;
+  if (prec == 1) {
+    if (!(absmax > 0.f)) STORM_TRY(tc_weight_absmax(w, (size_t)Cout * Cin * taps, &absmax, st));
+    beta = scale_for_absmax(absmax);
+  }
   const size_t bytes = (size_t)(Cin / 16) * taps * 64 * tc_mpad(Cout);      // same size in both modes
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
@@ -289,11 +311,12 @@ int pack_common(const float* w, int Cout, int Cin, int taps, int io, int max_pre
   STORM_CUDA_TRY(cudaMemsetAsync(p, 0, bytes, st));
   const size_t total = (size_t)(Cin / 16) * taps * Cout * 16;
   const unsigned blocks = (unsigned)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
-  if (prec) tc_pack_kernel_p1<<<blocks, 256, 0, st>>>(w, (uint8_t*)p, Cout, Cin, taps, io);
+  if (prec) tc_pack_kernel_p1<<<blocks, 256, 0, st>>>(w, (uint8_t*)p, Cout, Cin, taps, io, beta);
   else tc_pack_kernel<<<blocks, 256, 0, st>>>(w, (uint16_t*)p, Cout, Cin, taps, io);
   STORM_LAUNCH_CHECK();
-  pack_prec()[p] = prec;
-  *out = p;
+  out->img = p;
+  out->prec = prec;
+  out->scale = beta;
   return 0;
 }
 
@@ -318,11 +341,12 @@ struct TcpCfg {
   int a_half, a_stage, w_half, w_stage;
   int tiles_x, tiles_y;
   int per_sm;          // CTAs per SM this config is built for (1 or 2)
-  int fuse;            // 1: fused 1x1 skip (4 activation planes per stage, second accumulator set)
   int a_plane;         // bytes of one activation plane (hi or lo) = a_half
   int prec;            // 0: bf16 x 3, 16-channel K chunks (planes hi, lo); 1: f16 + 2 x fp8, 32-channel K chunks
-                       //    (activation planes f16[0-15], f16[16-31], e5m2, e4m3; weight planes alike), see split_f16f8
+                       //    (activation planes f16[0-15], f16[16-31], e5m2(h), e5m2(l); weight planes f16, f16, e4m3, e4m3), see split_f16f8
   int w_plane;         // bytes of one weight plane of a stage (prec 1)
+  int pf_depth;        // how many K chunks ahead of the one being staged the producers prefetch into L2
+  float acc_scale;     // 1 / (scale carried by the packed weights): multiplies the accumulators in the epilogue
 };
 
 // K-chunk schedule shared by the three roles.  With a 1x1 skip segment (seg 1) its chunks are interleaved with the
@@ -355,7 +379,7 @@ template <int NPT, int NMB, int PREC>
 __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
                                            uint32_t tmem_base) {
   const uint32_t idesc = PREC ? make_idesc_fmt(c.ncol, 0, 0) : make_idesc(c.ncol);          // f16 x f16 | bf16 x bf16
-  const uint32_t idesc8a = make_idesc_fmt(c.ncol, 0, 1), idesc8b = make_idesc_fmt(c.ncol, 1, 0);   // e4m3 x e5m2 | e5m2 x e4m3
+  const uint32_t idesc8 = make_idesc_fmt(c.ncol, 0, 1);                                      // e4m3 (weights) x e5m2 (activations)
   const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = (uint32_t)c.w_plane >> 4;
   const uint64_t pd_const = make_desc(0, (uint32_t)c.np * 16u, (uint32_t)c.hx * 16u);   // pixel operand (B)
   const uint64_t wd_const = make_desc(0, 128, 256);                                      // weight operand (A)
@@ -368,7 +392,7 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   const int sa_n = c.sa, sw_n = c.sw;
   int sa = 0, sw = 0;
   uint32_t pa = 0, pw = 0;
-  uint32_t acc = 0, acc_skip = 0;
+  uint32_t acc = 0;
   const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long t_wa = 0, t_ww = 0, t_start = dbg ? clock64() : 0;
   ChunkIter it(p, PREC);
@@ -401,8 +425,8 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
             if constexpr (PREC == 1) {
               umma_bf16(d, w_hi, p_hi, idesc, acc);                                          // wh x h, channels 0-15
               umma_bf16(d, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);                         // wh x h, channels 16-31
-              umma_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8a, 1u);               // e4m3(wl) x e5m2(h), 32 channels
-              umma_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8b, 1u);               // e5m2(w) x e4m3(l), 32 channels
+              umma_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);                // e4m3(Wl) x e5m2(h), 32 channels
+              umma_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);                // e4m3(W 2^-10) x e5m2(l 2^10), 32 channels
             } else {
               const uint64_t w_lo = w_hi + w_half16;
               umma_bf16(d, w_hi, p_hi, idesc, acc);
@@ -415,30 +439,6 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
         umma_commit(bar_base + 8u * (2 * sa_n + sw_n + sw));               // w_empty: frees the weight stage
         if (++sw == sw_n) { sw = 0; pw ^= 1; }
         if (++dx == 3) { dx = 0; toff += (uint32_t)c.hx - 2u; } else { toff += 1u; }
-      }
-      if (c.fuse) {
-        // fused 1x1 skip: weight stage #10 of this chunk against the RAW planes (centre tap) -> second accumulator set
-        mbar_wait(bar_base + 8u * (2 * sa_n + sw), pw);
-        tc_fence_after();
-        const uint32_t w16 = w_base16 + sw * w_stage16;
-        const uint32_t raw16 = a16 + 2u * a_half16 + (uint32_t)(c.hx + 1);
-#pragma unroll
-        for (int pt = 0; pt < NPT; ++pt) {
-          const uint64_t p_hi = pd_const + (uint64_t)(raw16 + 8u * pt);
-          const uint64_t p_lo = p_hi + a_half16;
-#pragma unroll
-          for (int mb = 0; mb < NMB; ++mb) {
-            const uint64_t w_hi = wd_const + (uint64_t)(w16 + 256u * mb);
-            const uint64_t w_lo = w_hi + w_half16;
-            const uint32_t d = tmem_base + (uint32_t)(NPT * NMB + pt * NMB + mb) * ncol;
-            umma_bf16(d, w_hi, p_hi, idesc, acc_skip);
-            umma_bf16(d, w_hi, p_lo, idesc, 1u);
-            umma_bf16(d, w_lo, p_hi, idesc, 1u);
-          }
-        }
-        acc_skip = 1u;
-        umma_commit(bar_base + 8u * (2 * sa_n + sw_n + sw));
-        if (++sw == sw_n) { sw = 0; pw ^= 1; }
       }
       umma_commit(bar_base + 8u * (sa_n + sa));                            // a_empty: frees the activation stage
       if (++sa == sa_n) { sa = 0; pa ^= 1; }
@@ -457,14 +457,11 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
 // MAXU = halo pixels per producer thread (ceil(np / (32 NPW))); MINB = CTAs per SM.  MINB = 1: one CTA per SM owning
 // all 512 TMEM columns; MINB = 2: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
 // global stores) overlaps the other's MMA main loop on the shared tensor pipe.
-// FUSE: compile the fused 1x1-skip path (extra raw planes / loads) only into the instantiation that uses it, so the
-// others keep their register budget (the <2,2> variant is capped at 102 registers).
 // NPW: activation-producer warps (all of them run the epilogue afterwards); warp NPW = weight producer,
 // warp NPW + 1 = TMEM allocator + MMA issuer.
 // PREC: operand split (TcpCfg::prec), compiled in so that each instantiation only carries its own conversion code.
-template <int MAXU, int MINB, bool FUSE, int NPW, int PREC>
+template <int MAXU, int MINB, int NPW, int PREC>
 __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
-  static_assert(!(FUSE && PREC), "the fused-skip variant exists for the bf16 x 3 split only");
   constexpr int P_PRODUCERS = NPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -522,7 +519,6 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
         upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
       }
     }
-    const bool fuse = FUSE && c.fuse != 0, skip_sep = fuse && p.skip_src0 != nullptr;
     auto split_store = [&](const float (&v)[8], bool valid, uint32_t off) {   // 8 channels of one pixel -> hi plane, lo plane
       uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
       if (valid) {
@@ -542,9 +538,27 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     };
     // prec 1: the 8 channels of one pixel -> fp16 k-core of the half's plane; the fp8 bytes of both 8-channel groups of a
     // unit are stored together (16 bytes per pixel and fp8 plane k-core)
-    ChunkIter it(p, PREC);
-    int si, chk;
     constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
+    auto prefetch_chunk = [&](int nsi, int nch) {
+      const ConvSeg& ns = p.seg[nsi];
+      const int n0c = nch * (16 * NH);
+      const float* nsrc;
+      int nCs, ncl;
+      if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+      const bool nfull = ns.taps == 9;
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i)
+        if (upix[i] >= 0 && (nfull || uinterior[i]))
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
+    };
+    ChunkIter it(p, PREC), pf_it(p, PREC);
+    int si, chk;
+    {   // chunk 0 is loaded directly; chunks 1 .. pf_depth - 1 are prefetched now, chunk i + pf_depth while chunk i is staged
+      int nsi, nch;
+      pf_it.next(nsi, nch);
+      for (int d = 1; d < c.pf_depth; ++d)
+        if (pf_it.next(nsi, nch)) prefetch_chunk(nsi, nch);
+    }
     while (it.next(si, chk)) {
       const ConvSeg& s = p.seg[si];
       const int C = s.C0 + s.C1;
@@ -565,36 +579,12 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
           }
         }
-        float4 sraw[FUSE ? MAXU : 1][4];   // separate raw source of the fused skip (up/down blocks): interior pixels only
-        if constexpr (FUSE) if (skip_sep) {
-          const float* ssrc;
-          int sCs, scl;
-          if (c0 < s.C0) { ssrc = p.skip_src0; sCs = s.C0; scl = c0; } else { ssrc = p.skip_src1; sCs = s.C1; scl = c0 - s.C0; }
-#pragma unroll
-          for (int i = 0; i < MAXU; ++i) {
-            if (upix[i] >= 0 && uinterior[i]) {
-              const float4* gp = reinterpret_cast<const float4*>(ssrc + (size_t)upix[i] * sCs + scl);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) sraw[i][j] = __ldg(gp + j);
-            }
-          }
-        }
-        // ---- L2 prefetch of the next chunk in schedule order (once per stage; a 32-channel chunk is one 128-byte line)
+        // ---- L2 prefetch, pf_depth chunks ahead in schedule order (once per stage; a 32-channel chunk is one 128-byte
+        // line per pixel).  The 1x1 skip chunks need a whole tile of fresh HBM lines per ~1k cycles of tensor work, several
+        // times what HBM delivers; looking further ahead than one chunk lets the long 3x3 chunks pay for them.
         if (hsel == 0) {
-          ChunkIter peek = it;
           int nsi, nch;
-          if (peek.next(nsi, nch)) {
-            const ConvSeg& ns = p.seg[nsi];
-            const int n0c = nch * (16 * NH);
-            const float* nsrc;
-            int nCs, ncl;
-            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
-            const bool nfull = ns.taps == 9;
-#pragma unroll
-            for (int i = 0; i < MAXU; ++i)
-              if (upix[i] >= 0 && (nfull || uinterior[i]))
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
-          }
+          if (pf_it.next(nsi, nch)) prefetch_chunk(nsi, nch);
         }
         float sc[16], sh[16];
         if (s.ss) {
@@ -617,15 +607,6 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             const bool valid = upix[i] >= 0;
             const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
             float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            if constexpr (FUSE) if (fuse && uinterior[i]) {          // raw planes (centre tap only needs the interior)
-              if (skip_sep) {
-                const float4 s0 = sraw[FUSE ? i : 0][2 * kh], s1 = sraw[FUSE ? i : 0][2 * kh + 1];
-                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                split_store(sv, valid, off + 2u * c.a_half);
-              } else {
-                split_store(v, valid, off + 2u * c.a_half);
-              }
-            }
             if (valid) {
               if (s.ss) {
 #pragma unroll
@@ -665,52 +646,75 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     const long long t_e0 = dbg ? clock64() : 0;
     constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
     const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
-    const int nacc_main = c.npt * c.nmb;
-    const int nacc = c.fuse ? 2 * nacc_main : nacc_main;     // fused skip: a second accumulator set after the main one
+    const int nacc = c.npt * c.nmb;
     const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
     const int nunits = nacc * units_per_acc;
-    if (p.res && !p.out_cm) {
+    const int Hl = p.H >> 1, Wl = p.W >> 1;         // extents of the half-resolution residual (res_up)
+    if ((p.res || p.res_up) && !p.out_cm) {
       // the producers are idle until the accumulators are complete: pull the residual lines this warp will add
       // into L2 now (one 128-byte line per pixel per warp), so the epilogue loads do not pay HBM latency
       for (int u = grp; u < nunits; u += NGRP) {
         const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
-        if (ai >= nacc_main) continue;
         const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
-        const int y = ty0 + g32 * 4 + (lane >> 3), x = tx0 + 8 * pt + (lane & 7);
         const int cb = m_lo + mb * 128 + q * 32;
-        if (y < p.H && x < p.W && cb < p.Cout)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cb));
+        if (cb >= p.Cout) continue;
+        if (p.res) {
+          const int y = ty0 + g32 * 4 + (lane >> 3), x = tx0 + 8 * pt + (lane & 7);
+          if (y < p.H && x < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cb));
+        } else if (lane < 24) {
+          const int y = ((ty0 + g32 * 4) >> 1) - 1 + lane / 6, x = ((tx0 + 8 * pt) >> 1) - 1 + lane % 6;
+          if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + cb));
+        }
       }
     }
     mbar_wait_relaxed(acc_full, 0);
     const long long t_e1 = dbg ? clock64() : 0;
     tc_fence_after();
     const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
+    const float asc = c.acc_scale;
     double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
     for (int u = grp; u < nunits; u += NGRP) {
       const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
-      const bool is_skip = ai >= nacc_main;
-      const int am = is_skip ? ai - nacc_main : ai;
-      const int pt = am / c.nmb, mb = am - pt * c.nmb;
+      const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
       const int cout = m_lo + mb * 128 + q * 32 + lane;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
       const bool cok = cout < p.Cout;                // rows beyond Cout are zero padding of the weight image
-      if (is_skip) {                                  // skip_out = conv1x1(raw) + skip_bias, no statistics
-        const float sb = (p.skip_bias && cok) ? __ldg(p.skip_bias + cout) : 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int y = ty0 + g32 * 4 + (jj >> 3);
-          const int x = tx0 + 8 * pt + (jj & 7);
-          if (cok && y < p.H && x < p.W) p.skip_out[(((size_t)b * p.H + y) * p.W + x) * p.Cout + cout] = __uint_as_float(r[jj]) + sb;
-        }
-        continue;
-      }
       float add = 0.f;
       if (p.bias && cok) add += __ldg(p.bias + cout);
       if (tembp && cok) add += __ldg(tembp + cout);
       float fs = 0.f, fq = 0.f;
       const int uy0 = ty0 + g32 * 4, ux0 = tx0 + 8 * pt;       // the unit is a 4-row x 8-pixel patch
+      float rv[32];
+      const bool have_res = (p.res != nullptr) | (p.res_up != nullptr);
+      if (p.res_up) {
+        // residual = x2 FIR upsampling of the half-resolution tensor: 4 x 6 source pixels cover the 4 x 8 unit; separable
+        // [1,3]/4 | [3,1]/4 taps, zero outside the image (upfirdn2d pads with zeros)
+        float sv[4][6];
+        const int i0 = (uy0 >> 1) - 1, j0 = (ux0 >> 1) - 1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 6; ++bb) {
+            const int y = i0 + a, x = j0 + bb;
+            sv[a][bb] = (cok && (unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
+                            ? __ldg(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + cout) : 0.f;
+          }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          float vr[6];
+          const int m = rr >> 1;
+#pragma unroll
+          for (int bb = 0; bb < 6; ++bb)
+            vr[bb] = (rr & 1) ? fmaf(0.25f, sv[m + 2][bb], 0.75f * sv[m + 1][bb]) : fmaf(0.75f, sv[m + 1][bb], 0.25f * sv[m][bb]);
+#pragma unroll
+          for (int xx = 0; xx < 8; ++xx) {
+            const int n = xx >> 1;
+            rv[rr * 8 + xx] = (xx & 1) ? fmaf(0.25f, vr[n + 2], 0.75f * vr[n + 1]) : fmaf(0.75f, vr[n + 1], 0.25f * vr[n]);
+          }
+        }
+      }
       if (uy0 + 4 <= p.H && ux0 + 8 <= p.W && !(p.out_cm && (p.W & 3))) {
         // ---- interior unit (every unit of the benchmark shapes): no per-element bounds checks, addresses are
         // row pointer + constant multiples of the pixel stride
@@ -722,7 +726,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
               float v[8];
 #pragma unroll
               for (int xx = 0; xx < 8; ++xx) {
-                v[xx] = (__uint_as_float(r[rr * 8 + xx]) + add) * p.out_scale;
+                v[xx] = fmaf(__uint_as_float(r[rr * 8 + xx]), asc, add) * p.out_scale;
                 fs += v[xx];
                 fq = fmaf(v[xx], v[xx], fq);
               }
@@ -734,18 +738,19 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             const size_t pix0 = (((size_t)b * p.H + uy0) * p.W + ux0) * p.Cout + cout;
             const size_t rstride = (size_t)p.W * p.Cout;
             float* op = p.out + pix0;
-            if (p.res) {
-              const float* rp = p.res + pix0;
-              float rv[32];
+            if (have_res) {
+              if (p.res) {
+                const float* rp = p.res + pix0;
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr)
+                for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                for (int xx = 0; xx < 8; ++xx) rv[rr * 8 + xx] = __ldg(rp + rr * rstride + (size_t)xx * p.Cout);
+                  for (int xx = 0; xx < 8; ++xx) rv[rr * 8 + xx] = __ldg(rp + rr * rstride + (size_t)xx * p.Cout);
+              }
 #pragma unroll
               for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
                 for (int xx = 0; xx < 8; ++xx) {
-                  const float v = (__uint_as_float(r[rr * 8 + xx]) + add + rv[rr * 8 + xx]) * p.out_scale;
+                  const float v = (fmaf(__uint_as_float(r[rr * 8 + xx]), asc, add) + rv[rr * 8 + xx]) * p.out_scale;
                   op[rr * rstride + (size_t)xx * p.Cout] = v;
                   fs += v;
                   fq = fmaf(v, v, fq);
@@ -755,7 +760,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
               for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
                 for (int xx = 0; xx < 8; ++xx) {
-                  const float v = (__uint_as_float(r[rr * 8 + xx]) + add) * p.out_scale;
+                  const float v = fmaf(__uint_as_float(r[rr * 8 + xx]), asc, add) * p.out_scale;
                   op[rr * rstride + (size_t)xx * p.Cout] = v;
                   fs += v;
                   fq = fmaf(v, v, fq);
@@ -764,7 +769,6 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
           }
         }
       } else {
-        float rv[32];
         if (p.res) {     // issue every residual load of the unit before consuming any
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
@@ -780,8 +784,8 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
           if (cok && y < p.H && x < p.W) {
             const size_t o = p.out_cm ? ((size_t)b * p.Cout + cout) * ((size_t)p.H * p.W) + (size_t)y * p.W + x
                                       : (((size_t)b * p.H + y) * p.W + x) * p.Cout + cout;
-            float v = __uint_as_float(r[jj]) + add;
-            if (p.res) v += rv[jj];
+            float v = fmaf(__uint_as_float(r[jj]), asc, add);
+            if (have_res) v += rv[jj];
             v *= p.out_scale;
             p.out[o] = v;
             fs += v;
@@ -834,15 +838,6 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
           }
           if (++stage == c.sw) { stage = 0; phase ^= 1; }
         }
-        if (c.fuse) {      // stage #10 of the chunk: Conv_2 weights (1x1), one image per chunk
-          const uint8_t* sbase = reinterpret_cast<const uint8_t*>(p.skip_wtc) + (size_t)m_lo * 32 + (size_t)ch * q_stride;
-          mbar_wait(w_empty(stage), phase ^ 1);
-          const uint32_t dst = w_base + stage * c.w_stage;
-          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-          bulk_g2s(dst, sbase, (uint32_t)c.w_half, w_full(stage));
-          bulk_g2s(dst + c.w_half, sbase + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
-          if (++stage == c.sw) { stage = 0; phase ^= 1; }
-        }
       }
     }
   } else {
@@ -869,39 +864,22 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   }
   // operand split of the packed weights (decided when they were packed); every segment of a launch must agree, and the
   // 32-channel K chunks of mode 1 must not straddle a concat seam
-  c.prec = seg_prec(p.seg[0]);
+  c.prec = p.seg[0].wprec;
   for (int i = 0; i < p.nseg; ++i) {
     const ConvSeg& s = p.seg[i];
-    if (seg_prec(s) != c.prec) return false;
+    if (s.wprec != c.prec) return false;
     if (c.prec == 1 && (s.C0 % 32 != 0 || s.C1 % 32 != 0)) return false;
+    if (c.prec == 1 && s.wscale != p.seg[0].wscale) return false;       // one accumulator, one weight scale
   }
-  if (c.prec == 1 && p.skip_wtc) return false;
-  static bool env_read = false;
-  if (!env_read) {
-    const char* e = getenv("STORM_B200_TC_PER_SM");
-    if (e) g_tc_force_per_sm = atoi(e);
-    env_read = true;
-  }
+  c.acc_scale = c.prec == 1 ? 1.0f / p.seg[0].wscale : 1.0f;
+  if (p.res && p.res_up) return false;
+  if (p.res_up && ((p.H | p.W) & 1)) return false;
+  static const int env_per_sm = [] { const char* e = getenv("STORM_B200_TC_PER_SM"); return e ? atoi(e) : -1; }();
+  if (env_per_sm >= 0) g_tc_force_per_sm = env_per_sm;
+  // K chunks the producers prefetch ahead (L2): 1 = round 1's behaviour
+  static const int env_pf = [] { const char* e = getenv("STORM_B200_PF_DEPTH"); return e ? atoi(e) : 0; }();
+  c.pf_depth = env_pf > 0 ? env_pf : (p.nseg == 2 ? 4 : 2);
   const int nblk = tc_mpad(p.Cout) / 128;
-  if (p.skip_wtc) {
-    // fused skip: 256-pixel (or 128-pixel) tile x one 128-channel block, main + skip accumulators = 512 (256) columns,
-    // one CTA per SM, four activation planes per stage
-    if (p.nseg != 1 || p.seg[0].taps != 9 || !p.skip_out || p.out_cm) return false;
-    c.rows = p.H > 16 ? 32 : 16; c.npt = 1; c.nmb = 1; c.per_sm = 1; c.fuse = 1;
-    c.ncol = 8 * c.rows;
-    c.msplit = nblk;
-    c.hx = 10; c.hy = c.rows + 2; c.np = c.hx * c.hy;
-    c.a_half = 2 * c.np * 16; c.a_plane = c.a_half; c.a_stage = 4 * c.a_half;
-    c.w_half = 4096; c.w_stage = 8192;
-    c.sa = 2;
-    int sw = (SMEM_BUDGET - c.sa * c.a_stage - 256) / c.w_stage;
-    c.sw = sw > 10 ? 10 : sw;
-    c.tiles_x = ceil_div(p.W, 8);
-    c.tiles_y = ceil_div(p.H, c.rows);
-    c.w_plane = c.w_half;
-    return true;
-  }
-  c.fuse = 0;
   // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
   // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).
   struct Cand { int rows, npt, nmb, per_sm; };
@@ -978,7 +956,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
 }  // namespace
 
 // epilogue warp groups per TMEM lane quadrant (= GroupNorm partial-sum chunks per tile) of the kernel variant launched
-static int tc_ngrp(const TcpCfg& c) { return (c.per_sm == 1 && !c.fuse) ? 3 : 2; }
+static int tc_ngrp(const TcpCfg& c) { return c.per_sm == 1 ? 3 : 2; }
 
 bool conv_tc_eligible(const ConvParams& p) {
   TcpCfg cp;
@@ -991,37 +969,59 @@ int conv_tc_stats_chunks(const ConvParams& p) {
   return tc_ngrp(cp) * cp.tiles_x * cp.tiles_y;
 }
 
+int conv_tc_init_device() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  STORM_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
+
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, false, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, false, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, true, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, false, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
-    STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)));
-    attr = true;
-  }
+  STORM_TRY(conv_tc_init_device());
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return fail(-1, "conv_tc: shape not eligible");
-  if (p.out_cm && p.res) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
+  if (p.out_cm && (p.res || p.res_up)) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
   if (p.stats_out && p.stats_chunks != tc_ngrp(cp) * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-  if (cp.fuse) conv_tcp_kernel<2, 1, true, 8, 0><<<grid, 320, smem, st>>>(p, cp);
-  else if (cp.per_sm == 2 && cp.prec) conv_tcp_kernel<2, 2, false, 8, 1><<<grid, 320, smem, st>>>(p, cp);
-  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, false, 8, 0><<<grid, 320, smem, st>>>(p, cp);
-  else if (cp.prec) conv_tcp_kernel<2, 1, false, 12, 1><<<grid, 448, smem, st>>>(p, cp);
-  else conv_tcp_kernel<2, 1, false, 12, 0><<<grid, 448, smem, st>>>(p, cp);      // np <= 612 <= 2 * 384
+  if (cp.per_sm == 2 && cp.prec) conv_tcp_kernel<2, 2, 8, 1><<<grid, 320, smem, st>>>(p, cp);
+  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, 8, 0><<<grid, 320, smem, st>>>(p, cp);
+  else if (cp.prec) conv_tcp_kernel<2, 1, 12, 1><<<grid, 448, smem, st>>>(p, cp);
+  else conv_tcp_kernel<2, 1, 12, 0><<<grid, 448, smem, st>>>(p, cp);      // np <= 612 <= 2 * 384
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
-int tc_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void** out, std::vector<void*>* owned, cudaStream_t st,
-                    int max_prec) {
-  return pack_common(w_oihw, Cout, Cin, taps, 0, max_prec, out, owned, st);
+int tc_weight_absmax(const float* w, size_t n, float* out_host, cudaStream_t st) {
+  unsigned* d = nullptr;
+  STORM_CUDA_TRY(cudaMalloc((void**)&d, sizeof(unsigned)));
+  STORM_CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned), st));
+  const unsigned blocks = (unsigned)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
+  absmax_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(w, n, d);
+  unsigned u = 0;
+  cudaError_t e = cudaMemcpyAsync(&u, d, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(-2, std::string("tc_weight_absmax: ") + cudaGetErrorString(e));
+  memcpy(out_host, &u, sizeof(float));
+  return 0;
 }
-int tc_pack_weights_io(const float* w_io, int Cin, int Cout, void** out, std::vector<void*>* owned, cudaStream_t st, int max_prec) {
-  return pack_common(w_io, Cout, Cin, 1, 1, max_prec, out, owned, st);
+
+int tc_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, TcWeights* out, std::vector<void*>* owned, cudaStream_t st,
+                    int max_prec, float absmax) {
+  return pack_common(w_oihw, Cout, Cin, taps, 0, max_prec, absmax, out, owned, st);
+}
+int tc_pack_weights_io(const float* w_io, int Cin, int Cout, TcWeights* out, std::vector<void*>* owned, cudaStream_t st, int max_prec,
+                       float absmax) {
+  return pack_common(w_io, Cout, Cin, 1, 1, max_prec, absmax, out, owned, st);
 }
 
 }  // namespace storm

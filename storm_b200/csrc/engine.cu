@@ -27,7 +27,9 @@ int fail(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------------
-constexpr int PYR_CH = 16;   // channels of the (zero-padded) input pyramid tensors
+constexpr int PYR_CH = 16;   // channels of the (zero-padded) network input = level 0 of the input pyramid (one 16-channel K chunk)
+constexpr int PYR_DOWN_CH = 32;   // channels of the downsampled pyramid levels: a whole 32-channel K chunk, so that the down blocks'
+                                  // Conv_1 + Conv_2 + Combine launches stay on the two-pass operand split
 
 enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RES, M_ATTN, M_COMBINE, M_GN, M_CONV_OUT };
 
@@ -83,23 +85,22 @@ struct Pool {
 struct ResPack {
   const float *gn0_g = nullptr, *gn0_b = nullptr, *gn1_g = nullptr, *gn1_b = nullptr;
   const float *b0 = nullptr;        // Conv_0.bias
-  const float *b1 = nullptr, *b2 = nullptr;   // Conv_1.bias, Conv_2.bias (fused-skip path)
   float* b12 = nullptr;             // Conv_1.bias (+ Conv_2.bias)
   float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;   // SIMT layouts
-  void *tc0 = nullptr, *tc1 = nullptr, *tc2 = nullptr; // tcgen05 layouts
+  TcWeights tc0, tc1, tc2;                              // tcgen05 layouts (tc1 and tc2 share one weight scale: one launch)
   int temb_off = 0;
   bool has_skip_conv = false;
   // down blocks followed by a Combine: Conv_2 and sqrt(2)*Combine.Conv_0 concatenated along K (x' | padded pyramid)
-  void* tc2c = nullptr;
+  TcWeights tc2c, tc1c;     // tc1c: Conv_1 packed with the scale it shares with tc2c
   float* b12c = nullptr;
 };
 struct AttnPack {
   const float *gn_g = nullptr, *gn_b = nullptr;
   const float* w[4] = {nullptr, nullptr, nullptr, nullptr};   // NIN W is already [in][out]
   const float* b[4] = {nullptr, nullptr, nullptr, nullptr};
-  void* tc[4] = {nullptr, nullptr, nullptr, nullptr};
+  TcWeights tc[4];
 };
-struct SmallConvPack { float* w = nullptr; const float* b = nullptr; void* tc = nullptr; int npad = 0; };
+struct SmallConvPack { float* w = nullptr; const float* b = nullptr; TcWeights tc; int npad = 0; };
 
 }  // namespace storm
 
@@ -125,7 +126,8 @@ struct StormHandle {
   std::map<std::string, Act> taps;
   // per-step cache of the time-embedding biases: corrector and predictor of one PC step share t
   float* temb_cache = nullptr;
-  int temb_cache_B = 0;
+  int temb_cache_B = 0;       // rows allocated
+  int temb_cache_rows = 0;    // rows computed at temb_cache_t
   float temb_cache_t = -1.f;
   bool temb_cache_valid = false;
   bool profile_on = false;
@@ -143,6 +145,19 @@ struct StormHandle {
 };
 
 namespace storm {
+
+// Every entry point that takes a handle runs on the device the handle was created on (and restores the caller's
+// current device afterwards): `model.cuda(1)` from a process whose current device is 0 must not launch device-0 kernels
+// on device-1 pointers.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const StormHandle* h) {
+    if (!h) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 static void add_param(StormHandle* h, const std::string& name, std::initializer_list<int64_t> shape) {
   ParamEntry e;
@@ -295,8 +310,6 @@ static int repack(StormHandle* h, cudaStream_t st) {
       r.gn0_g = h->P(p + ".GroupNorm_0.weight"); r.gn0_b = h->P(p + ".GroupNorm_0.bias");
       r.gn1_g = h->P(p + ".GroupNorm_1.weight"); r.gn1_b = h->P(p + ".GroupNorm_1.bias");
       r.b0 = h->P(p + ".Conv_0.bias");
-      r.b1 = h->P(p + ".Conv_1.bias");
-      r.b2 = h->P(p + ".Conv_2.bias");
       r.has_skip_conv = h->P(p + ".Conv_2.weight") != nullptr;
       STORM_TRY(dev_alloc(h, (size_t)9 * m.in_ch * m.out_ch, &r.w0));
       LAUNCH(h, launch_pack_conv_simt(h->P(p + ".Conv_0.weight"), r.w0, m.out_ch, m.in_ch, 9, st));
@@ -312,8 +325,13 @@ static int repack(StormHandle* h, cudaStream_t st) {
       }
       if (use_tc) {
         STORM_TRY(tc_pack_weights(h->P(p + ".Conv_0.weight"), m.out_ch, m.in_ch, 9, &r.tc0, &h->packed, st));
-        STORM_TRY(tc_pack_weights(h->P(p + ".Conv_1.weight"), m.out_ch, m.out_ch, 9, &r.tc1, &h->packed, st));
-        if (r.has_skip_conv) STORM_TRY(tc_pack_weights(h->P(p + ".Conv_2.weight"), m.out_ch, m.in_ch, 1, &r.tc2, &h->packed, st));
+        // Conv_1 and Conv_2 accumulate into one TMEM tile: one weight scale for both (largest |w| of the two tensors)
+        float a1 = 0.f, a2 = 0.f;
+        STORM_TRY(tc_weight_absmax(h->P(p + ".Conv_1.weight"), (size_t)9 * m.out_ch * m.out_ch, &a1, st));
+        if (r.has_skip_conv) STORM_TRY(tc_weight_absmax(h->P(p + ".Conv_2.weight"), (size_t)m.out_ch * m.in_ch, &a2, st));
+        const float a12 = std::max(a1, a2);
+        STORM_TRY(tc_pack_weights(h->P(p + ".Conv_1.weight"), m.out_ch, m.out_ch, 9, &r.tc1, &h->packed, st, 1, a12));
+        if (r.has_skip_conv) STORM_TRY(tc_pack_weights(h->P(p + ".Conv_2.weight"), m.out_ch, m.in_ch, 1, &r.tc2, &h->packed, st, 1, a12));
       }
       r.temb_off = off;
       if (h->conditional()) {
@@ -377,11 +395,15 @@ static int repack(StormHandle* h, cudaStream_t st) {
         ResPack& r = it->second;
         const std::string pp = "all_modules." + std::to_string(pm.index);
         float* wcat = nullptr;
-        STORM_TRY(dev_alloc(h, (size_t)pm.out_ch * (pm.in_ch + PYR_CH), &wcat));
-        LAUNCH(h, launch_concat_1x1(h->P(pp + ".Conv_2.weight"), pm.in_ch, s.w, m.in_ch, PYR_CH, 1.41421356237309505f, wcat, pm.out_ch, st));
-        STORM_TRY(tc_pack_weights(wcat, pm.out_ch, pm.in_ch + PYR_CH, 1, &r.tc2c, &h->packed, st, 0));
-        // the 16 pyramid channels keep this launch on 16-channel K chunks: Conv_1's image must be in the same mode
-        STORM_TRY(tc_pack_weights(h->P(pp + ".Conv_1.weight"), pm.out_ch, pm.out_ch, 9, &r.tc1, &h->packed, st, 0));
+        STORM_TRY(dev_alloc(h, (size_t)pm.out_ch * (pm.in_ch + PYR_DOWN_CH), &wcat));
+        LAUNCH(h, launch_concat_1x1(h->P(pp + ".Conv_2.weight"), pm.in_ch, s.w, m.in_ch, PYR_DOWN_CH, 1.41421356237309505f, wcat, pm.out_ch, st));
+        // Conv_1 and the concatenated 1x1 share a launch: same operand split, same weight scale -> repack Conv_1 with it
+        float a1 = 0.f, ac = 0.f;
+        STORM_TRY(tc_weight_absmax(h->P(pp + ".Conv_1.weight"), (size_t)9 * pm.out_ch * pm.out_ch, &a1, st));
+        STORM_TRY(tc_weight_absmax(wcat, (size_t)pm.out_ch * (pm.in_ch + PYR_DOWN_CH), &ac, st));
+        const float a1c = std::max(a1, ac);
+        STORM_TRY(tc_pack_weights(wcat, pm.out_ch, pm.in_ch + PYR_DOWN_CH, 1, &r.tc2c, &h->packed, st, 1, a1c));
+        STORM_TRY(tc_pack_weights(h->P(pp + ".Conv_1.weight"), pm.out_ch, pm.out_ch, 9, &r.tc1c, &h->packed, st, r.tc2c.prec, a1c));
         STORM_TRY(dev_alloc(h, (size_t)pm.out_ch, &r.b12c));
         LAUNCH(h, launch_add_vec(r.b12, s.b, r.b12c, pm.out_ch, 1.41421356237309505f, st));
       }
@@ -495,12 +517,44 @@ struct Fwd {
       if (x1) return fail(STORM_E_STATE, "res_block: resampling block with concatenated input");
       H = m.up ? 2 * x0.H : x0.H / 2;
       W = m.up ? 2 * x0.W : x0.W / 2;
-      STORM_TRY(alloc(hr, H, W, Cin));
-      STORM_TRY(alloc(xr, H, W, Cin));
-      LAUNCH(h, launch_resample(x0, ss0, hr.p, xr.p, m.up ? 1 : 2, st));
     }
-    Act h1, skipS;
-    bool fused = false;
+    // ---- Conv_1 (+ Conv_2 / identity skip) launch, described first: whether the up block's skip can run at LOW
+    // resolution depends on the tensor-core kernel taking both launches
+    ConvParams p1{};
+    Act skipL;        // up blocks: S = Conv_2.weight * x at the INPUT resolution (bias folded into b12)
+    bool lowres_skip = false;
+    ConvParams ps{};
+    {
+      ConvSeg& s = p1.seg[0];
+      s.src0 = nullptr; s.C0 = m.out_ch; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 1; s.taps = 9; s.w = r.w1;
+      set_wtc(s, r.tc1);
+      p1.nseg = 1;
+      p1.bias = r.b12;
+      p1.B = B; p1.H = H; p1.W = W; p1.Cout = m.out_ch;
+      p1.out_scale = 0.70710678118654752f;   // (x + h) / sqrt(2), layerspp.py:274
+      static const bool no_lowres = getenv("STORM_B200_NO_LOWRES_SKIP") && atoi(getenv("STORM_B200_NO_LOWRES_SKIP")) != 0;
+      if (m.up && r.has_skip_conv && h->cfg.engine == 0 && r.tc1.img && r.tc2.img && !no_lowres) {
+        // Conv_2 is 1x1 and the FIR resampling is linear and per channel, so they commute:
+        //   Conv_2(FIR_up(x)) = FIR_up(Conv_2.weight * x) + b2   (layerspp.py:250-252,268-269)
+        // The 1x1 runs on a quarter of the pixels, FIR_up(x) is never materialised, and Conv_1's epilogue adds the
+        // upsampled S (4 x 6 low-resolution loads per 4 x 8 output unit instead of 32 residual loads).
+        ps.nseg = 1;
+        ConvSeg& k = ps.seg[0];
+        k.src0 = x0.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2;
+        set_wtc(k, r.tc2);
+        ps.B = B; ps.H = x0.H; ps.W = x0.W; ps.Cout = m.out_ch; ps.out_scale = 1.0f;
+        ConvParams probe = p1;
+        probe.seg[0].src0 = x0.p;                 // any non-null pointer: eligibility does not look at the data
+        probe.res_up = x0.p;
+        lowres_skip = conv_tc_eligible(ps) && conv_tc_eligible(probe);
+      }
+    }
+    if (resamp) {
+      STORM_TRY(alloc(hr, H, W, Cin));
+      if (!lowres_skip) STORM_TRY(alloc(xr, H, W, Cin));
+      LAUNCH(h, launch_resample(x0, ss0, hr.p, lowres_skip ? nullptr : xr.p, m.up ? 1 : 2, st));
+    }
+    Act h1;
     STORM_TRY(alloc(h1, H, W, m.out_ch));
     {
       ConvParams p{};
@@ -508,66 +562,54 @@ struct Fwd {
       ConvSeg& s = p.seg[0];
       if (resamp) { s.src0 = hr.p; s.C0 = Cin; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; }
       else { s.src0 = x0.p; s.C0 = x0.C; s.src1 = x1 ? x1->p : nullptr; s.C1 = x1 ? x1->C : 0; s.ss = ss0; s.silu = 1; }
-      s.taps = 9; s.w = r.w0; s.wtc = r.tc0;
+      s.taps = 9; s.w = r.w0;
+      set_wtc(s, r.tc0);
       p.B = B; p.H = H; p.W = W; p.Cout = m.out_ch;
       p.bias = r.b0;
       p.temb = tembias ? tembias + r.temb_off : nullptr;
       p.temb_stride = h->dense_total;
       p.res = nullptr; p.out_scale = 1.0f; p.out = h1.p;
-      // Measured slower than the interleaved 1x1 segment (the activation producers, not the MMAs, are the limiter:
-      // profiles/r1_bench_history.md), so it is opt-in: STORM_B200_FUSE_SKIP=1.
-      static const bool fuse_enabled = getenv("STORM_B200_FUSE_SKIP") && atoi(getenv("STORM_B200_FUSE_SKIP")) != 0;
-      if (fuse_enabled && r.has_skip_conv && h->cfg.engine == 0 && r.tc0 && r.tc2) {
-        // fused skip: this launch also produces S = Conv_2(raw x) + b2 from the values its producers already hold
-        STORM_TRY(alloc(skipS, H, W, m.out_ch));
-        p.skip_wtc = r.tc2;
-        p.skip_src0 = resamp ? xr.p : nullptr;
-        p.skip_src1 = nullptr;
-        p.skip_bias = r.b2;
-        p.skip_out = skipS.p;
-        if (conv_tc_eligible(p)) fused = true;
-        else { release(skipS); p.skip_wtc = nullptr; p.skip_src0 = nullptr; p.skip_bias = nullptr; p.skip_out = nullptr; }
-      }
       STORM_TRY(conv(p, &h1));
     }
     h->pool.put(ss0);
     if (resamp) release(hr);
+    if (lowres_skip) {
+      STORM_TRY(alloc(skipL, x0.H, x0.W, m.out_ch));
+      ps.out = skipL.p;
+      STORM_TRY(conv(ps));
+    }
     float* ss1 = nullptr;
     STORM_TRY(gn_ss(h1, nullptr, r.gn1_g, r.gn1_b, &ss1));
     STORM_TRY(alloc(out, H, W, m.out_ch));
     {
-      ConvParams p{};
-      ConvSeg& s = p.seg[0];
-      s.src0 = h1.p; s.C0 = m.out_ch; s.src1 = nullptr; s.C1 = 0; s.ss = ss1; s.silu = 1; s.taps = 9; s.w = r.w1; s.wtc = r.tc1;
-      p.nseg = 1;
-      p.res = nullptr;
-      p.bias = r.b12;
-      if (fused) {
-        p.res = skipS.p;              // (Conv_1(h) + b1 + S) / sqrt(2)
-        p.bias = r.b1;
+      ConvParams& p = p1;
+      p.seg[0].src0 = h1.p;
+      p.seg[0].ss = ss1;
+      if (lowres_skip) {
+        p.res_up = skipL.p;
       } else if (r.has_skip_conv) {
         ConvSeg& k = p.seg[1];
         if (resamp) { k.src0 = xr.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; }
         else { k.src0 = x0.p; k.C0 = x0.C; k.src1 = x1 ? x1->p : nullptr; k.C1 = x1 ? x1->C : 0; }
-        k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2; k.wtc = r.tc2;
-        if (pyr_fuse) {      // Combine folded in: the padded pyramid rides along as 16 more K channels of the skip segment
-          k.src1 = pyr_fuse->p; k.C1 = PYR_CH; k.w = nullptr; k.wtc = r.tc2c;
+        k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2;
+        set_wtc(k, r.tc2);
+        if (pyr_fuse) {      // Combine folded in: the padded pyramid rides along as 32 more K channels of the skip segment
+          k.src1 = pyr_fuse->p; k.C1 = pyr_fuse->C; k.w = nullptr;
+          set_wtc(k, r.tc2c);
+          set_wtc(p.seg[0], r.tc1c);
           p.bias = r.b12c;
         }
         p.nseg = 2;
       } else {
         p.res = x0.p;     // identity skip: in_ch == out_ch, no resampling, single source
       }
-      p.B = B; p.H = H; p.W = W; p.Cout = m.out_ch;
-      p.temb = nullptr; p.temb_stride = 0;
-      p.out_scale = 0.70710678118654752f;   // (x + h) / sqrt(2), layerspp.py:274
       p.out = out.p;
       STORM_TRY(conv(p, &out));
     }
     h->pool.put(ss1);
     release(h1);
-    if (fused) release(skipS);
-    if (resamp) release(xr);
+    if (lowres_skip) release(skipL);
+    if (resamp && !lowres_skip) release(xr);
     return 0;
   }
 
@@ -585,7 +627,7 @@ struct Fwd {
       ConvParams p{};
       p.nseg = 1;
       ConvSeg& s = p.seg[0];
-      s.src0 = x.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = ss; s.silu = 0; s.taps = 1; s.w = a.w[i]; s.wtc = a.tc[i];
+      s.src0 = x.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = ss; s.silu = 0; s.taps = 1; s.w = a.w[i]; set_wtc(s, a.tc[i]);
       p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[i]; p.out_scale = 1.0f; p.out = qkv[i]->p;
       if (i == 2 && use_tc_attn) {
         if (conv_tc_eligible(p)) p.out_cm = 1;     // V channel-major: K-major operand of the P.V tensor-core GEMM
@@ -603,7 +645,7 @@ struct Fwd {
       ConvParams p{};
       p.nseg = 1;
       ConvSeg& s = p.seg[0];
-      s.src0 = o.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; s.taps = 1; s.w = a.w[3]; s.wtc = a.tc[3];
+      s.src0 = o.p; s.C0 = C; s.src1 = nullptr; s.C1 = 0; s.ss = nullptr; s.silu = 0; s.taps = 1; s.w = a.w[3]; set_wtc(s, a.tc[3]);
       p.B = B; p.H = x.H; p.W = x.W; p.Cout = C; p.bias = a.b[3]; p.res = x.p; p.out_scale = 0.70710678118654752f; p.out = out.p;
       STORM_TRY(conv(p, &out));
     }
@@ -652,7 +694,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
         h->temb_cache_valid = false;
       }
       tembias = h->temb_cache;
-      hit = h->temb_cache_valid && h->temb_cache_t == *t_uniform;
+      hit = h->temb_cache_valid && h->temb_cache_t == *t_uniform && h->temb_cache_rows >= B;
     } else {
       STORM_TRY(h->pool.get((size_t)B * h->dense_total * sizeof(float), &p)); tembias = (float*)p;
       tembias_pooled = true;
@@ -662,7 +704,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
       LAUNCH(h, launch_temb_mlp(t, h->P("all_modules.0.W"), h->W1t, h->P("all_modules.1.bias"), h->W2t,
                                 h->P("all_modules.2.bias"), act, B, nf, st));
       LAUNCH(h, launch_dense_all(act, h->denseWt, h->denseB, tembias, B, 4 * nf, h->dense_total, st));
-      if (t_uniform) { h->temb_cache_valid = true; h->temb_cache_t = *t_uniform; }
+      if (t_uniform) { h->temb_cache_valid = true; h->temb_cache_t = *t_uniform; h->temb_cache_rows = B; }
     }
   }
 
@@ -679,7 +721,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     STORM_TRY(f.alloc(a, F, T, nf));
     ConvParams p{};
     p.nseg = 1;
-    p.seg[0].src0 = x0.p; p.seg[0].C0 = PYR_CH; p.seg[0].taps = 9; p.seg[0].w = s.w; p.seg[0].wtc = s.tc;
+    p.seg[0].src0 = x0.p; p.seg[0].C0 = PYR_CH; p.seg[0].taps = 9; p.seg[0].w = s.w; set_wtc(p.seg[0], s.tc);
     p.B = B; p.H = F; p.W = T; p.Cout = nf; p.bias = s.b; p.out_scale = 1.0f; p.out = a.p;
     static const bool no_tc_in = getenv("STORM_B200_NO_FUSE_INPUT") && atoi(getenv("STORM_B200_NO_FUSE_INPUT")) != 0;
     if (no_tc_in) { LAUNCH(h, launch_conv_simt(p, st)); } else { STORM_TRY(f.conv(p, &a)); }
@@ -709,13 +751,13 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     }
     if (lvl != nres - 1) {
       Act pd;      // input pyramid one level down (ncsnpp.py:353)
-      STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, PYR_CH));
-      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, PYR_CH, st));
+      STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, PYR_DOWN_CH));
+      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, pyr_in.C, PYR_DOWN_CH, st));
       f.release(pyr_in);
       pyr_in = pd;
       const Mod& dm = h->mods[mi];
       static const bool no_fuse_in = getenv("STORM_B200_NO_FUSE_INPUT") && atoi(getenv("STORM_B200_NO_FUSE_INPUT")) != 0;
-      const bool fuse_combine = !no_fuse_in && !h->taps_on && h->cfg.engine == 0 && h->res.at(dm.index).tc2c != nullptr;
+      const bool fuse_combine = !no_fuse_in && !h->taps_on && h->cfg.engine == 0 && h->res.at(dm.index).tc2c.img != nullptr;
       Act o;
       STORM_TRY(f.res_block(dm, hs.back(), nullptr, tembias, o, fuse_combine ? &pyr_in : nullptr));
       ++mi;
@@ -727,7 +769,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
         const SmallConvPack& s = h->combine.at(h->mods[mi].index);
         Act o2;
         STORM_TRY(f.alloc(o2, o.H, o.W, o.C));
-        LAUNCH(h, launch_combine(o.p, pyr_in.p, PYR_CH, s.w, s.b, o2.p, B, o.H * o.W, o.C, inch, st));
+        LAUNCH(h, launch_combine(o.p, pyr_in.p, pyr_in.C, s.w, s.b, o2.p, B, o.H * o.W, o.C, inch, st));
         STORM_TRY(tapmod(h->mods[mi], o2));
         ++mi;
         f.release(o);
@@ -782,10 +824,10 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
       Act np;
       STORM_TRY(f.alloc(np, hcur.H, hcur.W, inch));
       bool done = false;
-      if (h->cfg.engine == 0 && s.tc) {
+      if (h->cfg.engine == 0 && s.tc.img) {
         ConvParams p{};
         p.nseg = 1;
-        p.seg[0].src0 = hcur.p; p.seg[0].C0 = hcur.C; p.seg[0].ss = ss; p.seg[0].silu = 1; p.seg[0].taps = 1; p.seg[0].wtc = s.tc;
+        p.seg[0].src0 = hcur.p; p.seg[0].C0 = hcur.C; p.seg[0].ss = ss; p.seg[0].silu = 1; p.seg[0].taps = 1; set_wtc(p.seg[0], s.tc);
         p.B = B; p.H = hcur.H; p.W = hcur.W; p.Cout = s.npad; p.out_scale = 1.0f;
         if (conv_tc_eligible(p)) {
           void* zq;
@@ -967,7 +1009,8 @@ int storm_create(const StormNetConfig* cfg, StormHandle** out) {
   StormHandle* h = new StormHandle();
   h->cfg = *cfg;
   cudaGetDevice(&h->device);
-  int rc = build_plan(h);
+  int rc = conv_tc_init_device();
+  if (rc == 0) rc = build_plan(h);
   if (rc != 0) { delete h; return rc; }
   void* p = nullptr;
   e = cudaMalloc(&p, (size_t)h->n_floats * sizeof(float));
@@ -979,6 +1022,7 @@ int storm_create(const StormNetConfig* cfg, StormHandle** out) {
 
 int storm_destroy(StormHandle* h) {
   if (!h) return 0;
+  DeviceGuard dg(h);
   cudaDeviceSynchronize();
   free_packed(h);
   for (auto& kv : h->taps) cudaFree(kv.second.p);
@@ -1005,6 +1049,7 @@ int storm_param_info(const StormHandle* h, int32_t i, char* name, int32_t cap, i
 
 int storm_load_weights(StormHandle* h, const float* blob, int64_t n, int32_t is_device, void* stream) {
   if (!h || !blob) return fail(STORM_E_INVALID, "storm_load_weights: null argument");
+  DeviceGuard dg(h);
   if (n != h->n_floats)
     return fail(STORM_E_INVALID, "storm_load_weights: blob has " + std::to_string(n) + " floats, expected " + std::to_string(h->n_floats));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1019,6 +1064,7 @@ int storm_weights_device(StormHandle* h, float** dev, int64_t* n) {
 }
 int storm_repack_weights(StormHandle* h, void* stream) {
   if (!h) return fail(STORM_E_INVALID, "null handle");
+  DeviceGuard dg(h);
   return repack(h, (cudaStream_t)stream);
 }
 
@@ -1028,6 +1074,7 @@ int storm_reset_launch_count(StormHandle* h) { if (h) h->launches = 0; return 0;
 
 int storm_net_forward(StormHandle* h, const float* in, const float* t, float* out, int32_t B, int32_t F, int32_t T, void* stream) {
   if (!h || !in || !out) return fail(STORM_E_INVALID, "storm_net_forward: null argument");
+  DeviceGuard dg(h);
   const int nc = h->in_ch() / 2;
   UnpackSrc src{};
   for (int ch = 0; ch < nc; ++ch) { src.p[ch] = in + (size_t)ch * F * T * 2; src.bstride[ch] = (long long)nc * F * T; }
@@ -1036,6 +1083,7 @@ int storm_net_forward(StormHandle* h, const float* in, const float* t, float* ou
 
 int storm_reserve(StormHandle* h, int32_t B, int32_t F, int32_t T) {
   if (!h) return fail(STORM_E_INVALID, "null handle");
+  DeviceGuard dg(h);
   const int nc = h->in_ch() / 2;
   void *a, *b, *c;
   STORM_TRY(h->pool.get((size_t)B * nc * F * T * 8, &a));
@@ -1057,6 +1105,7 @@ int storm_set_debug_taps(StormHandle* h, int32_t enable) {
 }
 int storm_get_tap(StormHandle* h, const char* name, float* out, int64_t cap, int64_t shape[4], void* stream) {
   if (!h || !name) return fail(STORM_E_INVALID, "null argument");
+  DeviceGuard dg(h);
   auto it = h->taps.find(name);
   if (it == h->taps.end()) return fail(STORM_E_INVALID, std::string("no tap named ") + name);
   const Act& a = it->second;
@@ -1076,6 +1125,7 @@ int storm_pc_sample(StormHandle* h, const float* Y, const float* cond0, const fl
                     const StormSamplerConfig* sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int32_t* nfe_out,
                     void* stream) {
   if (!h || !Y || !X) return fail(STORM_E_INVALID, "storm_pc_sample: null argument");
+  DeviceGuard dg(h);
   STORM_TRY(check_sampler(sc));
   return pc_sample(h, Y, cond0, cond1, X, B, F, T, *sc, seed, utt_ids, noise, nfe_out, (cudaStream_t)stream);
 }
@@ -1088,6 +1138,7 @@ int storm_philox_normal(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n
 int storm_ode_drift(StormHandle* h, const float* X, const float* Y, float t, float* drift, int32_t B, int32_t F, int32_t T,
                     const StormSamplerConfig* sc, void* stream) {
   if (!h || !X || !Y || !drift) return fail(STORM_E_INVALID, "storm_ode_drift: null argument");
+  DeviceGuard dg(h);
   STORM_TRY(check_sampler(sc));
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)F * T;
@@ -1113,6 +1164,7 @@ int storm_set_profile(StormHandle* h, int32_t enable) {
 }
 int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double flops[2]) {
   if (!h) return fail(STORM_E_INVALID, "null handle");
+  DeviceGuard dg(h);
   STORM_CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 2; ++i) { launches[i] = 0; ms[i] = 0; flops[i] = 0; }
   FILE* dump = nullptr;
@@ -1130,45 +1182,46 @@ int storm_get_profile(StormHandle* h, int64_t launches[2], double ms[2], double 
 int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
                      int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
                      const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, void* stream) {
-  return storm_debug_conv_timed(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, out_scale, out, B, H, W, nullptr,
-                                nullptr, stream);
+  return storm_debug_conv_ex(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, nullptr, out_scale, out, B, H, W, 1,
+                             nullptr, nullptr, stream);
 }
 
 int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
                            int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
                            const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W, long long* dbg_dev,
                            float* ms_out, void* stream) {
-  return storm_debug_conv_fused(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, out_scale, out, nullptr, B, H, W,
-                                dbg_dev, ms_out, stream);
+  return storm_debug_conv_ex(engine, x0, x1, C0, C1, ss, silu, taps, w, x2, C2, w2, Cout, bias, res, nullptr, out_scale, out, B, H, W, 1,
+                             dbg_dev, ms_out, stream);
 }
 
-int storm_debug_conv_fused(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
-                           int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
-                           const float* res, float out_scale, float* out, float* skip_out, int32_t B, int32_t H, int32_t W,
-                           long long* dbg_dev, float* ms_out, void* stream) {
+int storm_debug_conv_ex(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
+                        int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout, const float* bias,
+                        const float* res, const float* res_up, float out_scale, float* out, int32_t B, int32_t H, int32_t W,
+                        int32_t max_prec, long long* dbg_dev, float* ms_out, void* stream) {
   if (!x0 || !w || !out) return fail(STORM_E_INVALID, "storm_debug_conv: null argument");
-  if (skip_out && (engine != 0 || !w2)) return fail(STORM_E_INVALID, "storm_debug_conv: fused skip needs the tcgen05 engine and w2");
+  if (res_up && engine != 0) return fail(STORM_E_INVALID, "storm_debug_conv: the half-resolution residual needs the tcgen05 engine");
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<void*> owned;
   ConvParams p{};
-  p.nseg = (x2 && !skip_out) ? 2 : 1;
+  p.nseg = x2 ? 2 : 1;
   p.seg[0].src0 = x0; p.seg[0].src1 = x1; p.seg[0].C0 = C0; p.seg[0].C1 = x1 ? C1 : 0; p.seg[0].ss = ss; p.seg[0].silu = silu;
   p.seg[0].taps = taps;
-  if (x2 && !skip_out) { p.seg[1].src0 = x2; p.seg[1].C0 = C2; p.seg[1].taps = 1; }
-  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.bias = bias; p.res = res; p.out_scale = out_scale; p.out = out;
+  if (x2) { p.seg[1].src0 = x2; p.seg[1].C0 = C2; p.seg[1].taps = 1; }
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.bias = bias; p.res = res; p.res_up = res_up; p.out_scale = out_scale; p.out = out;
   int rc = 0;
   const int Cin = C0 + (x1 ? C1 : 0);
   if (engine == 0) {
-    void *t0 = nullptr, *t1 = nullptr;
-    // one operand split for the whole launch: the 32-channel mode only if every segment allows it (and never fused)
-    const int mp = (!skip_out && C0 % 32 == 0 && (!x1 || C1 % 32 == 0) && (!w2 || C2 % 32 == 0)) ? 1 : 0;
-    rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st, mp);
-    if (rc == 0 && w2) rc = tc_pack_weights(w2, Cout, skip_out ? Cin : C2, 1, &t1, &owned, st, mp);
-    p.seg[0].wtc = t0; p.seg[1].wtc = t1;
-    if (skip_out) {      // fused: skip over x2 (separate raw source, single tensor) or over the main sources when x2 == null
-      p.skip_wtc = t1; p.skip_src0 = x2; p.skip_src1 = nullptr; p.skip_bias = nullptr; p.skip_out = skip_out;
-      p.seg[1] = ConvSeg{};
-    }
+    TcWeights t0, t1;
+    // one operand split and one weight scale for the whole launch: the 32-channel mode only if every segment allows it
+    const int mp = (max_prec >= 1 && C0 % 32 == 0 && (!x1 || C1 % 32 == 0) && (!w2 || C2 % 32 == 0)) ? 1 : 0;
+    float a0 = 0.f, a1 = 0.f;
+    rc = tc_weight_absmax(w, (size_t)Cout * Cin * taps, &a0, st);
+    if (rc == 0 && w2) rc = tc_weight_absmax(w2, (size_t)Cout * C2, &a1, st);
+    const float amax = std::max(a0, a1);
+    if (rc == 0) rc = tc_pack_weights(w, Cout, Cin, taps, &t0, &owned, st, mp, amax);
+    if (rc == 0 && w2) rc = tc_pack_weights(w2, Cout, C2, 1, &t1, &owned, st, mp, amax);
+    set_wtc(p.seg[0], t0);
+    if (x2) set_wtc(p.seg[1], t1);
     if (rc == 0 && !conv_tc_eligible(p)) rc = fail(STORM_E_INVALID, "storm_debug_conv: shape not eligible for the tcgen05 kernel");
     if (rc == 0) rc = launch_conv_tc(p, st);
     if (rc == 0 && ms_out) {     // timed repeat (warm weights), optionally with the CTA-0 cycle counters
@@ -1240,6 +1293,7 @@ int storm_stft(const float* wav, const float* norm, int32_t B, int32_t L, float*
 int storm_istft_ragged(StormHandle* h, const float* spec, const float* norm, int32_t B, int32_t T_pad, float* wav, int32_t L,
                        const int32_t* lengths, const StormSpecConfig* sp, void* stream) {
   if (!h || !spec || !wav || !sp) return fail(STORM_E_INVALID, "storm_istft: null argument");
+  DeviceGuard dg(h);
   void* p;
   STORM_TRY(h->pool.get((size_t)B * T_pad * sp->n_fft * sizeof(float), &p));
   int rc = launch_istft(spec, norm, B, T_pad, (float*)p, wav, L, lengths, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
@@ -1263,6 +1317,7 @@ int storm_enhance_ragged(StormHandle* h, const float* wav_in, float* wav_out, in
                          const StormSamplerConfig* sc, const StormSpecConfig* sp, uint64_t seed, const uint64_t* utt_ids,
                          int32_t* nfe_out, void* stream) {
   if (!h || !wav_in || !wav_out || !sp) return fail(STORM_E_INVALID, "storm_enhance: null argument");
+  DeviceGuard dg(h);
   STORM_TRY(check_sampler(sc));
   cudaStream_t st = (cudaStream_t)stream;
   const int F = sp->n_fft / 2 + 1;

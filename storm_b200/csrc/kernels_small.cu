@@ -506,34 +506,37 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
   return 0;
 }
 
-__global__ void fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C) {
+// C input channels -> CO >= C output channels (channels beyond C are written as zeros: K padding of the tensor-core kernel)
+__global__ void fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C, int CO) {
   const int OH = H / 2, OW = W / 2;
-  const size_t total = (size_t)B * OH * OW * C;
+  const size_t total = (size_t)B * OH * OW * CO;
   const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % C;
-    size_t r = i / C;
+    const int c = i % CO;
+    size_t r = i / CO;
     const int ox = r % OW; r /= OW;
     const int oy = r % OH;
     const int b = r / OH;
     float acc = 0.f;
-    for (int jy = 0; jy < 4; ++jy) {
-      int y = 2 * oy - 1 + jy;
-      if ((unsigned)y >= (unsigned)H) continue;
-      for (int jx = 0; jx < 4; ++jx) {
-        int xx = 2 * ox - 1 + jx;
-        if ((unsigned)xx >= (unsigned)W) continue;
-        acc = fmaf(k[jy] * k[jx], __ldg(x + (((size_t)b * H + y) * W + xx) * C + c), acc);
+    if (c < C) {
+      for (int jy = 0; jy < 4; ++jy) {
+        int y = 2 * oy - 1 + jy;
+        if ((unsigned)y >= (unsigned)H) continue;
+        for (int jx = 0; jx < 4; ++jx) {
+          int xx = 2 * ox - 1 + jx;
+          if ((unsigned)xx >= (unsigned)W) continue;
+          acc = fmaf(k[jy] * k[jx], __ldg(x + (((size_t)b * H + y) * W + xx) * C + c), acc);
+        }
       }
     }
     out[i] = acc;
   }
 }
-int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, cudaStream_t st) {
-  size_t total = (size_t)B * (H / 2) * (W / 2) * C;
+int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, int CO, cudaStream_t st) {
+  size_t total = (size_t)B * (H / 2) * (W / 2) * CO;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   if (blocks == 0) blocks = 1;
-  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C);
+  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C, CO);
   STORM_LAUNCH_CHECK();
   return 0;
 }

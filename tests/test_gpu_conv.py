@@ -87,26 +87,63 @@ def test_attention_core(engine, B, N, C):
     assert torch.isfinite(out).all() and err < 2e-5
 
 
-@pytest.mark.parametrize("B,H,W,C0,C1,Cout,sep", [(2, 40, 24, 128, 0, 128, False), (1, 32, 32, 256, 128, 256, False),
-                                                    (2, 16, 16, 128, 0, 128, True), (1, 64, 16, 256, 0, 256, True),
-                                                    (1, 24, 8, 96, 96, 192, False)])
-def test_fused_skip_conv(B, H, W, C0, C1, Cout, sep):
-    """conv3x3(act(cat[x0,x1])) and conv1x1(raw) from ONE launch (ResnetBlock Conv_0 + Conv_2)."""
+@pytest.mark.parametrize("max_prec", [1, 0])
+@pytest.mark.parametrize("act_scale", [1e-3, 1.0, 1e2, 1e4])
+@pytest.mark.parametrize("w_scale", [1e-3, 1.0, 30.0])
+def test_dynamic_range_sweep(max_prec, act_scale, w_scale):
+    """The tensor-core operand splits must not depend on the scale of the data: RAW (un-normalised) activations x 1e-3..1e4
+    and weights x 1e-3..30 on a 3x3 segment plus a raw 1x1 skip segment (ResnetBlock Conv_1 + Conv_2), against fp64.
+    Round 1's fixed power-of-two scalings of the fp8 correction planes lost them below |x| ~ 0.06 / |w| ~ 1e-3 (6e-4)."""
+    from storm_b200 import _native
+    B, H, W, C0, C2, Cout = 2, 32, 24, 128, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)   # noqa: E731
+    x0 = rn(B, H, W, C0) * act_scale
+    x2 = rn(B, H, W, C2) * act_scale
+    w = rn(Cout, C0, 3, 3) / (C0 * 9) ** 0.5 * w_scale
+    w2 = rn(Cout, C2, 1, 1) / C2 ** 0.5 * w_scale
+    bias = 0.1 * rn(Cout) * act_scale * w_scale
+    kw = dict(x2=x2, w2=w2, bias=bias, out_scale=0.70710678)
+    ref = _ref(x0, w, **kw)
+    out = _native.debug_conv(0, x0, w, max_prec=max_prec, **kw)
+    err = _rel(out, ref)
+    print(f"sweep prec={max_prec} act x{act_scale:g} w x{w_scale:g}: rel-L2={err:.3e}")
+    assert torch.isfinite(out).all() and err < (4e-5 if max_prec else 1e-5)
+
+
+def test_split_saturates_instead_of_overflowing():
+    """Activations beyond fp16's range (65504) must saturate in the f16 + 2 x fp8 split, not turn into inf / NaN."""
+    from storm_b200 import _native
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x0 = torch.randn(1, 16, 16, 64, device="cuda", generator=g)
+    x0[0, 3, 5, 7] = 3.0e5
+    x0[0, 9, 2, 40] = -1.0e6
+    w = torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24.0
+    out = _native.debug_conv(0, x0, w, max_prec=1)
+    assert torch.isfinite(out).all()
+    ref = _ref(x0.clamp(-65504, 65504), w)
+    assert _rel(out, ref) < 1e-3       # the two saturated inputs lose their correction terms, nothing else changes
+    exact = _native.debug_conv(0, x0, w, max_prec=0)      # bf16 x 3 keeps fp32's range
+    assert _rel(exact, _ref(x0, w)) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,C0,Cout,max_prec", [(2, 32, 16, 128, 128, 1), (1, 64, 64, 256, 256, 1), (2, 16, 24, 64, 192, 1),
+                                                       (1, 32, 32, 96, 96, 0), (3, 8, 8, 32, 32, 1)])
+def test_half_resolution_residual(B, H, W, C0, Cout, max_prec):
+    """Conv_1 of an up block: out = (conv3x3(act(h1)) + b + FIR_up(S)) / sqrt(2) with S given at half resolution (the
+    1x1 skip commutes with the FIR upsampling, layerspp.py:250-252,268-269)."""
+    from oracle import storm_oracle as O
     from storm_b200 import _native
     g = torch.Generator(device="cuda").manual_seed(H * W + Cout)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g)   # noqa: E731
-    Cin = C0 + C1
     x0 = rn(B, H, W, C0)
-    x1 = rn(B, H, W, C1) if C1 else None
-    x2 = rn(B, H, W, Cin) if sep else None
-    w = rn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5
-    w2 = rn(Cout, Cin, 1, 1) / Cin ** 0.5
-    ss = torch.stack([1.0 + 0.3 * rn(B, Cin), 0.2 * rn(B, Cin)], dim=-1).contiguous()
+    w = rn(Cout, C0, 3, 3) / (C0 * 9) ** 0.5
+    ss = torch.stack([1.0 + 0.3 * rn(B, C0), 0.2 * rn(B, C0)], dim=-1).contiguous()
     bias = 0.1 * rn(Cout)
-    out, skip = _native.debug_conv_fused(x0, w, w2, x1=x1, ss=ss, silu=True, x2=x2, bias=bias)
-    ref = _ref(x0, w, x1=x1, ss=ss, silu=True, bias=bias)
-    raw = x2 if sep else (x0 if x1 is None else torch.cat([x0, x1], dim=-1))
-    ref_skip = F.conv2d(raw.double().permute(0, 3, 1, 2), w2.double()).permute(0, 2, 3, 1).float()
-    e1, e2 = _rel(out, ref), _rel(skip, ref_skip)
-    print(f"fused skip {B,H,W,C0,C1,Cout,sep}: main {e1:.3e} skip {e2:.3e}")
-    assert e1 < 2e-5 and e2 < 2e-5
+    S = rn(B, H // 2, W // 2, Cout)
+    up = O.fir_upsample(S.double().permute(0, 3, 1, 2).cpu()).permute(0, 2, 3, 1).cuda()      # reference closed form, fp64
+    ref = _ref(x0, w, ss=ss, silu=True, bias=bias, res=up, out_scale=0.70710678)
+    out = _native.debug_conv(0, x0, w, ss=ss, silu=True, bias=bias, res_up=S, out_scale=0.70710678, max_prec=max_prec)
+    err = _rel(out, ref)
+    print(f"res_up {B, H, W, C0, Cout} prec={max_prec}: rel-L2={err:.3e}")
+    assert err < (4e-5 if max_prec else 1e-5)

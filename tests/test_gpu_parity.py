@@ -299,6 +299,76 @@ def test_trajectory_vs_oracle_and_sampler_sweep():
         assert nfe == nfeo and err < TOL
 
 
+@pytest.mark.parametrize("name,L,T_pad", [("ncsnpplarge", 128000, 1024), ("ncsnpp", 64000, 512)])
+def test_large_shapes_single_nfe_vs_oracle(name, L, T_pad):
+    """BASELINE configs[3] shape (8 s -> 256x1024, ncsnpplarge) and the literal-4 s row (64000 samples -> 501 frames ->
+    256x512, ncsnpp: 2048 attention tokens): one network evaluation against the CPU oracle."""
+    from storm_b200 import ncsnpp_spec
+    m = _model(name)
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=1, init_scale=1.0, bias_std=0.05)
+    m.load_state_dict(sd)
+    _, _, Y = _synth_Y(1, L)
+    assert tuple(Y.shape) == (1, 1, 256, T_pad)
+    t = torch.tensor([0.55], device="cuda")
+    x = Y + 0.2 * torch.view_as_complex(torch.randn(1, 1, 256, T_pad, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)))
+    d = m(torch.cat([x, Y], dim=1), t)
+    torch.set_num_threads(min(32, len(__import__("os").sched_getaffinity(0))))
+    do = O.ncsnpp_forward(sd, O.named_cfg(name), torch.cat([x, Y], dim=1).cpu(), t.cpu())
+    err = rel_l2(d.cpu(), do)
+    print(f"{name} 256x{T_pad} single NFE rel-L2 vs oracle = {err:.3e}")
+    assert err < TOL
+
+
+def test_headline_batch_of_8_is_batch_invariant_and_matches_oracle():
+    """The benchmarked batch (B = 8, 256x256, full-width ncsnpp): every utterance of the batch equals its own B = 1 run
+    bit for bit (tile selection, GroupNorm statistics and Philox noise must not depend on the batch), and one of them
+    matches the CPU oracle over a whole PC step."""
+    from storm_b200 import _native, ncsnpp_spec
+    m = _model("ncsnpp")
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=0, init_scale=1.0, bias_std=0.05)
+    m.load_state_dict(sd)
+    _, _, Y = _synth_Y(8, 32640)
+    assert tuple(Y.shape) == (8, 1, 256, 256)
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 1, 1, 0.5, 0.03)
+    ids = [10, 11, 12, 13, 14, 15, 16, 17]
+    X8, nfe = m.engine().pc_sample(Y, sc, seed=21, utt_ids=ids)
+    assert nfe == 2
+    for b in (0, 3, 7):
+        X1, _ = m.engine().pc_sample(Y[b:b + 1], sc, seed=21, utt_ids=[ids[b]])
+        assert torch.equal(X1[0], X8[b]), f"utterance {b} depends on the batch"
+    b = 3
+    n = Y[0].numel()
+    it = iter([_native.philox_normal(21, ids[b], dr, n).reshape(1, 1, 256, 256).cpu() for dr in range(3)])
+    torch.set_num_threads(min(32, len(__import__("os").sched_getaffinity(0))))
+    Xo, _ = O.pc_sample(O.make_score_fn(sd, O.NetCfg()), Y[b:b + 1].cpu(), O.OUVE(), 1, noise=lambda z: next(it))
+    err = rel_l2(X8[b:b + 1].cpu(), Xo)
+    print(f"B=8 headline shape, utterance {b}, one PC step rel-L2 vs oracle = {err:.3e}")
+    assert err < TOL
+
+
+def test_random_per_layer_weight_rescale_vs_oracle():
+    """Every conv weight tensor rescaled by its own random 2^k, k in [-6, 6] (biases and GroupNorm untouched): the
+    network function changes, and so do the magnitudes every tensor-core operand split sees - weights over 12 binades, the
+    un-normalised residual stream over several.  The CUDA path must still match the oracle run on the same weights."""
+    from storm_b200 import ncsnpp_spec
+    m = _model("ncsnpp")
+    sd = ncsnpp_spec.random_state_dict(m.cfg, seed=3, init_scale=1.0, bias_std=0.05)
+    gen = torch.Generator().manual_seed(99)
+    for k, v in sd.items():
+        if k.endswith(".weight") and v.dim() == 4:      # the NIN maps feed a softmax: scaling q.k by 2^12 would test that, not the convs
+            sd[k] = v * float(2.0 ** int(torch.randint(-6, 7, (1,), generator=gen)))
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(4)
+    x = torch.complex(torch.randn(2, 2, 256, 64, generator=g), torch.randn(2, 2, 256, 64, generator=g)) * 0.4
+    t = torch.tensor([0.9, 0.2])
+    y = m(x.cuda(), t.cuda()).cpu()
+    torch.set_num_threads(min(32, len(__import__("os").sched_getaffinity(0))))
+    yo = O.ncsnpp_forward(sd, O.NetCfg(), x, t)
+    err = rel_l2(y, yo)
+    print(f"per-layer 2^[-6,6] weight rescale: rel-L2 vs oracle = {err:.3e}")
+    assert torch.isfinite(torch.view_as_real(y)).all() and err < TOL
+
+
 def test_ncsnpplarge_8s_shape_runs():
     """Config 4 shape: 128000 samples -> 1001 frames -> padded 1024; ncsnpplarge, one PC step, finite output and
     bit-exact independence from batch composition."""
