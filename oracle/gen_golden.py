@@ -342,7 +342,26 @@ def gen_metrics(ns):
     save("metrics", **arrs)
 
 
-GENS = dict(headline=gen_headline, metrics=gen_metrics, storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
+def gen_param_order(ns):
+    """``named_parameters()`` of the reference networks: name, shape (at nf=8) and requires_grad, in the order
+    ``torch_ema`` sees them (sgmse/model.py:55,102-107: ExponentialMovingAverage(self.parameters())).  Checkpoint loading
+    maps ``ema.shadow_params`` positionally onto this list, so the order and the one frozen parameter
+    (GaussianFourierProjection.W, layerspp.py:37) are pinned here."""
+    import json
+    N = ns.BackboneRegistry.get_by_name("ncsnpp")
+    out = {}
+    for tag, kw in [("ncsnpp_4ch", dict(input_channels=4)), ("ncsnpp_6ch", dict(input_channels=6)),
+                    ("ncsnpp_disc", dict(input_channels=2, discriminative=True))]:
+        m = N(nf=8, **kw)
+        assert [n for n, _ in m.named_parameters()] == list(m.state_dict().keys())
+        out[tag] = [[n, list(p.shape), bool(p.requires_grad)] for n, p in m.named_parameters()]
+    path = os.path.join(OUT, "param_order.json")
+    with open(path, "w") as f:
+        json.dump(out, f)
+    print(f"wrote {path}")
+
+
+GENS = dict(param_order=gen_param_order, headline=gen_headline, metrics=gen_metrics, storm=gen_storm, fir=gen_fir, layers=gen_layers, net_tiny=gen_net_tiny, net_large_tiny=gen_net_large_tiny,
             net_full=gen_net_full, sampler=gen_sampler, stft=gen_stft, enhance=gen_enhance)
 
 if __name__ == "__main__":

@@ -437,7 +437,7 @@ def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=Non
     out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x0.device)
     cont = lambda t: None if t is None else _cf(t, "arg")   # noqa: E731
     x1, ss, x2, w2, bias, res, res_up, w = cont(x1), cont(ss), cont(x2), cont(w2), cont(bias), cont(res), cont(res_up), cont(w)
-    dbg = torch.zeros(8, dtype=torch.int64, device=x0.device) if timed else None
+    dbg = torch.zeros(16, dtype=torch.int64, device=x0.device) if timed else None
     ms = C.c_float()
     with torch.cuda.device(x0.device):
         _check(lib().storm_debug_conv_ex(engine, x0.data_ptr(), _ptr(x1), C0, 0 if x1 is None else x1.shape[-1], _ptr(ss), int(silu),

@@ -77,8 +77,14 @@ struct ConvParams {
   float* out;              // NHWC [B][H][W][Cout]
   double* stats_out;       // optional GroupNorm partial sums of `out`: [B][stats_chunks][Cout][2] (tcgen05 mode P only)
   int stats_chunks;
-  long long* dbg;          // optional [8] cycle counters written by CTA 0 (tools/conv_timeline.py)
+  long long* dbg;          // optional [16] cycle counters written by CTA 0 (tools/conv_timeline.py)
   int out_cm;              // 1: write `out` channel-major [B][Cout][H*W] (tcgen05 kernel only; attention V operand)
+  // Magnitude of the RAW (un-normalised) operands of this launch: [B][raw_ms_n] mean squares (gn_finalize writes them for
+  // the GroupNorm groups of the same tensor).  The f16-based operand split of the tcgen05 kernel scales every operand of
+  // sample b by one power of two alpha_b <= 1 chosen from max_g raw_ms[b][g], so that a residual stream beyond fp16's
+  // range (65504) does not saturate; the epilogue multiplies by 1 / alpha_b.  null: alpha = 1.
+  const float* raw_ms;
+  int raw_ms_n;
 };
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);

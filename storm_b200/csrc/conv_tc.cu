@@ -345,7 +345,6 @@ struct TcpCfg {
   int prec;            // 0: bf16 x 3, 16-channel K chunks (planes hi, lo); 1: f16 + 2 x fp8, 32-channel K chunks
                        //    (activation planes f16[0-15], f16[16-31], e5m2(h), e5m2(l); weight planes f16, f16, e4m3, e4m3), see split_f16f8
   int w_plane;         // bytes of one weight plane of a stage (prec 1)
-  int pf_depth;        // how many K chunks ahead of the one being staged the producers prefetch into L2
   float acc_scale;     // 1 / (scale carried by the packed weights): multiplies the accumulators in the epilogue
 };
 
@@ -497,6 +496,21 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp < NPW) {
+    // ---- per-sample operand scale alpha = 2^-e <= 1 (ConvParams::raw_ms): rms of the largest raw group brought down to <= 2^9,
+    // which leaves fp16 (max 2^16) a factor 128 for peaks; alpha = 1 (no extra instruction below) up to rms 512
+    float alpha = 1.0f, inv_alpha = 1.0f;
+    if (p.raw_ms) {
+      float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (m > 262144.0f && m < 3.0e38f) {                      // rms > 2^9
+        const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;        // m = f 2^ex, f in [0.5, 1)
+        int e = (ex + 1) / 2 - 9;                              // ceil(log2(rms)) - 9
+        e = e < 0 ? 0 : (e > 60 ? 60 : e);
+        alpha = __uint_as_float((uint32_t)(127 - e) << 23);
+        inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
+      }
+    }
     // =================================== activation producers ==========================================
     // Each thread owns up to 3 halo pixels per stage and handles all 16 channels (64 contiguous bytes) of each.
     // All global loads of a stage are issued before any is consumed (memory-level parallelism), and the next
@@ -539,26 +553,10 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     // prec 1: the 8 channels of one pixel -> fp16 k-core of the half's plane; the fp8 bytes of both 8-channel groups of a
     // unit are stored together (16 bytes per pixel and fp8 plane k-core)
     constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
-    auto prefetch_chunk = [&](int nsi, int nch) {
-      const ConvSeg& ns = p.seg[nsi];
-      const int n0c = nch * (16 * NH);
-      const float* nsrc;
-      int nCs, ncl;
-      if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
-      const bool nfull = ns.taps == 9;
-#pragma unroll
-      for (int i = 0; i < MAXU; ++i)
-        if (upix[i] >= 0 && (nfull || uinterior[i]))
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
-    };
-    ChunkIter it(p, PREC), pf_it(p, PREC);
+    ChunkIter it(p, PREC);
     int si, chk;
-    {   // chunk 0 is loaded directly; chunks 1 .. pf_depth - 1 are prefetched now, chunk i + pf_depth while chunk i is staged
-      int nsi, nch;
-      pf_it.next(nsi, nch);
-      for (int d = 1; d < c.pf_depth; ++d)
-        if (pf_it.next(nsi, nch)) prefetch_chunk(nsi, nch);
-    }
+    const bool pdbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    long long t_ld[2] = {0, 0}, t_empty = 0, t_cv[2] = {0, 0};     // [segment]: cycles waiting for loads / converting + storing
     while (it.next(si, chk)) {
       const ConvSeg& s = p.seg[si];
       const int C = s.C0 + s.C1;
@@ -570,6 +568,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
         int Cs, cl;
         if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
         // ---- issue all loads of this stage
+        const long long t_a = pdbg ? clock64() : 0;
         float4 raw[MAXU][4];
 #pragma unroll
         for (int i = 0; i < MAXU; ++i) {
@@ -579,12 +578,23 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
           }
         }
-        // ---- L2 prefetch, pf_depth chunks ahead in schedule order (once per stage; a 32-channel chunk is one 128-byte
-        // line per pixel).  The 1x1 skip chunks need a whole tile of fresh HBM lines per ~1k cycles of tensor work, several
-        // times what HBM delivers; looking further ahead than one chunk lets the long 3x3 chunks pay for them.
+        // ---- L2 prefetch of the next chunk in schedule order (once per stage; a 32-channel chunk is one 128-byte line per
+        // pixel).  Looking further ahead (2, 4, 8 chunks) was measured and changes nothing: profiles/r2_bench_history.md.
         if (hsel == 0) {
+          ChunkIter peek = it;
           int nsi, nch;
-          if (pf_it.next(nsi, nch)) prefetch_chunk(nsi, nch);
+          if (peek.next(nsi, nch)) {
+            const ConvSeg& ns = p.seg[nsi];
+            const int n0c = nch * (16 * NH);
+            const float* nsrc;
+            int nCs, ncl;
+            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+            const bool nfull = ns.taps == 9;
+#pragma unroll
+            for (int i = 0; i < MAXU; ++i)
+              if (upix[i] >= 0 && (nfull || uinterior[i]))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
+          }
         }
         float sc[16], sh[16];
         if (s.ss) {
@@ -595,7 +605,18 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
           }
         }
+        const long long t_b = pdbg ? clock64() : 0;
         if (hsel == 0) mbar_wait_relaxed(a_empty(stage), phase ^ 1);
+        long long t_c = 0;
+        if (pdbg) {
+          t_c = clock64();
+          t_empty += t_c - t_b;
+          float probe = raw[0][3].w;                                  // last load of the first pixel: wait for it to land
+          if (upix[0] >= 0 && (full_halo || uinterior[0])) asm volatile("mov.f32 %0, %0;" : "+f"(probe));
+          const long long t_d = clock64();
+          t_ld[si] += t_d - t_c;
+          t_c = t_d;
+        }
         const uint32_t st_base = a_base + stage * c.a_stage;
 #pragma unroll
         for (int i = 0; i < MAXU; ++i) {
@@ -616,6 +637,10 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
               }
+              if (alpha != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= alpha;
+              }
             }
             if constexpr (PREC == 1) {
               uint4 h16 = make_uint4(0, 0, 0, 0);
@@ -633,6 +658,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
             st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
           }
         }
+        if (pdbg) t_cv[si] += clock64() - t_c;
         if (hsel == NH - 1) {
           fence_async_shared();
           mbar_arrive(a_full(stage));
@@ -642,8 +668,9 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     }
     // =================================== epilogue (every producer warp) ==================================
     {
-    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    const bool dbg = pdbg;
     const long long t_e0 = dbg ? clock64() : 0;
+    if (dbg) { p.dbg[6] = t_ld[0]; p.dbg[7] = t_ld[1]; p.dbg[8] = t_empty; p.dbg[9] = t_cv[0]; p.dbg[10] = t_cv[1]; }
     constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
     const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
     const int nacc = c.npt * c.nmb;
@@ -672,7 +699,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     const long long t_e1 = dbg ? clock64() : 0;
     tc_fence_after();
     const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
-    const float asc = c.acc_scale;
+    const float asc = c.acc_scale * inv_alpha;
     double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
     for (int u = grp; u < nunits; u += NGRP) {
       const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
@@ -876,9 +903,6 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   if (p.res_up && ((p.H | p.W) & 1)) return false;
   static const int env_per_sm = [] { const char* e = getenv("STORM_B200_TC_PER_SM"); return e ? atoi(e) : -1; }();
   if (env_per_sm >= 0) g_tc_force_per_sm = env_per_sm;
-  // K chunks the producers prefetch ahead (L2): 1 = round 1's behaviour
-  static const int env_pf = [] { const char* e = getenv("STORM_B200_PF_DEPTH"); return e ? atoi(e) : 0; }();
-  c.pf_depth = env_pf > 0 ? env_pf : (p.nseg == 2 ? 4 : 2);
   const int nblk = tc_mpad(p.Cout) / 128;
   // candidates (rows, pixel tiles, M blocks per CTA, CTAs per SM), preferred first; take the first that fills the
   // chip, else the one with the most CTAs.  256-column tiles run two CTAs per SM (epilogue/main-loop overlap).

@@ -445,13 +445,17 @@ struct Fwd {
     a.part_valid = true;
     return 0;
   }
-  int gn_ss(Act& a0, Act* a1, const float* g, const float* b, float** ss) {
+  // ss: [B][C][2] scale/shift, followed by [B][gn_groups(C)] mean squares of the raw groups (*ms, optional)
+  int gn_ss(Act& a0, Act* a1, const float* g, const float* b, float** ss, const float** ms = nullptr) {
     STORM_TRY(stats(a0));
     if (a1) STORM_TRY(stats(*a1));
     void* p;
-    STORM_TRY(h->pool.get((size_t)B * (a0.C + (a1 ? a1->C : 0)) * 2 * sizeof(float), &p));
+    const int C = a0.C + (a1 ? a1->C : 0);
+    STORM_TRY(h->pool.get(((size_t)B * C * 2 + (size_t)B * 32) * sizeof(float), &p));
     *ss = (float*)p;
-    LAUNCH(h, launch_gn_finalize(a0, a1, g, b, *ss, st));
+    float* m = *ss + (size_t)B * C * 2;
+    if (ms) *ms = m;
+    LAUNCH(h, launch_gn_finalize(a0, a1, g, b, *ss, m, st));
     return 0;
   }
   int conv(ConvParams& p, Act* out_act = nullptr) {
@@ -509,7 +513,9 @@ struct Fwd {
     const int Cin = x0.C + (x1 ? x1->C : 0);
     if (Cin != m.in_ch) return fail(STORM_E_STATE, "res_block: channel mismatch");
     float* ss0 = nullptr;
-    STORM_TRY(gn_ss(x0, x1, r.gn0_g, r.gn0_b, &ss0));
+    const float* ms0 = nullptr;       // magnitude of the raw block input (for the launches that consume it un-normalised)
+    STORM_TRY(gn_ss(x0, x1, r.gn0_g, r.gn0_b, &ss0, &ms0));
+    const int ms0_n = gn_groups(Cin);
     Act hr, xr;       // FIR-resampled activated / raw inputs (up/down blocks)
     const bool resamp = m.up || m.down;
     int H = x0.H, W = x0.W;
@@ -543,6 +549,7 @@ struct Fwd {
         k.src0 = x0.p; k.C0 = Cin; k.src1 = nullptr; k.C1 = 0; k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2;
         set_wtc(k, r.tc2);
         ps.B = B; ps.H = x0.H; ps.W = x0.W; ps.Cout = m.out_ch; ps.out_scale = 1.0f;
+        ps.raw_ms = ms0; ps.raw_ms_n = ms0_n;
         ConvParams probe = p1;
         probe.seg[0].src0 = x0.p;                 // any non-null pointer: eligibility does not look at the data
         probe.res_up = x0.p;
@@ -571,7 +578,6 @@ struct Fwd {
       p.res = nullptr; p.out_scale = 1.0f; p.out = h1.p;
       STORM_TRY(conv(p, &h1));
     }
-    h->pool.put(ss0);
     if (resamp) release(hr);
     if (lowres_skip) {
       STORM_TRY(alloc(skipL, x0.H, x0.W, m.out_ch));
@@ -593,6 +599,7 @@ struct Fwd {
         else { k.src0 = x0.p; k.C0 = x0.C; k.src1 = x1 ? x1->p : nullptr; k.C1 = x1 ? x1->C : 0; }
         k.ss = nullptr; k.silu = 0; k.taps = 1; k.w = r.w2;
         set_wtc(k, r.tc2);
+        p.raw_ms = ms0; p.raw_ms_n = ms0_n;      // FIR_down(x) (down blocks) is bounded by x
         if (pyr_fuse) {      // Combine folded in: the padded pyramid rides along as 32 more K channels of the skip segment
           k.src1 = pyr_fuse->p; k.C1 = pyr_fuse->C; k.w = nullptr;
           set_wtc(k, r.tc2c);
@@ -607,6 +614,7 @@ struct Fwd {
       STORM_TRY(conv(p, &out));
     }
     h->pool.put(ss1);
+    h->pool.put(ss0);
     release(h1);
     if (lowres_skip) release(skipL);
     if (resamp && !lowres_skip) release(xr);

@@ -22,8 +22,10 @@ int launch_dense_all(const float* act, const float* Wt, const float* bias, float
 // ---- GroupNorm statistics (nn.GroupNorm eps=1e-6, groups=min(C/4,32): layerspp.py:219,231,67) ------------
 int gn_num_chunks(int HW);
 int launch_gn_partial(const Act& a, cudaStream_t st);   // fills a.part
-// scale/shift [B][C0+C1][2] from the partials of one or two (concatenated) tensors
-int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const float* beta, float* ss, cudaStream_t st);
+// scale/shift [B][C0+C1][2] from the partials of one or two (concatenated) tensors; ms (optional, [B][G], G = gn_groups(C))
+// receives the mean square of every RAW group (what the tensor-core kernel scales un-normalised operands by)
+int gn_groups(int C);
+int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const float* beta, float* ss, float* ms, cudaStream_t st);
 
 // ---- FIR resampling, taps [1,3,3,1] (up_or_down_sampling.py:195-257) ------------------------------------
 // h_out = FIR(SiLU(x*scale+shift)) (if ss) and x_out = FIR(x); mode: 1 = up x2, 2 = down x2.  C % 4 == 0.

@@ -271,7 +271,7 @@ int launch_gn_partial(const Act& a, cudaStream_t st) {
 __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restrict__ part0, int C0, int nchunk0,
                                                           const double* __restrict__ part1, int C1, int nchunk1,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ ss, int HW, int G) {
+                                                          float* __restrict__ ss, float* __restrict__ ms, int HW, int G) {
   const int g = blockIdx.x, b = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / G;
@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
     if (var < 0) var = 0;
     rs[0] = mean;
     rq[0] = 1.0 / sqrt(var + 1e-6);
+    if (ms) ms[(size_t)b * G + g] = (float)(Q / n);      // mean square of the RAW group: magnitude of the un-normalised tensor
   }
   __syncthreads();
   const double mean = rs[0], rstd = rq[0];
@@ -321,12 +322,13 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
     o[1] = (float)((double)beta[cc] - mean * sc);
   }
 }
-int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const float* beta, float* ss, cudaStream_t st) {
+int gn_groups(int C) { return C / 4 < 32 ? C / 4 : 32; }     // nn.GroupNorm(num_groups=min(C // 4, 32)), layerspp.py:219
+int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const float* beta, float* ss, float* ms, cudaStream_t st) {
   const int C = a0.C + (a1 ? a1->C : 0);
-  int G = C / 4 < 32 ? C / 4 : 32;
+  const int G = gn_groups(C);
   if (G < 1 || C % G != 0) return fail(-1, "gn_finalize: channels not divisible into groups");
   gn_finalize_kernel<<<dim3(G, a0.B), 128, 0, st>>>(a0.part, a0.C, a0.nchunk, a1 ? a1->part : nullptr, a1 ? a1->C : 0,
-                                                     a1 ? a1->nchunk : 0, gamma, beta, ss, a0.H * a0.W, G);
+                                                     a1 ? a1->nchunk : 0, gamma, beta, ss, ms, a0.H * a0.W, G);
   STORM_LAUNCH_CHECK();
   return 0;
 }

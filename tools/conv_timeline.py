@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from storm_b200 import _native  # noqa: E402
 
 B = 8
-SHAPES = [  # name, H, W, C0, C1, Cout, prologue(ss+silu), skip C2, res
+SHAPES = [  # name, H, W, C0, C1, Cout, prologue(ss+silu), skip C2, res (True | "up" = half-resolution residual)
     ("b31.conv0 up 256->256 @256", 256, 256, 256, 0, 256, False, 0, False),
     ("b31.conv1 256->256 +skip256 @256", 256, 256, 256, 0, 256, True, 256, False),
     ("b32.conv0 384->128 @256", 256, 256, 256, 128, 128, True, 0, False),
@@ -18,6 +18,10 @@ SHAPES = [  # name, H, W, C0, C1, Cout, prologue(ss+silu), skip C2, res
     ("b27.conv0 512->256 @128", 128, 128, 256, 256, 256, True, 0, False),
     ("b22.conv0 512->256 @64", 64, 64, 256, 256, 256, True, 0, False),
     ("b13.conv0 256->256 @32", 32, 32, 256, 0, 256, True, 0, False),
+    ("b17.conv1 256->256 +skip512 @32", 32, 32, 256, 0, 256, True, 512, False),
+    ("b33.conv1 128->128 +skip256 @256", 256, 256, 128, 0, 128, True, 256, False),
+    ("b27.conv1 256->256 +skip512 @128", 128, 128, 256, 0, 256, True, 512, False),
+    ("b31.conv1 256->256 +res_up @256", 256, 256, 256, 0, 256, True, 0, "up"),
 ]
 g = torch.Generator(device="cuda").manual_seed(0)
 rn = lambda *s: torch.randn(*s, device="cuda", generator=g)   # noqa: E731
@@ -29,9 +33,10 @@ for name, H, W, C0, C1, Cout, pro, C2, use_res in SHAPES:
     ss = torch.stack([1.0 + 0.3 * rn(B, Cin), 0.2 * rn(B, Cin)], dim=-1).contiguous() if pro else None
     x2 = rn(B, H, W, C2) if C2 else None
     w2 = rn(Cout, C2, 1, 1) / C2 ** 0.5 if C2 else None
-    res = rn(B, H, W, Cout) if use_res else None
-    out, ms, d = _native.debug_conv(0, x0, w, x1=x1, ss=ss, silu=pro, x2=x2, w2=w2, bias=None, res=res, timed=True)
+    res = rn(B, H, W, Cout) if use_res is True else None
+    res_up = rn(B, H // 2, W // 2, Cout) if use_res == "up" else None
+    out, ms, d = _native.debug_conv(0, x0, w, x1=x1, ss=ss, silu=pro, x2=x2, w2=w2, bias=None, res=res, res_up=res_up, timed=True)
     macs = B * H * W * Cout * (9 * Cin + C2)
     tf = 2 * macs / (ms * 1e-3) / 1e12
-    print(f"{name:36s} {ms * 1e3:8.1f} us  {tf:6.1f} TFLOP/s alg ({3 * tf:6.1f} issued)  cta0: issue {d[0]} wait_act {d[1]} wait_w {d[2]} "
-          f"retire {d[3]} prod_idle {d[4]} epi {d[5]}")
+    print(f"{name:36s} {ms * 1e3:8.1f} us  {tf:6.1f} TFLOP/s alg  cta0: issue {d[0]} wait_act {d[1]} wait_w {d[2]} "
+          f"retire {d[3]} prod_idle {d[4]} epi {d[5]} | producer t0: ld_wait seg0 {d[6]} seg1 {d[7]} empty_wait {d[8]} convert seg0 {d[9]} seg1 {d[10]}")
