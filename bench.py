@@ -27,20 +27,40 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(backbone="ncsnpp", B_per_gpu=8, L=32640, F=256, T=256, N=30, corrector="ald", corrector_steps=1,
-                predictor="reverse_diffusion", snr=0.5)
-GFLOP_PER_UTT_NFE = 624.8       # algorithmic conv/NIN/attention FLOPs, 256x256, ncsnpp
-GB_PER_UTT_NFE = 0.879
+# Workloads = BASELINE.json `configs` (SURVEY.md section 8d restates them).  The default line is configs[1]; the others are
+# selected with --config and are what BASELINE.md section 4 quotes.  gflop / gb: algorithmic work per utterance per network
+# evaluation.
+WORKLOADS = {
+    "headline": dict(tag="BASELINE configs[1]", backbone="ncsnpp", B_per_gpu=8, L=32640, F=256, T=256, N=30, corrector="ald",
+                     corrector_steps=1, predictor="reverse_diffusion", snr=0.5, gflop=624.8, gb=0.879, params="27.8M"),
+    "4s": dict(tag="literal 4 s row of SURVEY 8(d)", backbone="ncsnpp", B_per_gpu=8, L=64000, F=256, T=512, N=30, corrector="ald",
+               corrector_steps=1, predictor="reverse_diffusion", snr=0.5, gflop=1251.8, gb=1.648, params="27.8M"),
+    "large8s": dict(tag="BASELINE configs[3]", backbone="ncsnpplarge", B_per_gpu=32, L=128000, F=256, T=1024, N=50, corrector="ald",
+                    corrector_steps=1, predictor="reverse_diffusion", snr=0.5, gflop=2131.0, gb=3.721, params="65.6M"),
+    "sweep": dict(tag="BASELINE configs[4]", backbone="ncsnpp", B_per_gpu=16, L=32640, F=256, T=256, N=30, corrector="ald",
+                  corrector_steps=1, predictor="reverse_diffusion", snr=0.5, gflop=624.8, gb=0.879, params="27.8M"),
+    "storm": dict(tag="StoRM mode (SURVEY 8(f)-1)", backbone="ncsnpp", B_per_gpu=8, L=32640, F=256, T=256, N=30, corrector="none",
+                  corrector_steps=1, predictor="reverse_diffusion", snr=0.5, gflop=624.8, gb=0.879, params="2 x 27.8M"),
+}
+WORKLOAD = WORKLOADS["headline"]
+GFLOP_PER_UTT_NFE = WORKLOAD["gflop"]
+GB_PER_UTT_NFE = WORKLOAD["gb"]
 
 
-def workload_config(world: int, nfe: int = 60) -> dict:
+def nfe_of(W) -> int:
+    return W["N"] * ((W["corrector_steps"] if W["corrector"] != "none" else 0) + 1)
+
+
+def workload_config(world: int, name: str = "headline", nfe: int = None) -> dict:
     """Same `config` object in both arms (native / --impl reference)."""
-    W = WORKLOAD
-    return dict(workload="BASELINE configs[1]: ncsnpp 27.8M, B=8/GPU, 32640 samples -> 256x256 complex STFT, N=30 PC "
-                         "(reverse_diffusion+ald x1, 60 NFE), random-init weights init_scale=1.0",
+    W = WORKLOADS[name]
+    nfe = nfe_of(W) if nfe is None else nfe
+    return dict(workload=f"{W['tag']}: {W['backbone']} {W['params']}, B={W['B_per_gpu']}/GPU, {W['L']} samples -> {W['F']}x{W['T']} complex "
+                         f"STFT, N={W['N']} PC ({W['predictor']}+{W['corrector']}x{W['corrector_steps']}, {nfe} NFE), random-init weights "
+                         "init_scale=1.0", name=name,
                 global_batch=world * W["B_per_gpu"], parallelism=f"dp{world} (utterance sharding, one NCCL weight broadcast)",
-                l2="working set per step (activations ~3 GB) >> 126 MB L2; no explicit flush", nfe=nfe,
-                tflop_per_step=world * W["B_per_gpu"] * nfe * GFLOP_PER_UTT_NFE / 1e3)
+                l2="working set per step (activations >= 3 GB) >> 126 MB L2; no explicit flush", nfe=nfe,
+                tflop_per_step=world * W["B_per_gpu"] * nfe * W["gflop"] / 1e3)
 
 
 def peaks():
@@ -126,20 +146,23 @@ def synth_batch(B, L, first_id):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(threads, nfe_target, F=256, T=256, pc_steps=1):
-    """utterances/sec of the reference algorithm (oracle port) on the host: time `pc_steps` PC steps of one
-    256x256 utterance and scale linearly in NFE (all steps have identical shapes)."""
+def cpu_oracle_rate(threads, nfe_target, W=None, pc_steps=1):
+    """utterances/sec of the reference algorithm (oracle port) on the host: time `pc_steps` PC steps of ONE utterance of the
+    workload's shape and scale linearly in NFE (every step has identical shapes)."""
     import torch
     from oracle import storm_oracle as O
     from storm_b200 import ncsnpp_spec
+    W = W or WORKLOAD
     torch.set_num_threads(threads)
-    sd = ncsnpp_spec.random_state_dict(ncsnpp_spec.NCSNppConfig(), seed=0, init_scale=1.0)
+    ocfg = O.named_cfg(W["backbone"])
+    cfg = ncsnpp_spec.NCSNppConfig(nf=ocfg.nf, ch_mult=ocfg.ch_mult, num_res_blocks=ocfg.num_res_blocks, attn_resolutions=ocfg.attn_resolutions)
+    sd = ncsnpp_spec.random_state_dict(cfg, seed=0, init_scale=1.0)
     gen = torch.Generator().manual_seed(0)
-    Y = torch.complex(torch.randn(1, 1, F, T, generator=gen), torch.randn(1, 1, F, T, generator=gen)) * 0.3
-    score = O.make_score_fn(sd, O.NetCfg())
+    Y = torch.complex(torch.randn(1, 1, W["F"], W["T"], generator=gen), torch.randn(1, 1, W["F"], W["T"], generator=gen)) * 0.3
+    score = O.make_score_fn(sd, ocfg)
     with torch.no_grad():
         t0 = time.perf_counter()
-        _, nfe = O.pc_sample(score, Y, O.OUVE(), pc_steps, snr=WORKLOAD["snr"])
+        _, nfe = O.pc_sample(score, Y, O.OUVE(), pc_steps, snr=W["snr"])
         dt = time.perf_counter() - t0
     per_nfe = dt / nfe
     return 1.0 / (per_nfe * nfe_target), dt, nfe
@@ -151,29 +174,42 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    W = WORKLOADS[args.config]
     threads = pick_cpu_threads()
-    nfe_target = WORKLOAD["N"] * 2
+    nfe_target = nfe_of(W)
     rates = []
     for i in range(args.warmup + args.steps):
-        r, dt, nfe = cpu_oracle_rate(threads, nfe_target)
+        r, dt, nfe = cpu_oracle_rate(threads, nfe_target, W)
         if i >= args.warmup:
             rates.append((r, dt))
     value = sum(r for r, _ in rates) / len(rates)
-    sample = f"B=1, 256x256, 1 PC step (2 NFE) per bench step, utt/s extrapolated linearly in NFE to N=30 (60 NFE)"
+    sample = (f"B=1, {W['F']}x{W['T']}, 1 PC step (2 NFE) per bench step, utt/s extrapolated linearly in NFE to {nfe_target} NFE; the CPU arm "
+              "runs ONE utterance, it does not batch or shard")
+    cfg = workload_config(args.gpus, args.config)
+    cfg["reference_config"] = f"B=1, 1 PC step of the {W['F']}x{W['T']} shape on the host CPU, extrapolated linearly to {nfe_target} NFE"
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * sum(dt for _, dt in rates) / len(rates), higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=workload_config(args.gpus),
+                config=cfg,
                 cpu_baseline=dict(value=value, unit="utt/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit="utt/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
+def path_traffic():
+    """DRAM bytes of ONE whole network evaluation (every kernel), from the committed ncu capture of this build
+    (profiles/r2_path_traffic.json, written by tools/path_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)."""
+    tp = os.path.join(ROOT, "profiles", "r2_path_traffic.json")
+    if os.path.exists(tp):
+        return json.load(open(tp))
+    return None
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from storm_b200 import ScoreModel, ncsnpp_spec, parallel
+    from storm_b200 import ScoreModel, StochasticRegenerationModel, ncsnpp_spec, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,28 +220,49 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    W = WORKLOAD
+    name = args.config
+    W = WORKLOADS[name]
     B, L = W["B_per_gpu"], W["L"]
-    model = ScoreModel(backbone=W["backbone"], sde="ouve", init_scale=1.0, seed=42)
-    # ---- weights: rank 0 owns the seeded state, ONE NCCL broadcast of the flat blob, no later collective
+    storm = name == "storm"
+    if storm:
+        model = StochasticRegenerationModel(backbone_denoiser=W["backbone"], backbone_score=W["backbone"], sde="ouve", init_scale=1.0, seed=42)
+        nets = model._nets()
+    else:
+        model = ScoreModel(backbone=W["backbone"], sde="ouve", init_scale=1.0, seed=42)
+        nets = [model.dnn]
+    # ---- weights: rank 0 owns the seeded state, ONE NCCL broadcast of the flat blob per network, no later collective
     if rank == 0:
-        model.dnn.load_state_dict(ncsnpp_spec.random_state_dict(model.dnn.cfg, seed=0, init_scale=1.0))
+        for i, net in enumerate(nets):
+            net.load_state_dict(ncsnpp_spec.random_state_dict(net.cfg, seed=i, init_scale=1.0))
     model.cuda()
-    parallel.broadcast_weights(model.dnn, src=0)      # no-op at world == 1
-    eng = model.dnn.engine()
-    sc = model._sampler_cfg(W["predictor"], W["corrector"], W["N"], W["corrector_steps"], W["snr"])
+    for net in nets:
+        parallel.broadcast_weights(net, src=0)      # no-op at world == 1
+    eng = nets[-1].engine()                          # the score network carries ~all of the work
+    engines = [n.engine() for n in nets]
     sp = model.data_module.spec_config()
     ids = list(range(rank * B, rank * B + B))
     y_host = synth_batch(B, L, rank * B).pin_memory()
     y_dev = y_host.cuda()
+    kw = dict(predictor=W["predictor"], corrector=W["corrector"], N=W["N"], corrector_steps=W["corrector_steps"], snr=W["snr"])
+    nfe_step = nfe_of(W) + (1 if storm else 0)       # StoRM: + one denoiser evaluation
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev():
-        return eng.enhance(y_dev, sc, sp, seed=42, utt_ids=ids)
+    sweep_rows = None
+    if storm:
+        def step_dev():
+            return model.enhance_batch(y_dev, seed=42, utt_ids=ids, return_nfe=True, **kw)
+    elif name == "sweep":
+        def step_dev():
+            return sweep_once(model, y_dev, ids, W)
+    else:
+        sc = model._sampler_cfg(W["predictor"], W["corrector"], W["N"], W["corrector_steps"], W["snr"])
+
+        def step_dev():
+            return eng.enhance(y_dev, sc, sp, seed=42, utt_ids=ids)
 
     for _ in range(args.warmup):
         step_dev()
@@ -213,31 +270,54 @@ def run_native(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    eng.reset_launch_count()
-    eng.set_profile(True)
+    for e in engines:
+        e.reset_launch_count()
+    # ---- `value`: device-resident inputs, CUDA events, NO per-launch instrumentation inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        out, nfe = step_dev()
+        res = step_dev()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = eng.launch_count()
-    prof = eng.get_profile()
-    eng.set_profile(False)
-    assert torch.isfinite(out).all()
+    launches = sum(e.launch_count() for e in engines)
+    if name == "sweep":
+        sweep_rows = res
+        out = None
+    else:
+        out, nfe = res
+        assert torch.isfinite(out).all() and nfe == nfe_of(W)
 
     # ---- end to end through the public API with host buffers (pinned H2D + D2H inside the timed region)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = model.enhance_batch(y_host, predictor=W["predictor"], corrector=W["corrector"], N=W["N"],
-                                  corrector_steps=W["corrector_steps"], snr=W["snr"], seed=42, utt_ids=ids)
-        assert res.device.type == "cpu"
+        if name == "sweep":
+            r = sweep_once(model, y_host, ids, W, host=True)
+        else:
+            r = model.enhance_batch(y_host, seed=42, utt_ids=ids, **kw)
+            assert r.device.type == "cpu"
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- separate profiled pass (two CUDA events around every conv launch): the live roofline measurement of the
+    # dominant kernel class; its instrumentation never touches `value`
+    for e in engines:
+        e.set_profile(True)
+    barrier()
+    p0 = time.perf_counter()
+    step_dev()
+    barrier()
+    prof_ms = (time.perf_counter() - p0) * 1e3
+    prof = {"tcgen05": dict(launches=0, ms=0.0, flops=0.0), "simt": dict(launches=0, ms=0.0, flops=0.0)}
+    for e in engines:
+        pe = e.get_profile()
+        for k in prof:
+            for kk in prof[k]:
+                prof[k][kk] += pe[k][kk]
+        e.set_profile(False)
 
     if world > 1:
         tt = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
@@ -249,52 +329,114 @@ def run_native(args):
         return
 
     pk = peaks()
-    traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
-    if os.path.exists(tp):       # from the committed ncu --set full capture of the same kernel (not measured in this run)
-        tj = json.load(open(tp))
-        traffic = tj.get("mean_dram_bytes_per_launch")
-        traffic_note = "profiles/r1_conv_traffic.json: mean dram bytes of the 4 largest conv launches (ncu --set full); " + tj.get("note", "")
     total_utts = world * B * args.steps
     value = total_utts / (ms * 1e-3)
     e2e_value = total_utts / (e2e_ms * 1e-3)
     dom = "tcgen05" if prof["tcgen05"]["flops"] >= prof["simt"]["flops"] else "simt"
     dp = prof[dom]
     achieved = dp["flops"] / (dp["ms"] * 1e-3) / 1e12 if dp["ms"] > 0 else 0.0
-    conv_share = (prof["tcgen05"]["ms"] + prof["simt"]["ms"]) / ms
+    conv_share = (prof["tcgen05"]["ms"] + prof["simt"]["ms"]) / prof_ms
     peak = pk["bf16_sustained"]
     # operand split of the tensor-core convolutions (storm_b200/csrc/conv_tc.cu): default = one fp16 pass + two fp8 correction
     # passes at twice the rate (2 passes); STORM_B200_TC_PREC=0 = bf16 hi/lo split (3 passes)
     passes = 3 if os.environ.get("STORM_B200_TC_PREC", "1") == "0" else 2
     split = "f16 x f16 + two e4m3 x e5m2 correction passes, fp32 accumulation" if passes == 2 else "bf16 hi/lo x 3, fp32 accumulation"
+    pt = path_traffic()
+    traffic, traffic_note = None, "no ncu capture committed for this build"
+    if pt and name == "headline":
+        traffic = pt.get("conv_dram_bytes_per_launch")
+        traffic_note = pt.get("note")
     roofline = dict(bound="tensor", kernel=f"implicit-GEMM conv3x3/1x1 ({dom})", achieved=achieved, peak=peak, unit="TFLOP/s",
                     frac=achieved / peak if peak else None, traffic=traffic, traffic_note=traffic_note,
+                    path_dram_bytes_per_utt_nfe=(pt or {}).get("path_dram_bytes_per_utt_nfe") if name == "headline" else None,
+                    path_algorithmic_bytes_per_utt_nfe=W["gb"] * 1e9,
                     peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
-                    note=(f"algorithmic fp32-equivalent FLOPs (2*MACs); the tcgen05 kernel spends {passes} 16-bit-equivalent tensor "
-                          f"passes per algorithmic MAC for fp32-grade results ({split}), so the tensor pipe runs at {passes}x this rate")
+                    note=(f"algorithmic fp32-equivalent FLOPs (2*MACs) / CUDA-event time of the conv launches, measured in a SEPARATE profiled "
+                          f"pass of one step (the timed `value` steps carry no instrumentation); the tcgen05 kernel spends {passes} "
+                          f"16-bit-equivalent tensor passes per algorithmic MAC for fp32-grade results ({split}), so the tensor pipe runs at "
+                          f"{passes}x this rate")
                     if dom == "tcgen05" else "fp32 SIMT FFMA kernel; tensor-core (tcgen05) path not used for this run",
                     issued_frac=(passes * achieved / peak) if (peak and dom == "tcgen05") else None,
                     launches=dp["launches"], avg_launch_ms=dp["ms"] / max(1, dp["launches"]), conv_share_of_step=conv_share,
                     by_engine=prof)
-    if world == 1:      # the CPU baseline is a per-box figure: timed on rank 0 of the single-GPU run only
+    if world == 1 and not args.no_cpu:      # the CPU baseline is a per-box figure: timed on rank 0 of the single-GPU run only
         threads = pick_cpu_threads()
-        cpu_rate, cpu_dt, cpu_nfe = cpu_oracle_rate(threads, W["N"] * 2)
+        cpu_rate, cpu_dt, cpu_nfe = cpu_oracle_rate(threads, nfe_of(W), W)
         cpu_baseline = dict(value=cpu_rate, unit="utt/s", cores=threads, kind="port",
-                            sample=f"oracle port, B=1 256x256, 1 PC step ({cpu_nfe} NFE) in {cpu_dt:.1f}s, scaled linearly to 60 NFE")
+                            sample=f"oracle port, B=1 {W['F']}x{W['T']}, 1 PC step ({cpu_nfe} NFE) in {cpu_dt:.1f}s, scaled linearly to {nfe_of(W)} NFE")
     else:
         cpu_baseline = dict(value=None, unit="utt/s", cores=0, kind="port", sample="measured in the N=1 run only")
+    cfg = workload_config(world, name, nfe_step)
     line = dict(metric="utterances/sec", value=value, unit="utt/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", dtype_detail=f"fp32 in/out; tensor-core products as {split} (fp32-grade: 6.6e-5 vs the reference over the 60-evaluation headline trajectory; tolerance 1e-3)" if dom == "tcgen05" else "fp32 FFMA", data="synthetic",
-                config=workload_config(world, nfe),
-                roofline=roofline,
-                cpu_baseline=cpu_baseline,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                dtype_detail=f"fp32 in/out; tensor-core products as {split} (fp32-grade; tolerance 1e-3 vs the reference)" if dom == "tcgen05" else "fp32 FFMA",
+                data="synthetic", config=cfg, roofline=roofline, cpu_baseline=cpu_baseline,
                 e2e=dict(value=e2e_value, unit="utt/s", h2d_bytes_per_step=world * B * L * 4, d2h_bytes_per_step=world * B * L * 4,
                          ms_per_step=e2e_ms / args.steps),
                 gpu_launches=launches, clocks=clk,
-                path_tflops=world * B * nfe * args.steps * GFLOP_PER_UTT_NFE / 1e3 / (ms * 1e-3))
+                path_tflops=(world * B * nfe_step * args.steps * W["gflop"] / 1e3 / (ms * 1e-3)) if name != "sweep" else None)
+    if sweep_rows is not None:
+        line["sweep"] = sweep_rows
+        line["config"]["workload"] = (f"{W['tag']}: sampler sweep, ncsnpp 27.8M, B={B}, 256x256: PC (reverse_diffusion+ald) and fixed-step "
+                                      "probability flow at N in {10,20,30,50}, plus the reference's RK45 PF-ODE; `value` = utterances of ALL "
+                                      "sweep rows / time of one whole sweep; per-row rates in `sweep`")
+        line["value"] = world * B * len(sweep_rows) * args.steps / (ms * 1e-3)
+        line["e2e"]["value"] = world * B * len(sweep_rows) * args.steps / (e2e_ms * 1e-3)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_once(model, y, ids, W, host=False):
+    """BASELINE configs[4]: PC vs probability-flow ODE at N in {10, 20, 30, 50} on one batch; every row is timed on the device.
+    PC = reverse_diffusion + ald (2N evaluations); PF = the same predictor on RSDE.discretize(probability_flow=True), no
+    corrector, no noise (N evaluations); RK45 = the reference's scipy solver (sampling/__init__.py:119-129, rtol = atol = 1e-5,
+    one utterance per solve like model.py:224-244), NFE reported."""
+    import torch
+    from storm_b200 import _native
+    rows = []
+    dev = model._device()
+    yd = y.to(dev, non_blocking=True) if host else y
+    sp = model.data_module.spec_config()
+    eng = model.dnn.engine()
+    B = yd.shape[0]
+
+    def timed(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        b.synchronize()
+        return r, a.elapsed_time(b)
+
+    for N in (10, 20, 30, 50):
+        sc = model._sampler_cfg("reverse_diffusion", "ald", N, 1, W["snr"])
+        (out, nfe), ms = timed(lambda: eng.enhance(yd, sc, sp, seed=42, utt_ids=ids))
+        if host:
+            out = out.cpu()
+        rows.append(dict(sampler="pc", N=N, nfe=nfe, ms=ms, utt_per_s=B / (ms * 1e-3)))
+    norm = _native.wave_norm(yd)
+    T_pad = _native.padded_frames(_native.num_frames(yd.shape[1], sp))
+    Y = _native.stft(yd, norm, sp, T_pad).unsqueeze(1)
+    for N in (10, 20, 30, 50):
+        s = model.sde
+        sc = _native.make_sampler_config("reverse_diffusion", "none", N, 0, 0.0, model.t_eps, s.theta, s.sigma_min, s.sigma_max,
+                                         probability_flow=True)
+        (res, ms) = timed(lambda: eng.istft(eng.pc_sample(Y, sc, seed=42, utt_ids=ids)[0].squeeze(1), norm, yd.shape[1], sp))
+        if host:
+            res = res.cpu()
+        rows.append(dict(sampler="pf_fixed_step", N=N, nfe=N, ms=ms, utt_per_s=B / (ms * 1e-3)))
+    t0 = time.perf_counter()
+    sampler = model.get_ode_sampler(Y, N=30, minibatch=1, seed=42)
+    sample, nfes = sampler()
+    wav = eng.istft(sample.squeeze(1), norm, yd.shape[1], sp)
+    if host:
+        wav = wav.cpu()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    rows.append(dict(sampler="pf_rk45_scipy", N=None, nfe=float(sum(nfes)) / len(nfes), ms=ms, utt_per_s=B / (ms * 1e-3),
+                     note="host-driven solver, one utterance per solve, state crosses PCIe per right-hand side as in the reference"))
+    return rows
 
 
 def main():
@@ -303,6 +445,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS), help="headline = BASELINE configs[1] (the driver's line)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (A/B runs of kernel variants)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

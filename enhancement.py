@@ -11,6 +11,7 @@ wav I/O uses torchaudio like the reference when it has a backend, scipy.io.wavfi
 """
 import glob
 import os
+import sys
 from argparse import ArgumentParser
 
 import torch
@@ -28,6 +29,8 @@ def build_parser() -> ArgumentParser:
     p.add_argument("--N", type=int, default=50, help="Number of reverse steps")
     p.add_argument("--batch-size", type=int, default=8)
     p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--gpus", type=int, default=1, help="GPUs of this node: re-launches itself under torch.distributed.run with one "
+                                                        "process per GPU (ignored when already running under torchrun)")
     p.add_argument("--io-workers", type=int, default=4, help="threads reading / writing wav files around the GPU work")
     p.add_argument("--random-init", type=str, default=None, help="backbone name: run with seeded random weights instead of --ckpt")
     return p
@@ -39,10 +42,19 @@ def shard(files, rank, world):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    from storm_b200 import ScoreModel, StochasticRegenerationModel
+    if args.gpus > 1 and "RANK" not in os.environ:      # one process per GPU; 127.0.0.1: the container hostname may not resolve
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + list(sys.argv[1:] if argv is None else argv)
+        os.execv(sys.executable, cmd)
+    from storm_b200 import DiscriminativeModel, ScoreModel, StochasticRegenerationModel
+    from storm_b200.model import checkpoint_kind
     if args.mode == "denoiser-only" and not args.random_init and args.ckpt is None:
         raise SystemExit("--ckpt is required")
-    model_cls = ScoreModel if args.mode == "score-only" else StochasticRegenerationModel   # enhancement.py:47-54
+    # enhancement.py:47-54: storm -> StochasticRegenerationModel, score-only -> ScoreModel, denoiser-only -> DiscriminativeModel.
+    # A StoRM checkpoint (denoiser_net.* / score_net.* keys) is also accepted for denoiser-only: its denoiser runs alone.
+    model_cls = {"score-only": ScoreModel, "storm": StochasticRegenerationModel, "denoiser-only": DiscriminativeModel}[args.mode]
+    if args.mode == "denoiser-only" and (not args.ckpt or checkpoint_kind(args.ckpt) == "storm"):
+        model_cls = StochasticRegenerationModel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -65,7 +77,7 @@ def main(argv=None):
     model.cuda()
     if world > 1:   # identical weights everywhere: one broadcast of the flat blob per network
         from storm_b200 import parallel
-        for net in ([model.dnn] if args.mode == "score-only" else model._nets()):
+        for net in ([model.dnn] if hasattr(model, "dnn") else model._nets()):
             parallel.broadcast_weights(net, src=0)
 
     from storm_b200.parallel import bucket_utterances
@@ -81,23 +93,25 @@ def main(argv=None):
         return idx, f, y[:1]
 
     with wavio.AsyncWriter(workers=args.io_workers) as writer:
-        if args.mode != "score-only":   # StoRM / denoiser-only: one utterance per call like the reference (enhancement.py:66-72)
-            for idx, f, y in wavio.Prefetcher(mine, load, depth=4, workers=args.io_workers):
-                x_hat = model.enhance(y, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
-                                      denoiser_only=(args.mode == "denoiser-only"))
-                writer.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().unsqueeze(0), model_sr)
-        else:
-            # lengths from the wav headers -> batches of one padded-frame bucket (ragged inside the bucket); the next
-            # batches are read by worker threads while the GPU enhances the current one, results are written behind it
-            lengths = [wavio.wav_length(f) for _, f in mine]
-            batches = [[mine[i] for i in b] for b in bucket_utterances(lengths, hop_length=model.data_module.hop_length,
-                                                                       max_batch=args.batch_size)]
-            for group in wavio.Prefetcher(batches, lambda b: [load(it) for it in b], depth=2, workers=args.io_workers):
-                outs = model.enhance_batch([t[2] for t in group], corrector=args.corrector, N=args.N,
-                                           corrector_steps=args.corrector_steps, snr=args.snr, seed=args.seed,
-                                           utt_ids=[t[0] for t in group], max_batch=args.batch_size)
-                for (idx, f, _), x_hat in zip(group, outs):
-                    writer.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().reshape(1, -1), model_sr)
+        # lengths from the wav headers -> batches of one padded-frame bucket (ragged inside the bucket); the next
+        # batches are read by worker threads while the GPU enhances the current one, results are written behind it.
+        # Every mode runs batched (the reference enhances one file per call, enhancement.py:66-72).
+        lengths = [wavio.wav_length(f) for _, f in mine]
+        batches = [[mine[i] for i in b] for b in bucket_utterances(lengths, hop_length=model.data_module.hop_length,
+                                                                   max_batch=args.batch_size)]
+        for group in wavio.Prefetcher(batches, lambda b: [load(it) for it in b], depth=2, workers=args.io_workers):
+            ys, ids = [t[2] for t in group], [t[0] for t in group]
+            if isinstance(model, StochasticRegenerationModel):
+                outs = model.enhance_batch(ys, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
+                                           denoiser_only=(args.mode == "denoiser-only"), seed=args.seed, utt_ids=ids,
+                                           max_batch=args.batch_size)
+            elif isinstance(model, DiscriminativeModel):
+                outs = [model.enhance(y) for y in ys] if len({y.numel() for y in ys}) > 1 else list(model.enhance_batch(ys))
+            else:
+                outs = model.enhance_batch(ys, corrector=args.corrector, N=args.N, corrector_steps=args.corrector_steps, snr=args.snr,
+                                           seed=args.seed, utt_ids=ids, max_batch=args.batch_size)
+            for (idx, f, _), x_hat in zip(group, outs):
+                writer.save(f"{args.enhanced_dir}/{os.path.basename(f)}", x_hat.type(torch.float32).cpu().reshape(1, -1), model_sr)
     if world > 1:
         dist.destroy_process_group()
 

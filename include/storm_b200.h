@@ -214,8 +214,8 @@ int storm_debug_conv(int32_t engine, const float* x0, const float* x1, int32_t C
 /* Same, launched twice; the second launch is timed with CUDA events (ms_out) and, when dbg_dev != NULL
  * (device int64[16]), CTA 0 of the tcgen05 kernel records cycle counters: [0] MMA issue loop, [1] waiting for
  * activation stages, [2] waiting for weight stages, [3] until the last MMA retired, [4] producer idle before
- * the epilogue, [5] epilogue; producer thread 0: [6] / [7] waiting for the global loads of segment 0 / 1,
- * [8] waiting for a free activation stage, [9] / [10] converting + storing segment 0 / 1. */
+ * the epilogue, [5] epilogue; producer thread 0: [6] issuing the global loads (back-pressure), [8] waiting for a
+ * free activation stage, [9] / [10] load latency + conversion + stores of segment 0 / 1. */
 int storm_debug_conv_timed(int32_t engine, const float* x0, const float* x1, int32_t C0, int32_t C1, const float* ss, int32_t silu,
                            int32_t taps, const float* w, const float* x2, int32_t C2, const float* w2, int32_t Cout,
                            const float* bias, const float* res, float out_scale, float* out, int32_t B, int32_t H, int32_t W,

@@ -7,6 +7,6 @@ from .backbones import BackboneRegistry  # noqa: F401
 from .sdes import SDERegistry  # noqa: F401
 from .sampling import PredictorRegistry, CorrectorRegistry  # noqa: F401
 from .data_module import SpecsDataModule  # noqa: F401
-from .model import ScoreModel, StochasticRegenerationModel  # noqa: F401
+from .model import ScoreModel, DiscriminativeModel, StochasticRegenerationModel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -7,6 +7,7 @@ and to provide the current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -133,8 +134,37 @@ def _check(rc: int):
     raise RuntimeError(msg)
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """torch's current stream on ``device`` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(t):
+    """Context that makes the device of tensor ``t`` (or the given device / index) current: every native call launches on
+    the device that owns its operands, whatever the process-wide current device is (``model.cuda(1)`` in a process whose
+    current device is 0 must not launch device-0 kernels on device-1 pointers)."""
+    dev = t.device if torch.is_tensor(t) else t
+    return torch.cuda.device(dev)
+
+
+def _engine_dev(fn):
+    """Engine method runs with the engine's device current (the C side also guards, include/storm_b200.h)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
+def _tensor_dev(fn):
+    """Handle-free entry point runs on the device of its first tensor argument."""
+    @functools.wraps(fn)
+    def wrapped(t, *a, **k):
+        if torch.is_tensor(t) and t.is_cuda:
+            with torch.cuda.device(t.device):
+                return fn(t, *a, **k)
+        return fn(t, *a, **k)
+    return wrapped
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -187,8 +217,14 @@ class Engine:
         self.in_cplx = 1 if discriminative else input_channels // 2
         self.discriminative = bool(discriminative)
         h = C.c_void_p()
+        self.device = torch.device("cuda", torch.cuda.current_device())     # the handle lives on the device current at creation
         _check(lib().storm_create(C.byref(cfg), C.byref(h)))
         self._h = h
+
+    def _own(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if t.is_cuda and t.device != self.device:
+            raise RuntimeError(f"storm_b200: {name} is on {t.device} but this engine was created on {self.device}")
+        return t
 
     def close(self):
         if getattr(self, "_h", None):
@@ -217,6 +253,7 @@ class Engine:
     def param_floats(self) -> int:
         return lib().storm_param_floats(self._h)
 
+    @_engine_dev
     def load_blob(self, blob: torch.Tensor):
         blob = blob.contiguous()
         if blob.dtype != torch.float32:
@@ -224,19 +261,22 @@ class Engine:
         _check(lib().storm_load_weights(self._h, blob.data_ptr(), blob.numel(), int(blob.is_cuda), _stream()))
         torch.cuda.current_stream().synchronize()   # blob may be a temporary
 
+    @_engine_dev
     def weights_view(self) -> torch.Tensor:
         """Zero-copy view of the raw device blob (for torch.distributed.broadcast)."""
         p = C.c_void_p()
         n = C.c_int64()
         _check(lib().storm_weights_device(self._h, C.byref(p), C.byref(n)))
-        return _DevView(p.value, n.value).tensor()
+        return _DevView(p.value, n.value, self.device).tensor()
 
+    @_engine_dev
     def repack(self):
         _check(lib().storm_repack_weights(self._h, _stream()))
 
     # ---- network ------------------------------------------------------------------------------------------
+    @_engine_dev
     def net_forward(self, x: torch.Tensor, t: Optional[torch.Tensor]) -> torch.Tensor:
-        x = _cf(x, "x")
+        x = self._own(_cf(x, "x"), "x")
         if x.dtype != torch.complex64 or x.dim() != 4 or x.shape[1] != self.in_cplx:
             raise ValueError(f"expected complex64 [B, {self.in_cplx}, F, T], got {x.dtype} {tuple(x.shape)}")
         B, _, F, T = x.shape
@@ -253,13 +293,15 @@ class Engine:
     def set_taps(self, on: bool):
         _check(lib().storm_set_debug_taps(self._h, int(on)))
 
+    @_engine_dev
     def get_tap(self, name: str) -> torch.Tensor:
         shape = (C.c_int64 * 4)()
         _check(lib().storm_get_tap(self._h, name.encode(), None, 0, shape, _stream()))
-        out = torch.empty(tuple(shape), dtype=torch.float32, device="cuda")
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
         _check(lib().storm_get_tap(self._h, name.encode(), out.data_ptr(), out.numel(), shape, _stream()))
         return out
 
+    @_engine_dev
     def reserve(self, B, F, T):
         _check(lib().storm_reserve(self._h, B, F, T))
 
@@ -275,6 +317,7 @@ class Engine:
     def set_profile(self, on: bool):
         _check(lib().storm_set_profile(self._h, int(on)))
 
+    @_engine_dev
     def get_profile(self) -> Dict[str, Dict[str, float]]:
         n = (C.c_int64 * 2)()
         ms = (C.c_double * 2)()
@@ -283,11 +326,12 @@ class Engine:
         return {k: dict(launches=int(n[i]), ms=float(ms[i]), flops=float(fl[i])) for i, k in enumerate(("tcgen05", "simt"))}
 
     # ---- sampler ------------------------------------------------------------------------------------------
+    @_engine_dev
     def pc_sample(self, Y: torch.Tensor, sc: SamplerConfig, seed: int = 0, utt_ids: Optional[Sequence[int]] = None,
                   noise: Optional[torch.Tensor] = None, cond: Optional[Sequence[torch.Tensor]] = None) -> Tuple[torch.Tensor, int]:
         """Y: SDE mean / prior centre.  cond: conditioning spectrograms stacked after x in the network input
         (default [Y]; StoRM passes [Y_noisy, Y_denoised] with Y = Y_denoised)."""
-        Y = _cf(Y, "Y")
+        Y = self._own(_cf(Y, "Y"), "Y")
         if Y.dtype != torch.complex64 or Y.dim() != 4 or Y.shape[1] != 1:
             raise ValueError(f"expected complex64 [B, 1, F, T], got {Y.dtype} {tuple(Y.shape)}")
         B, _, F, T = Y.shape
@@ -314,6 +358,7 @@ class Engine:
                                      C.cast(ids, C.c_void_p) if ids is not None else None, _ptr(noise), C.byref(nfe), _stream()))
         return X, int(nfe.value)
 
+    @_engine_dev
     def ode_drift(self, X: torch.Tensor, Y: torch.Tensor, t: float, sc: SamplerConfig) -> torch.Tensor:
         X, Y = _cf(X, "X"), _cf(Y, "Y")
         B, _, F, T = Y.shape
@@ -322,6 +367,7 @@ class Engine:
         return out
 
     # ---- STFT ---------------------------------------------------------------------------------------------
+    @_engine_dev
     def istft(self, spec: torch.Tensor, norm: Optional[torch.Tensor], L: int, sp: SpecConfig,
               lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """lengths: optional int32 CUDA tensor [B] (ragged batch of one frame bucket, row stride L)."""
@@ -330,15 +376,16 @@ class Engine:
         if F != sp.n_fft // 2 + 1:
             raise ValueError("spectrogram does not have n_fft/2+1 bins")
         wav = torch.empty((B, L), dtype=torch.float32, device=spec.device)
-        _check(lib().storm_istft_ragged(self._h, spec.data_ptr(), _ptr(norm), B, T, wav.data_ptr(), L, _ptr(_lens(lengths, B, L, sp)),
+        _check(lib().storm_istft_ragged(self._h, spec.data_ptr(), _ptr(norm), B, T, wav.data_ptr(), L, _ptr(_lens(lengths, B, L, sp, wav.device)),
                                         C.byref(sp), _stream()))
         return wav
 
+    @_engine_dev
     def enhance(self, wav: torch.Tensor, sc: SamplerConfig, sp: SpecConfig, seed: int = 0,
                 utt_ids: Optional[Sequence[int]] = None, lengths: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
-        wav = _cf(wav.to(torch.float32), "wav")
+        wav = self._own(_cf(wav.to(torch.float32), "wav"), "wav")
         B, L = wav.shape
-        lengths = _lens(lengths, B, L, sp)
+        lengths = _lens(lengths, B, L, sp, wav.device)
         out = torch.empty_like(wav)
         ids = None
         if utt_ids is not None:
@@ -353,11 +400,12 @@ class Engine:
 class _DevView:
     """Expose a raw device range as a torch tensor through __cuda_array_interface__."""
 
-    def __init__(self, ptr: int, n: int):
+    def __init__(self, ptr: int, n: int, device="cuda"):
+        self.device = device
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
     def tensor(self) -> torch.Tensor:
-        return torch.as_tensor(self, device="cuda")
+        return torch.as_tensor(self, device=self.device)
 
 
 # ---- handle-free entry points ------------------------------------------------------------------------------
@@ -379,21 +427,23 @@ def check_lengths(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> L
     return lh
 
 
-def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None) -> Optional[torch.Tensor]:
+def _lens(lengths, B: int, L: int, sp: Optional[SpecConfig] = None, device="cuda") -> Optional[torch.Tensor]:
     """Validated lengths as the int32 CUDA tensor the ragged entry points take (None = every row is L samples)."""
     if lengths is None:
         return None
-    return torch.tensor(check_lengths(lengths, B, L, sp), dtype=torch.int32, device="cuda")
+    return torch.tensor(check_lengths(lengths, B, L, sp), dtype=torch.int32, device=device)
 
 
+@_tensor_dev
 def wave_norm(wav: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     wav = _cf(wav, "wav")
     B, L = wav.shape
     norm = torch.empty((B,), dtype=torch.float32, device=wav.device)
-    _check(lib().storm_wave_norm_ragged(wav.data_ptr(), B, L, _ptr(_lens(lengths, B, L)), norm.data_ptr(), _stream()))
+    _check(lib().storm_wave_norm_ragged(wav.data_ptr(), B, L, _ptr(_lens(lengths, B, L, None, wav.device)), norm.data_ptr(), _stream()))
     return norm
 
 
+@_tensor_dev
 def si_sdr(s: torch.Tensor, s_hat: torch.Tensor, lengths: Optional[torch.Tensor] = None, eps: float = 0.0) -> torch.Tensor:
     """SI-SDR in dB per row of [B, L] CUDA tensors (sgmse/util/other.py:82-94); eps=1e-10 is the si_sdr_torch form."""
     s, s_hat = _cf(s.to(torch.float32), "s"), _cf(s_hat.to(torch.float32), "s_hat")
@@ -401,7 +451,7 @@ def si_sdr(s: torch.Tensor, s_hat: torch.Tensor, lengths: Optional[torch.Tensor]
         raise ValueError("si_sdr expects two [B, L] tensors of the same shape")
     B, L = s.shape
     out = torch.empty((B,), dtype=torch.float32, device=s.device)
-    _check(lib().storm_si_sdr(s.data_ptr(), s_hat.data_ptr(), B, L, _ptr(_lens(lengths, B, L)), float(eps), out.data_ptr(), _stream()))
+    _check(lib().storm_si_sdr(s.data_ptr(), s_hat.data_ptr(), B, L, _ptr(_lens(lengths, B, L, None, s.device)), float(eps), out.data_ptr(), _stream()))
     return out
 
 
@@ -413,6 +463,7 @@ def padded_frames(frames: int) -> int:
     return lib().storm_padded_frames(frames)
 
 
+@_tensor_dev
 def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad: Optional[int] = None,
          lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     wav = _cf(wav.to(torch.float32), "wav")
@@ -420,7 +471,7 @@ def stft(wav: torch.Tensor, norm: Optional[torch.Tensor], sp: SpecConfig, T_pad:
     frames = num_frames(L, sp)
     T_pad = frames if T_pad is None else T_pad
     spec = torch.empty((B, sp.n_fft // 2 + 1, T_pad), dtype=torch.complex64, device=wav.device)
-    _check(lib().storm_stft_ragged(wav.data_ptr(), _ptr(norm), B, L, _ptr(_lens(lengths, B, L, sp)), spec.data_ptr(), T_pad,
+    _check(lib().storm_stft_ragged(wav.data_ptr(), _ptr(norm), B, L, _ptr(_lens(lengths, B, L, sp, wav.device)), spec.data_ptr(), T_pad,
                                    C.byref(sp), _stream()))
     return spec
 
@@ -449,6 +500,7 @@ def debug_conv(engine: int, x0, w, x1=None, ss=None, silu=False, x2=None, w2=Non
     return out
 
 
+@_tensor_dev
 def debug_attention(engine: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """Test hook: q, k, v [B, N, C] fp32 CUDA; the tcgen05 kernel is handed v channel-major as the engine does."""
     q, k, v = _cf(q, "q"), _cf(k, "k"), _cf(v, "v")
@@ -459,7 +511,9 @@ def debug_attention(engine: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
     return o
 
 
-def philox_normal(seed: int, utt_id: int, draw: int, n: int) -> torch.Tensor:
-    out = torch.empty((n,), dtype=torch.complex64, device="cuda")
-    _check(lib().storm_philox_normal(C.c_uint64(seed), C.c_uint64(utt_id), C.c_uint32(draw), n, out.data_ptr(), _stream()))
+def philox_normal(seed: int, utt_id: int, draw: int, n: int, device=None) -> torch.Tensor:
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n,), dtype=torch.complex64, device=device)
+    with torch.cuda.device(device):
+        _check(lib().storm_philox_normal(C.c_uint64(seed), C.c_uint64(utt_id), C.c_uint32(draw), n, out.data_ptr(), _stream()))
     return out

@@ -78,12 +78,19 @@ class NCSNpp(nn.Module):
         return blob
 
     def engine(self) -> _native.Engine:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("storm_b200: move the backbone to a CUDA device first (.cuda()); the path has no CPU implementation")
+        if self._engine is not None and self._engine.device != dev:      # .cuda(other) / .to(other): the handle follows the weights
+            self._engine.close()
+            self._engine = None
         if self._engine is None:
             c = self.cfg
-            self._engine = _native.Engine(nf=c.nf, ch_mult=c.ch_mult, num_res_blocks=c.num_res_blocks,
-                                          attn_resolutions=c.attn_resolutions, image_size=c.image_size,
-                                          input_channels=c.input_channels, discriminative=c.discriminative,
-                                          engine=self._engine_kind)
+            with torch.cuda.device(dev):
+                self._engine = _native.Engine(nf=c.nf, ch_mult=c.ch_mult, num_res_blocks=c.num_res_blocks,
+                                              attn_resolutions=c.attn_resolutions, image_size=c.image_size,
+                                              input_channels=c.input_channels, discriminative=c.discriminative,
+                                              engine=self._engine_kind)
             self._table = self._engine.param_table()
             if [(n, s) for n, s, _ in self._table] != ncsnpp_spec.param_table(c):
                 raise RuntimeError("native parameter table disagrees with the Python specification")

@@ -32,6 +32,13 @@
 
 #include "conv_tc.cuh"
 
+// 1: producer thread 0 of CTA 0 also records where ITS cycles go (dbg[6..10], tools/conv_timeline.py); costs registers in the
+// producer warps, so it is compiled out of the shipped library (build with -DSTORM_TC_PRODUCER_TIMING=1 to get the numbers of
+// profiles/r2_conv_timeline_producer.txt)
+#ifndef STORM_TC_PRODUCER_TIMING
+#define STORM_TC_PRODUCER_TIMING 0
+#endif
+
 namespace storm {
 
 namespace {
@@ -55,6 +62,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking test (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is incomplete)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -453,266 +472,18 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
   }
 }
 
-// MAXU = halo pixels per producer thread (ceil(np / (32 NPW))); MINB = CTAs per SM.  MINB = 1: one CTA per SM owning
-// all 512 TMEM columns; MINB = 2: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
-// global stores) overlaps the other's MMA main loop on the shared tensor pipe.
-// NPW: activation-producer warps (all of them run the epilogue afterwards); warp NPW = weight producer,
-// warp NPW + 1 = TMEM allocator + MMA issuer.
-// PREC: operand split (TcpCfg::prec), compiled in so that each instantiation only carries its own conversion code.
-template <int MAXU, int MINB, int NPW, int PREC>
-__global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
-  constexpr int P_PRODUCERS = NPW * 32;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_base = smem_u32(smem);
-  const uint32_t w_base = a_base + c.sa * c.a_stage;
-  const uint32_t bar_base = w_base + c.sw * c.w_stage;
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
-  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };
-  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };
-  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 2 * c.sw);
-  const uint32_t tmem_slot = acc_full + 8;
-
-  const int tile = blockIdx.x;
-  const int ty0 = (tile / c.tiles_x) * c.rows;
-  const int tx0 = (tile % c.tiles_x) * 8 * c.npt;
-  const int m_lo = blockIdx.y * 128 * c.nmb;       // first output channel (row of the padded weight image) of this CTA
-  const int Mpad = tc_mpad(p.Cout);
-  const int b = blockIdx.z;
-
-  if (tid == 0) {
-    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), P_PRODUCERS); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
-    mbar_init(acc_full, 1);
-    fence_barrier_init();
-  }
-  constexpr uint32_t TMEM_COLS = MINB == 1 ? 512 : 256;
-  if (warp == NPW + 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp < NPW) {
-    // ---- per-sample operand scale alpha = 2^-e <= 1 (ConvParams::raw_ms): rms of the largest raw group brought down to <= 2^9,
-    // which leaves fp16 (max 2^16) a factor 128 for peaks; alpha = 1 (no extra instruction below) up to rms 512
-    float alpha = 1.0f, inv_alpha = 1.0f;
-    if (p.raw_ms) {
-      float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (m > 262144.0f && m < 3.0e38f) {                      // rms > 2^9
-        const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;        // m = f 2^ex, f in [0.5, 1)
-        int e = (ex + 1) / 2 - 9;                              // ceil(log2(rms)) - 9
-        e = e < 0 ? 0 : (e > 60 ? 60 : e);
-        alpha = __uint_as_float((uint32_t)(127 - e) << 23);
-        inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
-      }
-    }
-    // =================================== activation producers ==========================================
-    // Each thread owns up to 3 halo pixels per stage and handles all 16 channels (64 contiguous bytes) of each.
-    // All global loads of a stage are issued before any is consumed (memory-level parallelism), and the next
-    // chunk's lines are prefetched into L2 while this one is converted.
-    int stage = 0;
-    uint32_t phase = 0;
-    int upix[MAXU];                                        // global pixel index (b, y, x) or -1 (outside / unused)
-    uint32_t uoff[MAXU];
-    bool uinterior[MAXU];
-#pragma unroll
-    for (int i = 0; i < MAXU; ++i) {
-      const int ps = tid + i * P_PRODUCERS;
-      upix[i] = -2;                                        // -2: slot not present
-      uoff[i] = (uint32_t)ps * 16u;
-      uinterior[i] = false;
-      if (ps < c.np) {
-        const int hy = ps / c.hx, hxx = ps - hy * c.hx;
-        const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
-        uinterior[i] = !(hy == 0 || hy == c.hy - 1 || hxx == 0 || hxx == c.hx - 1);
-        upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
-      }
-    }
-    auto split_store = [&](const float (&v)[8], bool valid, uint32_t off) {   // 8 channels of one pixel -> hi plane, lo plane
-      uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        float r[8];
-        hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
-        hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
-        hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
-        hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
-        float d0, d1;
-        lo.x = pack_bf16x2(r[0], r[1], d0, d1);
-        lo.y = pack_bf16x2(r[2], r[3], d0, d1);
-        lo.z = pack_bf16x2(r[4], r[5], d0, d1);
-        lo.w = pack_bf16x2(r[6], r[7], d0, d1);
-      }
-      st_shared_v4(off, hi);
-      st_shared_v4(off + c.a_half, lo);
-    };
-    // prec 1: the 8 channels of one pixel -> fp16 k-core of the half's plane; the fp8 bytes of both 8-channel groups of a
-    // unit are stored together (16 bytes per pixel and fp8 plane k-core)
-    constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
-    ChunkIter it(p, PREC);
-    int si, chk;
-    const bool pdbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
-    long long t_ld[2] = {0, 0}, t_empty = 0, t_cv[2] = {0, 0};     // [segment]: cycles waiting for loads / converting + storing
-    while (it.next(si, chk)) {
-      const ConvSeg& s = p.seg[si];
-      const int C = s.C0 + s.C1;
-      const bool full_halo = s.taps == 9;
-#pragma unroll 1
-      for (int hsel = 0; hsel < NH; ++hsel) {
-        const int c0 = chk * (16 * NH) + 16 * hsel;
-        const float* src;
-        int Cs, cl;
-        if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
-        // ---- issue all loads of this stage
-        const long long t_a = pdbg ? clock64() : 0;
-        float4 raw[MAXU][4];
-#pragma unroll
-        for (int i = 0; i < MAXU; ++i) {
-          if (upix[i] >= 0 && (full_halo || uinterior[i])) {
-            const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix[i] * Cs + cl);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
-          }
-        }
-        // ---- L2 prefetch of the next chunk in schedule order (once per stage; a 32-channel chunk is one 128-byte line per
-        // pixel).  Looking further ahead (2, 4, 8 chunks) was measured and changes nothing: profiles/r2_bench_history.md.
-        if (hsel == 0) {
-          ChunkIter peek = it;
-          int nsi, nch;
-          if (peek.next(nsi, nch)) {
-            const ConvSeg& ns = p.seg[nsi];
-            const int n0c = nch * (16 * NH);
-            const float* nsrc;
-            int nCs, ncl;
-            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
-            const bool nfull = ns.taps == 9;
-#pragma unroll
-            for (int i = 0; i < MAXU; ++i)
-              if (upix[i] >= 0 && (nfull || uinterior[i]))
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
-          }
-        }
-        float sc[16], sh[16];
-        if (s.ss) {
-          const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + c0) * 2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = __ldg(sp + j);
-            sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
-          }
-        }
-        const long long t_b = pdbg ? clock64() : 0;
-        if (hsel == 0) mbar_wait_relaxed(a_empty(stage), phase ^ 1);
-        long long t_c = 0;
-        if (pdbg) {
-          t_c = clock64();
-          t_empty += t_c - t_b;
-          float probe = raw[0][3].w;                                  // last load of the first pixel: wait for it to land
-          if (upix[0] >= 0 && (full_halo || uinterior[0])) asm volatile("mov.f32 %0, %0;" : "+f"(probe));
-          const long long t_d = clock64();
-          t_ld[si] += t_d - t_c;
-          t_c = t_d;
-        }
-        const uint32_t st_base = a_base + stage * c.a_stage;
-#pragma unroll
-        for (int i = 0; i < MAXU; ++i) {
-          if (upix[i] == -2 || !(full_halo || uinterior[i])) continue;
-          uint2 a8[2], l8[2];                                            // prec 1: fp8 bytes of the two 8-channel groups
-#pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-            const uint32_t off = st_base + (uint32_t)(kh * c.np) * 16u + uoff[i];
-            const bool valid = upix[i] >= 0;
-            const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
-            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            if (valid) {
-              if (s.ss) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[kh * 8 + j], sh[kh * 8 + j]);
-              }
-              if (s.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
-              }
-              if (alpha != 1.0f) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= alpha;
-              }
-            }
-            if constexpr (PREC == 1) {
-              uint4 h16 = make_uint4(0, 0, 0, 0);
-              a8[kh] = make_uint2(0, 0);
-              l8[kh] = make_uint2(0, 0);
-              if (valid) split_f16f8(v, h16, a8[kh], l8[kh]);
-              st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);         // f16 plane of this half, k-core kh
-            } else {
-              split_store(v, valid, off);
-            }
-          }
-          if constexpr (PREC == 1) {       // fp8 planes: k-core hsel holds the 16 channels of this half
-            const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * c.np) * 16u + uoff[i];
-            st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
-            st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
-          }
-        }
-        if (pdbg) t_cv[si] += clock64() - t_c;
-        if (hsel == NH - 1) {
-          fence_async_shared();
-          mbar_arrive(a_full(stage));
-          if (++stage == c.sa) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    // =================================== epilogue (every producer warp) ==================================
-    {
-    const bool dbg = pdbg;
-    const long long t_e0 = dbg ? clock64() : 0;
-    if (dbg) { p.dbg[6] = t_ld[0]; p.dbg[7] = t_ld[1]; p.dbg[8] = t_empty; p.dbg[9] = t_cv[0]; p.dbg[10] = t_cv[1]; }
-    constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
-    const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
-    const int nacc = c.npt * c.nmb;
-    const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
-    const int nunits = nacc * units_per_acc;
-    const int Hl = p.H >> 1, Wl = p.W >> 1;         // extents of the half-resolution residual (res_up)
-    if ((p.res || p.res_up) && !p.out_cm) {
-      // the producers are idle until the accumulators are complete: pull the residual lines this warp will add
-      // into L2 now (one 128-byte line per pixel per warp), so the epilogue loads do not pay HBM latency
-      for (int u = grp; u < nunits; u += NGRP) {
-        const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
-        const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
-        const int cb = m_lo + mb * 128 + q * 32;
-        if (cb >= p.Cout) continue;
-        if (p.res) {
-          const int y = ty0 + g32 * 4 + (lane >> 3), x = tx0 + 8 * pt + (lane & 7);
-          if (y < p.H && x < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cb));
-        } else if (lane < 24) {
-          const int y = ((ty0 + g32 * 4) >> 1) - 1 + lane / 6, x = ((tx0 + 8 * pt) >> 1) - 1 + lane % 6;
-          if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + cb));
-        }
-      }
-    }
-    mbar_wait_relaxed(acc_full, 0);
-    const long long t_e1 = dbg ? clock64() : 0;
-    tc_fence_after();
-    const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
-    const float asc = c.acc_scale * inv_alpha;
-    double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
-    for (int u = grp; u < nunits; u += NGRP) {
-      const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
-      const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
-      const int cout = m_lo + mb * 128 + q * 32 + lane;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
+// Epilogue of ONE unit = the 32 accumulator columns (4 rows x 8 pixels at (uy0, ux0)) of output channel `cout` held by this
+// thread: out = (acc * asc + bias + temb [+ residual | FIR_up(half-resolution residual)]) * out_scale, stored NHWC (or
+// channel-major), with the sum / sum of squares of what was stored (GroupNorm statistics of the output tensor).
+__device__ __forceinline__ float2 epilogue_unit(const ConvParams& p, const uint32_t (&r)[32], int cout, int b, const float* tembp, float asc,
+                                                int uy0, int ux0) {
+      const int Hl = p.H >> 1, Wl = p.W >> 1;         // extents of the half-resolution residual (res_up)
+      float fs, fq;
       const bool cok = cout < p.Cout;                // rows beyond Cout are zero padding of the weight image
       float add = 0.f;
       if (p.bias && cok) add += __ldg(p.bias + cout);
       if (tembp && cok) add += __ldg(tembp + cout);
-      float fs = 0.f, fq = 0.f;
-      const int uy0 = ty0 + g32 * 4, ux0 = tx0 + 8 * pt;       // the unit is a 4-row x 8-pixel patch
+      fs = 0.f; fq = 0.f;
       float rv[32];
       const bool have_res = (p.res != nullptr) | (p.res_up != nullptr);
       if (p.res_up) {
@@ -820,6 +591,266 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
           }
         }
       }
+      return make_float2(fs, fq);
+}
+
+// MAXU = halo pixels per producer thread (ceil(np / (32 NPW))); MINB = CTAs per SM.  MINB = 1: one CTA per SM owning
+// all 512 TMEM columns; MINB = 2: two co-resident CTAs with 256 columns each, so that one CTA's epilogue (TMEM drain +
+// global stores) overlaps the other's MMA main loop on the shared tensor pipe.
+// NPW: activation-producer warps (all of them run the epilogue afterwards); warp NPW = weight producer,
+// warp NPW + 1 = TMEM allocator + MMA issuer.
+// PREC: operand split (TcpCfg::prec), compiled in so that each instantiation only carries its own conversion code.
+template <int MAXU, int MINB, int NPW, int PREC>
+__global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+  constexpr int P_PRODUCERS = NPW * 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t w_base = a_base + c.sa * c.a_stage;
+  const uint32_t bar_base = w_base + c.sw * c.w_stage;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
+  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };
+  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 2 * c.sw);
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / c.tiles_x) * c.rows;
+  const int tx0 = (tile % c.tiles_x) * 8 * c.npt;
+  const int m_lo = blockIdx.y * 128 * c.nmb;       // first output channel (row of the padded weight image) of this CTA
+  const int Mpad = tc_mpad(p.Cout);
+  const int b = blockIdx.z;
+
+  if (tid == 0) {
+    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), P_PRODUCERS); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  constexpr uint32_t TMEM_COLS = MINB == 1 ? 512 : 256;
+  if (warp == NPW + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < NPW) {
+    // ---- per-sample operand scale alpha = 2^-e <= 1 (ConvParams::raw_ms): rms of the largest raw group brought down to <= 2^9,
+    // which leaves fp16 (max 2^16) a factor 128 for peaks; alpha = 1 (no extra instruction below) up to rms 512
+    float alpha = 1.0f, inv_alpha = 1.0f;
+    if (p.raw_ms) {
+      float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (m > 262144.0f && m < 3.0e38f) {                      // rms > 2^9
+        const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;        // m = f 2^ex, f in [0.5, 1)
+        int e = (ex + 1) / 2 - 9;                              // ceil(log2(rms)) - 9
+        e = e < 0 ? 0 : (e > 60 ? 60 : e);
+        alpha = __uint_as_float((uint32_t)(127 - e) << 23);
+        inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
+      }
+    }
+    // =================================== activation producers ==========================================
+    // Each thread owns up to 3 halo pixels per stage and handles all 16 channels (64 contiguous bytes) of each.
+    // All global loads of a stage are issued before any is consumed (memory-level parallelism), and the next
+    // chunk's lines are prefetched into L2 while this one is converted.
+    int stage = 0;
+    uint32_t phase = 0;
+    int upix[MAXU];                                        // global pixel index (b, y, x) or -1 (outside / unused)
+    uint32_t uoff[MAXU];
+    bool uinterior[MAXU];
+#pragma unroll
+    for (int i = 0; i < MAXU; ++i) {
+      const int ps = tid + i * P_PRODUCERS;
+      upix[i] = -2;                                        // -2: slot not present
+      uoff[i] = (uint32_t)ps * 16u;
+      uinterior[i] = false;
+      if (ps < c.np) {
+        const int hy = ps / c.hx, hxx = ps - hy * c.hx;
+        const int y = ty0 + hy - 1, x = tx0 + hxx - 1;
+        uinterior[i] = !(hy == 0 || hy == c.hy - 1 || hxx == 0 || hxx == c.hx - 1);
+        upix[i] = ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
+      }
+    }
+    auto split_store = [&](const float (&v)[8], bool valid, uint32_t off) {   // 8 channels of one pixel -> hi plane, lo plane
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        float r[8];
+        hi.x = pack_bf16x2(v[0], v[1], r[0], r[1]);
+        hi.y = pack_bf16x2(v[2], v[3], r[2], r[3]);
+        hi.z = pack_bf16x2(v[4], v[5], r[4], r[5]);
+        hi.w = pack_bf16x2(v[6], v[7], r[6], r[7]);
+        float d0, d1;
+        lo.x = pack_bf16x2(r[0], r[1], d0, d1);
+        lo.y = pack_bf16x2(r[2], r[3], d0, d1);
+        lo.z = pack_bf16x2(r[4], r[5], d0, d1);
+        lo.w = pack_bf16x2(r[6], r[7], d0, d1);
+      }
+      st_shared_v4(off, hi);
+      st_shared_v4(off + c.a_half, lo);
+    };
+    // prec 1: the 8 channels of one pixel -> fp16 k-core of the half's plane; the fp8 bytes of both 8-channel groups of a
+    // unit are stored together (16 bytes per pixel and fp8 plane k-core)
+    constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
+    ChunkIter it(p, PREC);
+    int si, chk;
+#if STORM_TC_PRODUCER_TIMING
+    const bool pdbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    long long t_empty = 0, t_cv0 = 0, t_cv1 = 0, t_is = 0;     // cycles: waiting for a free stage / load wait + convert + store per segment / issuing loads
+#else
+    constexpr bool pdbg = false;
+    long long t_empty = 0, t_cv0 = 0, t_cv1 = 0, t_is = 0;
+#endif
+    while (it.next(si, chk)) {
+      const ConvSeg& s = p.seg[si];
+      const int C = s.C0 + s.C1;
+      const bool full_halo = s.taps == 9;
+#pragma unroll 1
+      for (int hsel = 0; hsel < NH; ++hsel) {
+        const int c0 = chk * (16 * NH) + 16 * hsel;
+        const float* src;
+        int Cs, cl;
+        if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
+        // ---- issue all loads of this stage
+        const long long t_a = pdbg ? clock64() : 0;
+        float4 raw[MAXU][4];
+#pragma unroll
+        for (int i = 0; i < MAXU; ++i) {
+          if (upix[i] >= 0 && (full_halo || uinterior[i])) {
+            const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix[i] * Cs + cl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[i][j] = __ldg(gp + j);
+          }
+        }
+        // ---- L2 prefetch of the next chunk in schedule order (once per stage; a 32-channel chunk is one 128-byte line per
+        // pixel).  Looking further ahead (2, 4, 8 chunks) was measured and changes nothing: profiles/r2_bench_history.md.
+        if (hsel == 0) {
+          ChunkIter peek = it;
+          int nsi, nch;
+          if (peek.next(nsi, nch)) {
+            const ConvSeg& ns = p.seg[nsi];
+            const int n0c = nch * (16 * NH);
+            const float* nsrc;
+            int nCs, ncl;
+            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+            const bool nfull = ns.taps == 9;
+#pragma unroll
+            for (int i = 0; i < MAXU; ++i)
+              if (upix[i] >= 0 && (nfull || uinterior[i]))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix[i] * nCs + ncl));
+          }
+        }
+        float sc[16], sh[16];
+        if (s.ss) {
+          const float4* sp = reinterpret_cast<const float4*>(s.ss + ((size_t)b * C + c0) * 2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = __ldg(sp + j);
+            sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+          }
+        }
+        const long long t_b = pdbg ? clock64() : 0;
+        if (hsel == 0) mbar_wait_relaxed(a_empty(stage), phase ^ 1);
+        long long t_c = 0;
+        if (pdbg) {
+          t_c = clock64();
+          t_is += t_b - t_a;
+          t_empty += t_c - t_b;
+        }
+        const uint32_t st_base = a_base + stage * c.a_stage;
+#pragma unroll
+        for (int i = 0; i < MAXU; ++i) {
+          if (upix[i] == -2 || !(full_halo || uinterior[i])) continue;
+          uint2 a8[2], l8[2];                                            // prec 1: fp8 bytes of the two 8-channel groups
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const uint32_t off = st_base + (uint32_t)(kh * c.np) * 16u + uoff[i];
+            const bool valid = upix[i] >= 0;
+            const float4 v0 = raw[i][2 * kh], v1 = raw[i][2 * kh + 1];
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (valid) {
+              if (s.ss) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[kh * 8 + j], sh[kh * 8 + j]);
+              }
+              if (s.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+              }
+              if (alpha != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= alpha;
+              }
+            }
+            if constexpr (PREC == 1) {
+              uint4 h16 = make_uint4(0, 0, 0, 0);
+              a8[kh] = make_uint2(0, 0);
+              l8[kh] = make_uint2(0, 0);
+              if (valid) split_f16f8(v, h16, a8[kh], l8[kh]);
+              st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);         // f16 plane of this half, k-core kh
+            } else {
+              split_store(v, valid, off);
+            }
+          }
+          if constexpr (PREC == 1) {       // fp8 planes: k-core hsel holds the 16 channels of this half
+            const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * c.np) * 16u + uoff[i];
+            st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
+            st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
+          }
+        }
+        if (pdbg) { if (si == 0) t_cv0 += clock64() - t_c; else t_cv1 += clock64() - t_c; }
+        if (hsel == NH - 1) {
+          fence_async_shared();
+          mbar_arrive(a_full(stage));
+          if (++stage == c.sa) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    // =================================== epilogue (every producer warp) ==================================
+    {
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    const long long t_e0 = dbg ? clock64() : 0;
+    if (dbg) { p.dbg[6] = t_is; p.dbg[7] = 0; p.dbg[8] = t_empty; p.dbg[9] = t_cv0; p.dbg[10] = t_cv1; }
+    constexpr int NGRP = NPW / 4;                   // warps sharing a TMEM lane quadrant split the work units
+    const int q = warp & 3, grp = warp >> 2;        // TMEM lane quadrant / which share of the work units
+    const int nacc = c.npt * c.nmb;
+    const int units_per_acc = c.ncol >> 5;          // 32-pixel groups per accumulator
+    const int nunits = nacc * units_per_acc;
+    const int Hl = p.H >> 1, Wl = p.W >> 1;         // extents of the half-resolution residual (res_up)
+    if ((p.res || p.res_up) && !p.out_cm) {
+      // the producers are idle until the accumulators are complete: pull the residual lines this warp will add
+      // into L2 now (one 128-byte line per pixel per warp), so the epilogue loads do not pay HBM latency
+      for (int u = grp; u < nunits; u += NGRP) {
+        const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
+        const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
+        const int cb = m_lo + mb * 128 + q * 32;
+        if (cb >= p.Cout) continue;
+        if (p.res) {
+          const int y = ty0 + g32 * 4 + (lane >> 3), x = tx0 + 8 * pt + (lane & 7);
+          if (y < p.H && x < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + cb));
+        } else if (lane < 24) {
+          const int y = ((ty0 + g32 * 4) >> 1) - 1 + lane / 6, x = ((tx0 + 8 * pt) >> 1) - 1 + lane % 6;
+          if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + cb));
+        }
+      }
+    }
+    mbar_wait_relaxed(acc_full, 0);
+    const long long t_e1 = dbg ? clock64() : 0;
+    tc_fence_after();
+    const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
+    const float asc = c.acc_scale * inv_alpha;
+    double s_sum[2] = {0.0, 0.0}, s_sq[2] = {0.0, 0.0};   // per M block handled by this thread
+    for (int u = grp; u < nunits; u += NGRP) {
+      const int ai = u / units_per_acc, g32 = u - ai * units_per_acc;
+      const int pt = ai / c.nmb, mb = ai - pt * c.nmb;
+      const int cout = m_lo + mb * 128 + q * 32 + lane;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * c.ncol + g32 * 32), r);
+      const float2 st = epilogue_unit(p, r, cout, b, tembp, asc, ty0 + g32 * 4, tx0 + 8 * pt);
+      const float fs = st.x, fq = st.y;
       s_sum[mb] += (double)fs;
       s_sq[mb] += (double)fq;
     }
@@ -879,6 +910,431 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
   tc_fence_before();
   __syncthreads();
   if (warp == NPW + 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =====================================================================================================
+// Mode Q: the persistent form of mode P.  One CTA per SM walks over (pixel tile, 128-channel block) tiles of
+// N = 256 pixels (32 rows x 8 columns) x M = 128 output channels; the accumulator (256 TMEM columns) is DOUBLE
+// BUFFERED, and the three roles run ahead of each other across tile boundaries:
+//   warps 0-10  activation producers: one halo pixel per thread (10 x 34 = 340 of 352 threads), global loads of
+//               half-stage i+1 in flight while half-stage i is converted (register double buffer, possible because
+//               a thread owns ONE pixel), GroupNorm scale/shift of the tile's sample staged in shared memory;
+//   warp 11     TMEM allocation + the single-thread MMA issue loop; starts tile i+1 as soon as its accumulator
+//               buffer has been drained, i.e. while the epilogue of tile i is still storing;
+//   warps 12-15 epilogue: one warp per TMEM lane quadrant, tcgen05.ld -> bias / temb / residual / scale -> stores +
+//               GroupNorm partial sums, overlapped with the main loop of the next tile;
+//   warp 16     weight producer (cp.async.bulk ring, as in mode P).  Measured: letting the MMA thread refill the ring
+//               itself halves the kernel's speed - a cp.async.bulk costs the issuing thread ~240 cycles
+//               (profiles/r2_bench_history.md);
+//   warps 17-19 idle: registers are allocated per warpgroup, and the 640-thread CTA starts at 96 registers per thread;
+//               setmaxnreg then moves them where they are needed: producers + MMA 104, epilogue 120, weight warpgroup 40 (384 x 104 + 128 x 120 + 128 x 40 <= 640 x 96).
+// What mode P loses per tile - pipeline fill (~7k cycles), the drained tensor pipe during the epilogue (~12k) and the CTA
+// launch / TMEM allocation / barrier init (~5k) of a 60-120k-cycle tile - is paid once per CTA here.  The price: tiles are
+// 128 channels tall, so a 256-channel layer converts every halo tile twice (once per channel block).
+// =====================================================================================================
+constexpr int Q_NPW = 11, Q_EPW = 4;
+constexpr int Q_WARP_MMA = Q_NPW, Q_WARP_EPI = 12, Q_WARP_W = 16;     // warpgroups: {0-10 producers, 11 MMA} {12-15 epilogue} {16 weights, 17-19 idle}
+constexpr int Q_THREADS = 20 * 32;                        // 640
+constexpr int Q_PRODUCERS = Q_NPW * 32;                   // 352
+constexpr int Q_HX = 10, Q_HY = 34, Q_NP = Q_HX * Q_HY;  // halo tile of one 32 x 8 pixel tile
+constexpr int Q_NCOL = 256;
+
+struct TcqCfg {
+  int prec;
+  int sa, sw;
+  int a_plane, a_stage, w_plane, w_stage;
+  int tiles_x, tiles_y, msplit;      // pixel tiles per row / column of one sample, 128-channel blocks
+  int ntiles, tpg, ngroups;          // tiles = B * tiles_y * tiles_x * msplit; consecutive tiles per CTA visit; groups
+  int ss_c;                          // channels of the staged scale/shift table (0: segment 0 has none)
+  float acc_scale;
+};
+
+struct QTile { int b, ty0, tx0, m_lo, pt_in_b; };
+__device__ __forceinline__ QTile q_tile(const TcqCfg& c, int tile) {
+  QTile t;
+  const int mb = tile % c.msplit;
+  int pt = tile / c.msplit;
+  const int per_b = c.tiles_x * c.tiles_y;
+  t.b = pt / per_b;
+  pt -= t.b * per_b;
+  t.pt_in_b = pt;
+  t.ty0 = (pt / c.tiles_x) * 32;
+  t.tx0 = (pt % c.tiles_x) * 8;
+  t.m_lo = mb * 128;
+  return t;
+}
+// tile sequence of this CTA: groups blockIdx.x, blockIdx.x + gridDim.x, ... of `tpg` consecutive tiles each
+struct QTileIter {
+  int g, j;
+  __device__ QTileIter() : g((int)blockIdx.x), j(-1) {}
+  __device__ bool next(const TcqCfg& c, int& tile) {
+    for (;;) {
+      if (++j >= c.tpg) { j = 0; g += (int)gridDim.x; }
+      if (g >= c.ngroups) return false;
+      tile = g * c.tpg + j;
+      if (tile < c.ntiles) return true;
+    }
+  }
+};
+
+__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(Q_PRODUCERS) : "memory"); }
+
+template <int PREC>
+__global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, TcqCfg c) {
+  constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t w_base = a_base + c.sa * c.a_stage;
+  const uint32_t ss_base = w_base + c.sw * c.w_stage;                       // two tables of ss_c (scale, shift) pairs
+  const uint32_t bar_base = ss_base + 2u * (uint32_t)c.ss_c * 8u;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
+  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };
+  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };
+  auto acc_full = [&](int i) { return bar_base + 8u * (2 * c.sa + 2 * c.sw + i); };
+  auto acc_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + 2 * c.sw + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * c.sa + 2 * c.sw + 4);
+  const int Mpad = tc_mpad(p.Cout);
+
+  if (tid == 0) {
+    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), Q_PRODUCERS); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), Q_EPW); }
+    fence_barrier_init();
+  }
+  if (warp == Q_WARP_MMA) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // register re-allocation per warpgroup: every warp of a warpgroup executes the same setmaxnreg, and each role's code
+  // sits INSIDE the branch that holds its setmaxnreg (ptxas budgets registers by dominance)
+  if (warp < Q_WARP_EPI) {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  if (warp < Q_NPW) {
+    // =================================== activation producers ==========================================
+    const int ps = tid;                                     // halo pixel slot of this thread
+    const bool present = ps < Q_NP;
+    const int hy = ps / Q_HX, hxx = ps - hy * Q_HX;
+    const bool interior = present && !(hy == 0 || hy == Q_HY - 1 || hxx == 0 || hxx == Q_HX - 1);
+    const uint32_t uoff = (uint32_t)ps * 16u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int ntile_c = 0;
+    QTileIter ti;
+    int tile;
+    while (ti.next(c, tile)) {
+      // ---- new tile: this thread's pixel, the sample's GroupNorm table (shared memory, double buffered), operand scale
+      const QTile t = q_tile(c, tile);
+      const int y = t.ty0 + hy - 1, x = t.tx0 + hxx - 1;
+      const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (t.b * p.H + y) * p.W + x : -1;
+      const bool valid = upix >= 0;
+      const uint32_t tab0 = ss_base + (uint32_t)(ntile_c & 1) * (uint32_t)c.ss_c * 8u;
+      if (c.ss_c) {
+        const float2* gs = reinterpret_cast<const float2*>(p.seg[0].ss) + (size_t)t.b * c.ss_c;
+        for (int i = tid; i < c.ss_c; i += Q_PRODUCERS) {
+          const float2 v = __ldg(gs + i);
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab0 + 8u * i), "f"(v.x), "f"(v.y) : "memory");
+        }
+      }
+      float alpha = 1.0f;
+      if (p.raw_ms) {
+        float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)t.b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > 262144.0f && m < 3.0e38f) {
+          const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
+          int e = (ex + 1) / 2 - 9;
+          e = e < 0 ? 0 : (e > 60 ? 60 : e);
+          alpha = __uint_as_float((uint32_t)(127 - e) << 23);
+        }
+      }
+      bar_sync_producers();                                  // table visible to every producer; also orders table reuse
+      ++ntile_c;
+
+      ChunkIter it(p, PREC);
+      int si, chk;
+      while (it.next(si, chk)) {
+        const ConvSeg& s = p.seg[si];
+        const bool active = present && (s.taps == 9 || interior);
+        const int c0 = chk * (16 * NH);
+        // ---- all loads of this K chunk (one pixel, 16 * NH channels) at once: one round trip per stage
+        float4 raw[4 * NH];
+        if (active && valid) {
+          const float* src;
+          int Cs, cl;
+          if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
+          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
+#pragma unroll
+          for (int j = 0; j < 4 * NH; ++j) raw[j] = __ldg(gp + j);
+        }
+        // ---- L2 prefetch of the next chunk in schedule order (a 32-channel chunk is one 128-byte line per pixel)
+        {
+          ChunkIter peek = it;
+          int nsi, nch;
+          if (valid && peek.next(nsi, nch)) {
+            const ConvSeg& ns = p.seg[nsi];
+            if (ns.taps == 9 || interior) {
+              const int n0c = nch * (16 * NH);
+              const float* nsrc;
+              int nCs, ncl;
+              if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix * nCs + ncl));
+            }
+          }
+        }
+        mbar_wait_relaxed(a_empty(stage), phase ^ 1);
+        const uint32_t st_base = a_base + stage * c.a_stage;
+        if (active) {
+#pragma unroll
+          for (int hsel = 0; hsel < NH; ++hsel) {
+            const uint32_t tab = tab0 + 8u * (uint32_t)(c0 + 16 * hsel);
+            uint2 a8[2], l8[2];
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+              const uint32_t off = st_base + (uint32_t)(kh * Q_NP) * 16u + uoff;
+              const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
+              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              if (valid) {
+                if (s.ss) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float4 t4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                                 : "r"(tab + (uint32_t)(kh * 8 + 2 * j) * 8u));
+                    v[2 * j] = fmaf(v[2 * j], t4.x, t4.y);
+                    v[2 * j + 1] = fmaf(v[2 * j + 1], t4.z, t4.w);
+                  }
+                }
+                if (s.silu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+                }
+                if (alpha != 1.0f) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= alpha;
+                }
+              }
+              if constexpr (PREC == 1) {
+                uint4 h16 = make_uint4(0, 0, 0, 0);
+                a8[kh] = make_uint2(0, 0);
+                l8[kh] = make_uint2(0, 0);
+                if (valid) split_f16f8(v, h16, a8[kh], l8[kh]);
+                st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);          // f16 plane of this half, k-core kh
+              } else {
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                if (valid) {
+                  float rr[8], d0, d1;
+                  hi.x = pack_bf16x2(v[0], v[1], rr[0], rr[1]);
+                  hi.y = pack_bf16x2(v[2], v[3], rr[2], rr[3]);
+                  hi.z = pack_bf16x2(v[4], v[5], rr[4], rr[5]);
+                  hi.w = pack_bf16x2(v[6], v[7], rr[6], rr[7]);
+                  lo.x = pack_bf16x2(rr[0], rr[1], d0, d1);
+                  lo.y = pack_bf16x2(rr[2], rr[3], d0, d1);
+                  lo.z = pack_bf16x2(rr[4], rr[5], d0, d1);
+                  lo.w = pack_bf16x2(rr[6], rr[7], d0, d1);
+                }
+                st_shared_v4(off, hi);
+                st_shared_v4(off + (uint32_t)c.a_plane, lo);
+              }
+            }
+            if constexpr (PREC == 1) {       // fp8 planes: k-core hsel holds the 16 channels of this half
+              const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * Q_NP) * 16u + uoff;
+              st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
+              st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
+            }
+          }
+        }
+        fence_async_shared();
+        mbar_arrive(a_full(stage));
+        if (++stage == c.sa) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // =================================== MMA issuer (warp 11) ===========================================
+    if (lane == 0) {
+      const uint32_t idesc = PREC ? make_idesc_fmt(Q_NCOL, 0, 0) : make_idesc(Q_NCOL);
+      const uint32_t idesc8 = make_idesc_fmt(Q_NCOL, 0, 1);
+      const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = (uint32_t)c.w_plane >> 4;
+      const uint64_t pd_const = make_desc(0, (uint32_t)Q_NP * 16u, (uint32_t)Q_HX * 16u);   // pixel operand (B)
+      const uint64_t wd_const = make_desc(0, 128, 256);                                    // weight operand (A)
+      const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
+      const uint32_t a_base16 = (a_base >> 4) & 0x3FFFu, w_base16 = (w_base >> 4) & 0x3FFFu;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      uint32_t eph[2] = {0, 0};
+      int buf = 0;
+      const bool dbg = p.dbg && blockIdx.x == 0;
+      long long t_wa = 0, t_ww = 0, t_we = 0;
+      const long long t_start = dbg ? clock64() : 0;
+      int ntile = 0;
+      QTileIter ti;
+      int tile;
+      while (ti.next(c, tile)) {
+        long long t0 = dbg ? clock64() : 0;
+        mbar_wait(acc_empty(buf), eph[buf] ^ 1);                              // the epilogue has drained this accumulator buffer
+        if (dbg) t_we += clock64() - t0;
+        eph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * Q_NCOL;
+        uint32_t acc = 0;
+        ChunkIter it(p, PREC);
+        int si, ch;
+        while (it.next(si, ch)) {
+          const bool k3 = p.seg[si].taps == 9;
+          t0 = dbg ? clock64() : 0;
+          mbar_wait(a_full(sa), pa);
+          if (dbg) t_wa += clock64() - t0;
+          tc_fence_after();
+          const uint32_t a16 = a_base16 + sa * a_stage16;
+          const int ntap = k3 ? 9 : 1;
+          uint32_t toff = k3 ? 0u : (uint32_t)(Q_HX + 1);
+          int dx = 0;
+          for (int tap = 0; tap < ntap; ++tap) {
+            t0 = dbg ? clock64() : 0;
+            mbar_wait(w_full(sw), pw);
+            if (dbg) t_ww += clock64() - t0;
+            tc_fence_after();
+            const uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
+            const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff);
+            if constexpr (PREC == 1) {
+              umma_bf16(d, w_hi, p_hi, idesc, acc);
+              umma_bf16(d, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
+              umma_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
+              umma_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
+            } else {
+              umma_bf16(d, w_hi, p_hi, idesc, acc);
+              umma_bf16(d, w_hi, p_hi + a_pl16, idesc, 1u);
+              umma_bf16(d, w_hi + w_pl16, p_hi, idesc, 1u);
+            }
+            acc = 1u;
+            umma_commit(w_empty(sw));
+            if (++sw == c.sw) { sw = 0; pw ^= 1; }
+            if (++dx == 3) { dx = 0; toff += (uint32_t)Q_HX - 2u; } else { toff += 1u; }
+          }
+          umma_commit(a_empty(sa));
+          if (++sa == c.sa) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(acc_full(buf));
+        buf ^= 1;
+        ++ntile;
+      }
+      if (dbg) {
+        p.dbg[0] = clock64() - t_start;   // whole issue loop of CTA 0 (all its tiles)
+        p.dbg[1] = t_wa;                  // waiting for activation stages
+        p.dbg[2] = t_ww;                  // waiting for weight stages
+        p.dbg[3] = t_we;                  // waiting for a drained accumulator buffer
+        p.dbg[4] = ntile;
+      }
+    }
+  }
+  } else if (warp >= Q_WARP_W) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // =================================== weight producer (warp 16; 17-19 idle) ============================
+    if (warp == Q_WARP_W && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t q_stride = (size_t)(PREC ? 128 : 64) * Mpad;
+      QTileIter ti;
+      int tile;
+      while (ti.next(c, tile)) {
+        const int m_lo = q_tile(c, tile).m_lo;
+        ChunkIter it(p, PREC);
+        int si, ch;
+        while (it.next(si, ch)) {
+          const ConvSeg& s = p.seg[si];
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32 + (size_t)ch * s.taps * q_stride;
+          for (int tap = 0; tap < s.taps; ++tap) {
+            mbar_wait(w_empty(stage), phase ^ 1);
+            const uint32_t dst = w_base + stage * c.w_stage;
+            mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
+            if constexpr (PREC == 1) {
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl)
+                bulk_g2s(dst + pl * c.w_plane, base + tap * q_stride + (size_t)pl * 32 * Mpad, (uint32_t)c.w_plane, w_full(stage));
+            } else {
+              bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_plane, w_full(stage));
+              bulk_g2s(dst + c.w_plane, base + tap * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_plane, w_full(stage));
+            }
+            if (++stage == c.sw) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    // =================================== epilogue warps (12-15) ===========================================
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int per_b = c.tiles_x * c.tiles_y;
+    int buf = 0;
+    uint32_t fph[2] = {0, 0};
+    QTileIter ti;
+    int tile;
+    const bool dbg = p.dbg && blockIdx.x == 0 && warp == Q_WARP_EPI && lane == 0;
+    long long t_wait = 0, t_work = 0;
+    while (ti.next(c, tile)) {
+      const QTile t = q_tile(c, tile);
+      const int cout = t.m_lo + q * 32 + lane;
+      const bool cok = cout < p.Cout;
+      const float* tembp = p.temb ? p.temb + (size_t)t.b * p.temb_stride : nullptr;
+      float inv_alpha = 1.0f;
+      if (p.raw_ms) {
+        float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)t.b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > 262144.0f && m < 3.0e38f) {
+          const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
+          int e = (ex + 1) / 2 - 9;
+          e = e < 0 ? 0 : (e > 60 ? 60 : e);
+          inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
+        }
+      }
+      const float asc = c.acc_scale * inv_alpha;
+      if (p.res && !p.out_cm && t.m_lo + q * 32 < p.Cout) {
+        // pull the residual lines this warp will add into L2 while the tile's MMAs are still running
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+          const int y = t.ty0 + u * 4 + (lane >> 3), x = t.tx0 + (lane & 7);
+          if (y < p.H && x < p.W)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)t.b * p.H + y) * p.W + x) * p.Cout + t.m_lo + q * 32));
+        }
+      }
+      long long t0 = dbg ? clock64() : 0;
+      mbar_wait_relaxed(acc_full(buf), fph[buf]);
+      fph[buf] ^= 1;
+      tc_fence_after();
+      long long t1 = dbg ? clock64() : 0;
+      double s_sum = 0.0, s_sq = 0.0;
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Q_NCOL + u * 32), r);
+        if (u == 7) {                                     // every column of this buffer is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(buf));
+        }
+        const float2 st = epilogue_unit(p, r, cout, t.b, tembp, asc, t.ty0 + u * 4, t.tx0);
+        s_sum += (double)st.x;
+        s_sq += (double)st.y;
+      }
+      if (p.stats_out && cok) {
+        double* o = p.stats_out + (((size_t)t.b * p.stats_chunks + t.pt_in_b) * p.Cout + cout) * 2;
+        o[0] = s_sum;
+        o[1] = s_sq;
+      }
+      if (dbg) { t_wait += t1 - t0; t_work += clock64() - t1; }
+      buf ^= 1;
+      (void)per_b;
+    }
+    if (dbg) { p.dbg[5] = t_work; p.dbg[6] = t_wait; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == Q_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 int g_tc_force_per_sm = 3;   // see choose_cfg_p (STORM_B200_TC_PER_SM)
@@ -979,6 +1435,77 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
 
 }  // namespace
 
+// ---- mode Q (persistent) ------------------------------------------------------------------------------
+static int num_sms() {
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    int v = 0;
+    n[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+  }
+  return n[dev];
+}
+
+static bool choose_cfg_q(const ConvParams& p, TcqCfg& c) {
+  if (p.Cout < 1 || p.Cout > 256) return false;
+  if (p.H < 17 || p.W < 8) return false;                     // a 32 x 8 tile would be mostly padding: mode P's 16-row tiles
+  for (int i = 0; i < p.nseg; ++i) {
+    const ConvSeg& s = p.seg[i];
+    if (!s.wtc || s.C0 % 16 != 0 || s.C1 % 16 != 0 || s.C0 < 16 || (s.taps != 9 && s.taps != 1)) return false;
+  }
+  if (p.nseg == 2 && p.seg[1].ss) return false;              // the staged GroupNorm table belongs to segment 0
+  c.prec = p.seg[0].wprec;
+  for (int i = 0; i < p.nseg; ++i) {
+    const ConvSeg& s = p.seg[i];
+    if (s.wprec != c.prec) return false;
+    if (c.prec == 1 && (s.C0 % 32 != 0 || s.C1 % 32 != 0)) return false;
+    if (c.prec == 1 && s.wscale != p.seg[0].wscale) return false;
+  }
+  c.acc_scale = c.prec == 1 ? 1.0f / p.seg[0].wscale : 1.0f;
+  if (p.res && p.res_up) return false;
+  if (p.res_up && ((p.H | p.W) & 1)) return false;
+  c.ss_c = p.seg[0].ss ? p.seg[0].C0 + p.seg[0].C1 : 0;
+  if (c.ss_c > 1024) return false;
+  c.a_plane = Q_NP * 32;
+  c.w_plane = 4096;
+  if (c.prec == 1) { c.a_stage = 4 * c.a_plane; c.w_stage = 4 * c.w_plane; c.sa = 3; c.sw = 5; }
+  else { c.a_stage = 2 * c.a_plane; c.w_stage = 2 * c.w_plane; c.sa = 4; c.sw = 8; }
+  c.tiles_x = ceil_div(p.W, 8);
+  c.tiles_y = ceil_div(p.H, 32);
+  c.msplit = tc_mpad(p.Cout) / 128;
+  const long nt = (long)p.B * c.tiles_x * c.tiles_y * c.msplit;
+  if (nt > (1L << 30)) return false;
+  c.ntiles = (int)nt;
+  // both channel blocks of a pixel tile in one CTA visit (the second one finds its activations in L2) as long as
+  // that still gives every SM something to do
+  c.tpg = (c.msplit > 1 && nt / c.msplit >= num_sms()) ? c.msplit : 1;
+  c.ngroups = ceil_div(c.ntiles, c.tpg);
+  return true;
+}
+// Measured policy (per-launch times of whole benchmark runs under STORM_B200_TCQ=0 / 1, profiles/r2_bench_history.md): the
+// persistent kernel wins where mode P cannot hide its per-tile fill / drain / launch costs - layers of at most 128 output
+// channels (one channel block: no halo tile is converted twice; -10..-15 % on the 256 x 256 levels) and the small
+// 32 x 32 levels (-15..-40 %) - and loses on the 256-channel layers at 64 x 64 and above, where converting every halo
+// tile once per channel block costs power (SM clock 1.57 instead of 1.87 GHz under the 1 kW cap), and on the 1x1
+// projection / output-branch GEMMs, which are bound by HBM latency either way.
+static bool tcq_policy(const ConvParams& p, const TcqCfg& c) {
+  if (p.seg[0].taps != 9) return false;
+  if (c.msplit == 1) return true;
+  return (long)p.B * p.H * p.W <= 16384;
+}
+static int tcq_smem_bytes(const TcqCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 2 * c.sw + 4) + 16; }
+
+// which kernel runs a launch.  STORM_B200_TCQ: 0 = mode P only, 1 = mode Q wherever it is eligible, 2 (default) = the measured
+// policy below.
+static bool use_mode_q(const ConvParams& p, TcqCfg& cq) {
+  static const int mode = [] { const char* e = getenv("STORM_B200_TCQ"); return e ? atoi(e) : 2; }();
+  if (mode == 0 || !choose_cfg_q(p, cq)) return false;
+  if (mode == 1) return true;
+  return tcq_policy(p, cq);
+}
+
 // epilogue warp groups per TMEM lane quadrant (= GroupNorm partial-sum chunks per tile) of the kernel variant launched
 static int tc_ngrp(const TcpCfg& c) { return c.per_sm == 1 ? 3 : 2; }
 
@@ -988,6 +1515,8 @@ bool conv_tc_eligible(const ConvParams& p) {
 }
 
 int conv_tc_stats_chunks(const ConvParams& p) {
+  TcqCfg cq;
+  if (use_mode_q(p, cq)) return cq.tiles_x * cq.tiles_y;
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return 0;
   return tc_ngrp(cp) * cp.tiles_x * cp.tiles_y;
@@ -1004,15 +1533,28 @@ int conv_tc_init_device() {
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return 0;
 }
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   STORM_TRY(conv_tc_init_device());
+  if (p.out_cm && (p.res || p.res_up)) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
+  TcqCfg cq;
+  if (use_mode_q(p, cq)) {
+    if (p.stats_out && p.stats_chunks != cq.tiles_x * cq.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+    const int smem = tcq_smem_bytes(cq);
+    if (smem > 227 * 1024 - 1024) return fail(-1, "conv_tc: mode Q shared-memory plan does not fit");
+    const int grid = cq.ngroups < num_sms() ? cq.ngroups : num_sms();
+    if (cq.prec) conv_tcq_kernel<1><<<grid, Q_THREADS, smem, st>>>(p, cq);
+    else conv_tcq_kernel<0><<<grid, Q_THREADS, smem, st>>>(p, cq);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
   TcpCfg cp;
   if (!choose_cfg_p(p, cp)) return fail(-1, "conv_tc: shape not eligible");
-  if (p.out_cm && (p.res || p.res_up)) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
   if (p.stats_out && p.stats_chunks != tc_ngrp(cp) * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);

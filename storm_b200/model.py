@@ -20,6 +20,35 @@ from .data_module import SpecsDataModule
 from .sdes import SDERegistry
 
 
+FROZEN_PARAMS = ("all_modules.0.W",)      # GaussianFourierProjection.W: requires_grad=False (layerspp.py:37)
+
+
+def map_ema_shadow(named_params, shadow):
+    """Pair ``ema.shadow_params`` of a reference checkpoint with the parameters they belong to.
+
+    ``torch_ema`` keeps its shadow list positionally, in ``model.parameters()`` order (sgmse/model.py:55: the EMA is built
+    from ``self.parameters()``; tests/golden/param_order.json pins that order).  Releases differ on whether frozen
+    parameters get a shadow: 0.2 filters on ``requires_grad``, 0.3 (requirements.txt:15) shadows every parameter.  The
+    only frozen parameter on this path is the Fourier ``W``.  Both layouts are accepted, every pair is shape-checked, and
+    anything else raises instead of silently mis-assigning weights.  Returns ``[(name, shadow_tensor), ...]``."""
+    named_params = list(named_params)
+    shadow = list(shadow)
+    trainable = [(n, p) for n, p in named_params if n.split("dnn.")[-1].split("_net.")[-1] not in FROZEN_PARAMS]
+    if len(shadow) == len(named_params):
+        target = named_params
+    elif len(shadow) == len(trainable):
+        target = trainable
+    else:
+        raise RuntimeError(f"checkpoint EMA has {len(shadow)} shadow parameters; the model has {len(named_params)} parameters "
+                           f"({len(trainable)} trainable) - cannot align them")
+    out = []
+    for (n, p), sh in zip(target, shadow):
+        if tuple(sh.shape) != tuple(p.shape):
+            raise RuntimeError(f"checkpoint EMA shadow for '{n}' has shape {tuple(sh.shape)}, expected {tuple(p.shape)}")
+        out.append((n, sh))
+    return out
+
+
 class ScoreModel:
     def __init__(self, backbone: str = "ncsnpp", sde: str = "ouve", lr: float = 1e-4, ema_decay: float = 0.999,
                  t_eps: float = 3e-2, transform: str = "none", nolog: bool = False, num_eval_files: int = 50,
@@ -35,8 +64,8 @@ class ScoreModel:
         self.hparams = dict(backbone=backbone, sde=sde, t_eps=t_eps, **kwargs)
         self._seed = seed
         self._calls = 0
-        self._ema_shadow: Optional[List[torch.Tensor]] = None
-        self._raw_params: Optional[List[torch.Tensor]] = None
+        self._ema_shadow: Optional[list] = None          # [(parameter name, shadow tensor)] from map_ema_shadow
+        self._raw_params: Optional[dict] = None
         self.device = torch.device("cpu")
 
     # ---- nn.Module-like plumbing ----------------------------------------------------------------------------
@@ -62,20 +91,21 @@ class ScoreModel:
     def eval(self, no_ema: bool = False):
         """Swap the EMA shadow weights in for inference unless ``no_ema`` (model.py:97-111)."""
         if self._ema_shadow is not None and not no_ema and self._raw_params is None:
-            params = list(self.dnn.parameters())
-            self._raw_params = [p.detach().clone() for p in params]
+            params = dict(self.dnn.named_parameters())
+            self._raw_params = {n: params[n].detach().clone() for n, _ in self._ema_shadow}
             with torch.no_grad():
-                for p, s in zip(params, self._ema_shadow):
-                    p.copy_(s.to(p.device))
+                for n, s in self._ema_shadow:
+                    params[n].copy_(s.to(params[n].device))
             self.dnn.mark_weights_changed()
         return self
 
     def train(self, mode: bool = True, no_ema: bool = False):
         if mode:
             if self._raw_params is not None:
+                params = dict(self.dnn.named_parameters())
                 with torch.no_grad():
-                    for p, s in zip(self.dnn.parameters(), self._raw_params):
-                        p.copy_(s)
+                    for n, s in self._raw_params.items():
+                        params[n].copy_(s)
                 self._raw_params = None
                 self.dnn.mark_weights_changed()
             return self
@@ -92,7 +122,7 @@ class ScoreModel:
         model.load_state_dict(ckpt["state_dict"], strict=True)
         ema = ckpt.get("ema")
         if ema is not None and ema.get("shadow_params") is not None:
-            model._ema_shadow = [s.detach().clone() for s in ema["shadow_params"]][: len(list(model.dnn.parameters()))]
+            model._ema_shadow = [(n, s.detach().clone()) for n, s in map_ema_shadow(model.dnn.named_parameters(), ema["shadow_params"])]
         return model
 
     def next_seed(self) -> int:
@@ -243,6 +273,52 @@ class ScoreModel:
         return p.device
 
 
+class DiscriminativeModel(ScoreModel):
+    """Predictive baseline of the reference (sgmse/model.py:320-370): the same backbone called once with ``t = 1``, no
+    sampler.  Checkpoints are ScoreModel-shaped (``dnn.*`` keys, ``backbone`` hyper-parameter) and are what
+    ``enhancement.py --mode denoiser-only`` loads (enhancement.py:54-55)."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("discriminative", False)     # the stock DiscriminativeModel keeps the 4-channel conditional NCSN++
+        super().__init__(*args, **kwargs)
+
+    def forward(self, y):                                            # model.py:322-327 (FORCE_STFT_OUT is False for NCSN++)
+        t = torch.ones(y.shape[0], device=y.device)
+        return self.dnn(y, t)
+
+    __call__ = forward
+
+    def _net_input(self, Y):
+        """ScoreModel.__init__ forces ``input_channels=4`` (model.py:47) while ``forward`` hands the backbone Y alone
+        (model.py:326): with the stock 4-channel NCSN++ the reference's own call fails on the channel count, so published
+        discriminative checkpoints necessarily carry a backbone whose real-valued input has 2 channels
+        (``discriminative=True``).  Anything else is reported instead of guessed."""
+        if self.dnn.cfg.in_ch != 2 * Y.shape[1]:
+            raise RuntimeError(f"DiscriminativeModel: the backbone expects {self.dnn.cfg.in_ch} real input channels but the noisy "
+                               f"spectrogram provides {2 * Y.shape[1]} (the reference's DiscriminativeModel.forward has the same "
+                               "mismatch with a 4-channel backbone, sgmse/model.py:326)")
+        return Y
+
+    def enhance(self, y, **ignored_kwargs):
+        """model.py:351-370 for one utterance ``y`` [1, L] -> [L] on the CPU."""
+        return self.enhance_batch(y.reshape(1, -1))[0].cpu()
+
+    def enhance_batch(self, ys, **ignored_kwargs):
+        """[B, L] (or list of equal-length utterances) -> [B, L]: normalise, STFT, one network call, iSTFT."""
+        if not torch.is_tensor(ys):
+            ys = torch.stack([y.reshape(-1) for y in ys])
+        dev = self._device()
+        src = ys.device
+        yd = ys.to(torch.float32)
+        yd = yd.pin_memory().to(dev, non_blocking=True) if not yd.is_cuda else yd
+        sp = self.data_module.spec_config()
+        norm = _native.wave_norm(yd)
+        T_pad = _native.padded_frames(_native.num_frames(yd.shape[1], sp))
+        Y = _native.stft(yd, norm, sp, T_pad).unsqueeze(1)
+        X = self.forward(self._net_input(Y))
+        return self.dnn.engine().istft(X.squeeze(1), norm, yd.shape[1], sp).to(src)
+
+
 class StochasticRegenerationModel:
     """StoRM inference (sgmse/model.py:392-780): a discriminative NCSN++ first estimates ``Y_denoised``; the score
     network, conditioned on ``[Y, Y_denoised]`` (6 real input channels), then runs reverse diffusion around
@@ -263,6 +339,15 @@ class StochasticRegenerationModel:
         self.t_eps, self.condition, self.mode = t_eps, condition, mode
         self.data_module = (data_module_cls or SpecsDataModule)(**kwargs)
         self._seed, self._calls = seed, 0
+        self._ema_shadow: Optional[list] = None
+        self._raw_params: Optional[dict] = None
+
+    def named_parameters(self):
+        """``self.parameters()`` order of the reference module: denoiser_net then score_net (model.py:416-423)."""
+        for name, net in (("denoiser_net", self.denoiser_net), ("score_net", self.score_net)):
+            if net is not None:
+                for n, p in net.named_parameters():
+                    yield f"{name}.{n}", p
 
     def _nets(self):
         return [n for n in (self.denoiser_net, self.score_net) if n is not None]
@@ -273,6 +358,28 @@ class StochasticRegenerationModel:
         return self
 
     def eval(self, no_ema: bool = False):
+        """Swap the EMA shadow weights in unless ``no_ema`` (model.py:517-531)."""
+        if self._ema_shadow is not None and not no_ema and self._raw_params is None:
+            params = dict(self.named_parameters())
+            self._raw_params = {n: params[n].detach().clone() for n, _ in self._ema_shadow}
+            with torch.no_grad():
+                for n, sh in self._ema_shadow:
+                    params[n].copy_(sh.to(params[n].device))
+            for n in self._nets():
+                n.mark_weights_changed()
+        return self
+
+    def train(self, mode: bool = True, no_ema: bool = False):
+        if not mode:
+            return self.eval(no_ema=no_ema)
+        if self._raw_params is not None:
+            params = dict(self.named_parameters())
+            with torch.no_grad():
+                for n, v in self._raw_params.items():
+                    params[n].copy_(v)
+            self._raw_params = None
+            for n in self._nets():
+                n.mark_weights_changed()
         return self
 
     def state_dict(self):
@@ -296,13 +403,8 @@ class StochasticRegenerationModel:
         model = cls(**hp)
         model.load_state_dict(ckpt["state_dict"], strict=True)
         ema = ckpt.get("ema")
-        if ema is not None and ema.get("shadow_params") is not None:      # inference uses the EMA weights (model.py:97-108)
-            params = [p for n in model._nets() for p in n.parameters()]
-            with torch.no_grad():
-                for p, sh in zip(params, ema["shadow_params"]):
-                    p.copy_(sh)
-            for n in model._nets():
-                n.mark_weights_changed()
+        if ema is not None and ema.get("shadow_params") is not None:      # swapped in by eval() (model.py:517-531)
+            model._ema_shadow = [(n, sh.detach().clone()) for n, sh in map_ema_shadow(model.named_parameters(), ema["shadow_params"])]
         return model
 
     def next_seed(self) -> int:
@@ -321,6 +423,63 @@ class StochasticRegenerationModel:
         kwargs = {"eps": self.t_eps, **kwargs}
         return sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self.forward_score, y=y,
                                        conditioning=conditioning, **kwargs)
+
+    def enhance_batch(self, ys, predictor="reverse_diffusion", corrector="none", N=30, corrector_steps=1, snr=0.5,
+                      denoiser_only=False, seed: Optional[int] = None, utt_ids: Optional[Sequence[int]] = None,
+                      return_nfe: bool = False, max_batch: int = 8):
+        """Batched StoRM enhancement (the reference loops over files one at a time, enhancement.py:66-72).
+
+        ``ys``: tensor [B, L] -> tensor [B, L]; or a list of utterances of any lengths -> list of [L_b] tensors (bucketed by
+        padded frame count and run as ragged batches of at most ``max_batch``, like ``ScoreModel.enhance_batch``).  Per batch:
+        per-utterance normalisation and STFT, ONE batched denoiser forward, ONE native N-step sampler around ``Y_denoised``
+        with ``[Y, Y_denoised]`` as conditioning, batched iSTFT.  Noise is keyed per utterance id."""
+        dev = next(self._nets()[0].parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("StochasticRegenerationModel.enhance_batch needs the model on a CUDA device: call model.cuda() first")
+        sp = self.data_module.spec_config()
+        seed = self.next_seed() if seed is None else seed
+        eng = (self.score_net or self.denoiser_net).engine()
+
+        def run(yd, ids, lengths):
+            norm = _native.wave_norm(yd, lengths)
+            T_pad = _native.padded_frames(_native.num_frames(yd.shape[1], sp))
+            Y = _native.stft(yd, norm, sp, T_pad, lengths=lengths).unsqueeze(1)
+            Y_den = self.forward_denoiser(Y) if self.denoiser_net is not None else None
+            nfe = 0
+            if self.score_net is not None and not denoiser_only:
+                cond = {"noisy": [Y], "post_denoiser": [Y_den], "both": [Y, Y_den]}[self.condition]
+                sampler = self.get_pc_sampler(predictor, corrector, Y_den if Y_den is not None else Y, N=N,
+                                              corrector_steps=corrector_steps, snr=snr, conditioning=cond, seed=seed, utt_ids=ids)
+                sample, nfe = sampler()
+            else:
+                sample = Y_den
+            return eng.istft(sample.squeeze(1), norm, yd.shape[1], sp, lengths=lengths), nfe
+
+        if not torch.is_tensor(ys):
+            ys = [y.reshape(-1) for y in ys]
+            lens = [int(y.numel()) for y in ys]
+            if len(set(lens)) > 1:
+                from .parallel import bucket_utterances
+                ids_all = list(range(len(ys))) if utt_ids is None else [int(u) for u in utt_ids]
+                outs: List[Optional[torch.Tensor]] = [None] * len(ys)
+                nfe = 0
+                for idx in bucket_utterances(lens, sp.hop_length, max_batch):
+                    Lmax = max(lens[i] for i in idx)
+                    host = torch.zeros(len(idx), Lmax, dtype=torch.float32)
+                    for r, i in enumerate(idx):
+                        host[r, :lens[i]] = ys[i].to("cpu", torch.float32)
+                    out, nfe = run(host.pin_memory().to(dev, non_blocking=True), [ids_all[i] for i in idx], [lens[i] for i in idx])
+                    for r, i in enumerate(idx):
+                        outs[i] = out[r, :lens[i]].to(ys[i].device)
+                return (outs, nfe) if return_nfe else outs
+            ys = torch.stack(ys)
+        src = ys.device
+        yd = ys.to(torch.float32)
+        yd = yd.pin_memory().to(dev, non_blocking=True) if not yd.is_cuda else yd
+        ids = list(range(yd.shape[0])) if utt_ids is None else [int(u) for u in utt_ids]
+        out, nfe = run(yd, ids, None)
+        out = out.to(src)
+        return (out, nfe) if return_nfe else out
 
     def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="none", N=30, corrector_steps=1, snr=0.5,
                 timeit=False, scale_factor=None, return_stft=False, denoiser_only=False, **kwargs):
@@ -353,6 +512,15 @@ class StochasticRegenerationModel:
         if timeit:
             return x_hat, nfe, (time.time() - start) / (len(x_hat) / 16000)
         return x_hat
+
+
+def checkpoint_kind(path) -> str:
+    """'storm' for StochasticRegenerationModel checkpoints (``denoiser_net.*`` / ``score_net.*`` keys), 'score' for
+    ScoreModel / DiscriminativeModel ones (``dnn.*``)."""
+    sd = _load_ckpt(path, "cpu").get("state_dict", {})
+    if any(k.startswith(("denoiser_net.", "score_net.")) for k in sd):
+        return "storm"
+    return "score"
 
 
 class _Tolerant:

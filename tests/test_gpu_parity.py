@@ -404,6 +404,128 @@ def test_storm_mode_vs_reference():
     assert x_hat.shape == (y.shape[1],) and x_hat.device.type == "cpu" and nfe == 2 and torch.isfinite(x_hat).all()
 
 
+def test_storm_enhance_batch_equals_per_file_and_oracle():
+    """Batched StoRM (one denoiser forward + one native sampler for the whole batch, ragged lengths inside a bucket)
+    equals enhancing every file alone with the same seed / utterance ids bit for bit, and matches the CPU oracle."""
+    from storm_b200 import StochasticRegenerationModel, _native, ncsnpp_spec
+    model = StochasticRegenerationModel(backbone_denoiser="ncsnpp", backbone_score="ncsnpp", sde="ouve", nf=32, seed=5)
+    sd_d = ncsnpp_spec.random_state_dict(model.denoiser_net.cfg, seed=11, init_scale=1.0, bias_std=0.05)
+    sd_s = ncsnpp_spec.random_state_dict(model.score_net.cfg, seed=12, init_scale=1.0, bias_std=0.05)
+    model.denoiser_net.load_state_dict(sd_d)
+    model.score_net.load_state_dict(sd_s)
+    model.cuda()
+    lens = [8000, 7700, 8100, 16000]                         # three share the 64-frame bucket, one is alone in the 128-frame one
+    ys = [O.synth_utterance(40 + i, L) for i, L in enumerate(lens)]
+    outs, nfe = model.enhance_batch(ys, N=3, seed=77, utt_ids=[100, 101, 102, 103], return_nfe=True)
+    assert nfe == 3 and [o.numel() for o in outs] == lens and all(o.device.type == "cpu" for o in outs)
+    for i, y in enumerate(ys):
+        one = model.enhance(y.reshape(1, -1), N=3, seed=77, utt_ids=[100 + i])
+        assert torch.equal(one, outs[i]), f"utterance {i}: batched result differs from the per-file result"
+    # oracle for the first utterance, Philox noise replayed (1 prior draw + N predictor draws)
+    y0 = ys[0].reshape(1, -1)
+    sp = _native.make_spec_config()
+    T_pad = _native.padded_frames(_native.num_frames(lens[0], sp))
+    n = 256 * T_pad
+    it = iter([_native.philox_normal(77, 100, d, n).reshape(1, 1, 256, T_pad).cpu() for d in range(4)])
+    xo, nfeo = O.enhance_storm(sd_d, sd_s, O.named_cfg("ncsnpp", nf=32, input_channels=2, discriminative=True),
+                               O.named_cfg("ncsnpp", nf=32, input_channels=6), y0, N=3, noise=lambda z: next(it))
+    err = rel_l2(outs[0], xo)
+    print(f"StoRM batch, utterance 0 waveform rel-L2 vs oracle = {err:.3e}")
+    assert nfeo == 3 and err < TOL
+
+
+def test_discriminative_model_vs_oracle(tmp_path):
+    """DiscriminativeModel (sgmse/model.py:320-370, --mode denoiser-only): ScoreModel-shaped checkpoint (``dnn.*`` keys),
+    one network call with t = 1, batched."""
+    from storm_b200 import DiscriminativeModel, ncsnpp_spec
+    src = DiscriminativeModel(backbone="ncsnpp", sde="ouve", nf=32, discriminative=True, init_scale=1.0)
+    assert src.dnn.cfg.in_ch == 2
+    sd = ncsnpp_spec.random_state_dict(src.dnn.cfg, seed=21, init_scale=1.0, bias_std=0.05)
+    src.dnn.load_state_dict(sd)
+    ckpt = dict(state_dict=src.state_dict(), hyper_parameters=dict(backbone="ncsnpp", sde="ouve", nf=32, discriminative=True, t_eps=0.03))
+    path = tmp_path / "disc.ckpt"
+    torch.save(ckpt, path)
+    m = DiscriminativeModel.load_from_checkpoint(str(path), base_dir="", batch_size=1, num_workers=0, kwargs=dict(gpu=False))
+    m.eval(no_ema=False).cuda()
+    ys = torch.stack([O.synth_utterance(60 + i, 8000) for i in range(3)])
+    out = m.enhance_batch(ys)
+    assert out.shape == ys.shape and out.device == ys.device
+    one = m.enhance(ys[1:2])
+    assert one.device.type == "cpu" and torch.equal(one, out[1])
+    sc = O.SpecCfg()
+    y = ys[1:2]
+    nf = y.abs().max()
+    Y = O.pad_spec(O.spec_fwd(O.stft(y / nf, sc), sc).unsqueeze(0))
+    Xo = O.ncsnpp_forward(sd, O.named_cfg("ncsnpp", nf=32, input_channels=2, discriminative=True), Y, None)
+    xo = O.istft(O.spec_back(Xo.squeeze(), sc), sc, 8000) * nf
+    err = rel_l2(out[1], xo.squeeze())
+    print(f"DiscriminativeModel waveform rel-L2 vs oracle = {err:.3e}")
+    assert err < TOL
+    with pytest.raises(RuntimeError, match="real input channels"):
+        DiscriminativeModel(backbone="ncsnpp", sde="ouve", nf=32).cuda().enhance_batch(ys)     # stock 4-channel backbone: same mismatch as model.py:326
+
+
+@pytest.mark.parametrize("frozen_has_shadow", [True, False])
+def test_reference_checkpoint_with_ema_runs_on_the_engine(tmp_path, frozen_has_shadow):
+    """A Lightning checkpoint in the reference's layout (``dnn.*`` state_dict in module order, ``ema.shadow_params`` in
+    ``parameters()`` order - tests/golden/param_order.json - with or without a shadow for the frozen Fourier W, the two
+    torch_ema conventions) -> ScoreModel.load_from_checkpoint -> eval() swaps the shadow weights into the native engine:
+    one PC step against the oracle run on the SHADOW weights; eval(no_ema=True) against the raw ones."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from storm_b200 import ScoreModel, _native, ncsnpp_spec
+    cfg = ncsnpp_spec.NCSNppConfig(nf=32)
+    raw = ncsnpp_spec.random_state_dict(cfg, seed=31, init_scale=1.0, bias_std=0.05)
+    ema = ncsnpp_spec.random_state_dict(cfg, seed=32, init_scale=1.0, bias_std=0.05)
+    ema["all_modules.0.W"] = raw["all_modules.0.W"].clone()             # frozen: never updated, identical in both sets
+    order = json.load(open(os.path.join(GOLDEN, "param_order.json")))["ncsnpp_4ch"]
+    assert [n for n, _, _ in order] == list(raw.keys())
+    shadow = [ema[n].clone() for n, _, rg in order if rg or frozen_has_shadow]
+    ckpt = dict(state_dict={"dnn." + k: v for k, v in raw.items()},
+                hyper_parameters=dict(backbone="ncsnpp", sde="ouve", nf=32, t_eps=0.03, theta=1.5, sigma_min=0.05, sigma_max=0.5,
+                                      data_module_cls=None),
+                ema=dict(decay=0.999, num_updates=1000, shadow_params=shadow, collected_params=None))
+    path = tmp_path / "score.ckpt"
+    torch.save(ckpt, path)
+    m = ScoreModel.load_from_checkpoint(str(path), base_dir="", batch_size=1, num_workers=0, kwargs=dict(gpu=False))
+    m.eval(no_ema=False)
+    m.cuda()
+    _, _, Y = _synth_Y(1, 8000)
+    sc = _native.make_sampler_config("reverse_diffusion", "ald", 1, 1, 0.5, 0.03)
+    n = Y[0].numel()
+    draws = [_native.philox_normal(13, 2, d, n).reshape(Y.shape).cpu() for d in range(3)]
+    ocfg = O.named_cfg("ncsnpp", nf=32)
+    for sd_o, no_ema in ((ema, False), (raw, True)):
+        m.train(True)
+        m.eval(no_ema=no_ema)
+        X, nfe = m.dnn.engine().pc_sample(Y, sc, seed=13, utt_ids=[2])
+        it = iter(draws)
+        Xo, _ = O.pc_sample(O.make_score_fn(sd_o, ocfg), Y.cpu(), O.OUVE(), 1, noise=lambda z: next(it))
+        err = rel_l2(X.cpu(), Xo)
+        print(f"checkpoint (frozen W shadowed: {frozen_has_shadow}), no_ema={no_ema}: one PC step rel-L2 vs oracle = {err:.3e}")
+        assert nfe == 2 and err < TOL
+    other = rel_l2(X.cpu(), O.pc_sample(O.make_score_fn(ema, ocfg), Y.cpu(), O.OUVE(), 1, noise=lambda z, it=iter(draws): next(it))[0])
+    assert other > 10 * TOL        # the two weight sets really differ: a mis-assigned shadow list could not pass both checks
+
+
+def test_engine_follows_the_weights_to_another_device_or_complains():
+    """Operands on a device other than the engine's are reported, not launched on (device handling)."""
+    from storm_b200 import ncsnpp_spec
+    m = _model("ncsnpp", nf=32)
+    m.load_state_dict(ncsnpp_spec.random_state_dict(m.cfg, seed=2, init_scale=1.0))
+    x = torch.complex(torch.randn(1, 2, 64, 64), torch.randn(1, 2, 64, 64)).cuda()
+    t = torch.tensor([0.5]).cuda()
+    y0 = m(x, t)
+    assert m.engine().device == x.device
+    if torch.cuda.device_count() > 1:
+        m.cuda(1)
+        y1 = m(x.to("cuda:1"), t.to("cuda:1"))                      # current device is still 0
+        assert m.engine().device == torch.device("cuda", 1) and torch.equal(y1.cpu(), y0.cpu())
+        with pytest.raises(RuntimeError, match="created on"):
+            m(x, t)
+
+
 @pytest.mark.parametrize("name", ["ncsnpp12M", "ncsnpp6M"])
 def test_small_backbones_vs_oracle(name):
     """nf = 96 variants (ncsnpp.py:479-513): channel counts 96/192 exercise zero-padded 128-row weight blocks."""

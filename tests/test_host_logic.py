@@ -206,3 +206,38 @@ def test_ragged_length_validation_is_host_side():
         with pytest.raises(ValueError):
             _native.check_lengths(bad, B, L, sp)
     assert _native.check_lengths([5000, 200], 2, 8100) == [5000, 200]     # without a SpecConfig only the range is checked
+
+
+def test_parameter_order_matches_the_reference_modules():
+    """tests/golden/param_order.json = named_parameters() of the reference NCSNpp (oracle/gen_golden.py::gen_param_order):
+    the order torch_ema's shadow list follows, and the only frozen parameter (the Fourier W)."""
+    import json
+    from storm_b200 import BackboneRegistry
+    from storm_b200.model import FROZEN_PARAMS
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "param_order.json")))
+    for tag, kw in [("ncsnpp_4ch", dict(input_channels=4)), ("ncsnpp_6ch", dict(input_channels=6)),
+                    ("ncsnpp_disc", dict(input_channels=2, discriminative=True))]:
+        m = BackboneRegistry.get_by_name("ncsnpp")(nf=8, **kw)
+        mine = [(n, list(p.shape)) for n, p in m.named_parameters()]
+        assert mine == [(n, shp) for n, shp, _ in ref[tag]], tag
+        assert [n for n, _, rg in ref[tag] if not rg] == list(FROZEN_PARAMS)
+
+
+def test_ema_shadow_mapping_is_name_and_shape_checked():
+    from storm_b200 import BackboneRegistry
+    from storm_b200.model import map_ema_shadow
+    m = BackboneRegistry.get_by_name("ncsnpp")(nf=8)
+    named = list(m.named_parameters())
+    full = [torch.full_like(p, float(i)) for i, (_, p) in enumerate(named)]
+    pairs = map_ema_shadow(named, full)                                   # torch_ema 0.3: every parameter has a shadow
+    assert [n for n, _ in pairs] == [n for n, _ in named]
+    trainable = [t for (n, _), t in zip(named, full) if n != "all_modules.0.W"]
+    pairs = map_ema_shadow(named, trainable)                              # torch_ema 0.2: frozen parameters have none
+    assert "all_modules.0.W" not in [n for n, _ in pairs] and len(pairs) == len(named) - 1
+    assert all(float(sh.flatten()[0]) == float([i for i, (k, _) in enumerate(named) if k == n][0]) for n, sh in pairs)
+    with pytest.raises(RuntimeError, match="cannot align"):
+        map_ema_shadow(named, full[:-3])
+    bad = list(full)
+    bad[5] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError, match="shape"):
+        map_ema_shadow(named, bad)

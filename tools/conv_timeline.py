@@ -39,4 +39,4 @@ for name, H, W, C0, C1, Cout, pro, C2, use_res in SHAPES:
     macs = B * H * W * Cout * (9 * Cin + C2)
     tf = 2 * macs / (ms * 1e-3) / 1e12
     print(f"{name:36s} {ms * 1e3:8.1f} us  {tf:6.1f} TFLOP/s alg  cta0: issue {d[0]} wait_act {d[1]} wait_w {d[2]} "
-          f"retire {d[3]} prod_idle {d[4]} epi {d[5]} | producer t0: ld_wait seg0 {d[6]} seg1 {d[7]} empty_wait {d[8]} convert seg0 {d[9]} seg1 {d[10]}")
+          f"retire {d[3]} prod_idle {d[4]} epi {d[5]} | producer t0: issue_loads {d[6]} empty_wait {d[8]} ld+convert seg0 {d[9]} seg1 {d[10]}")

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export STORM_B200_TCQ=1
+timeout 300 python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -4
+timeout 300 python tools/conv_timeline.py > gpurun_out/r2_timeline7_q.txt 2>&1; cat gpurun_out/r2_timeline7_q.txt
+STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_q1.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_q1.json 2> gpurun_out/r2_bench_q1.err
+export STORM_B200_TCQ=0
+STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_q0.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_q0.json 2> gpurun_out/r2_bench_q0.err
+for f in q0 q1; do python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2_bench_$f.json").read().strip().splitlines()[-1])
+    print("$f", d["value"], d["ms_per_step"], d["roofline"]["achieved"], d["clocks"]["sm_mhz"])
+except Exception as e: print("$f failed", e)
+PY
+done

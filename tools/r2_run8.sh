@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8
+STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_pol.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_pol.json 2> gpurun_out/r2_bench_pol.err
+STORM_B200_TCQ=0 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_q0.json 2> gpurun_out/r2_bench_q0.err
+for f in q0 pol; do python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2_bench_$f.json").read().strip().splitlines()[-1])
+    print("$f", d["value"], d["ms_per_step"], d["roofline"]["achieved"], d["clocks"]["sm_mhz"])
+except Exception as e: print("$f failed", e)
+PY
+done
