@@ -194,6 +194,14 @@ int storm_si_sdr(const float* s, const float* s_hat, int32_t B, int32_t L, const
 int64_t storm_launch_count(const StormHandle* h);
 int storm_reset_launch_count(StormHandle* h);
 
+/* CUDA-graph replay of whole sampler trajectories (default on; STORM_B200_GRAPH=0 in the environment disables it for the process):
+ * the first storm_pc_sample / storm_enhance call of a (B, F, T, sampler configuration) runs eagerly and sizes the workspace,
+ * the second captures the N-step loop (sgmse/sampling/__init__.py:59) into a graph, later calls replay it - results are
+ * bit-identical to the eager path.  Injected noise, debug taps and profiling always run eagerly.  The handle keeps up to 8
+ * graphs; they are dropped when the weights are re-packed.  storm_graph_replays: replays so far (tests / bench). */
+int storm_set_graph(StormHandle* h, int32_t enable);
+int64_t storm_graph_replays(const StormHandle* h);
+
 /* Live roofline measurement of the dominant kernel class (the implicit-GEMM convolutions): while enabled,
  * every conv launch is bracketed by CUDA events on its stream.  storm_get_profile synchronises the device
  * and returns, per engine (0 = tcgen05, 1 = SIMT): launches, summed device milliseconds and summed

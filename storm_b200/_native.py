@@ -95,6 +95,8 @@ _PROTOS = {
                                       C.POINTER(C.c_float), C.c_void_p]),
     "storm_debug_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]),
+    "storm_set_graph": (C.c_int, [C.c_void_p, C.c_int32]),
+    "storm_graph_replays": (C.c_int64, [C.c_void_p]),
     "storm_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "storm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -313,6 +315,13 @@ class Engine:
 
     def reset_launch_count(self):
         lib().storm_reset_launch_count(self._h)
+
+    def set_graph(self, on: bool):
+        """CUDA-graph replay of whole trajectories (default on)."""
+        _check(lib().storm_set_graph(self._h, int(on)))
+
+    def graph_replays(self) -> int:
+        return lib().storm_graph_replays(self._h)
 
     def set_profile(self, on: bool):
         _check(lib().storm_set_profile(self._h, int(on)))

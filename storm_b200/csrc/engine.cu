@@ -131,6 +131,22 @@ struct StormHandle {
   float temb_cache_t = -1.f;
   bool temb_cache_valid = false;
   bool profile_on = false;
+  // captured trajectories (see pc_sample)
+  struct TrajKey { int B, F, T, ncond; StormSamplerConfig sc; };
+  struct TrajGraph {
+    TrajKey key{};
+    cudaGraphExec_t exec = nullptr;
+    float *Y = nullptr, *c0 = nullptr, *c1 = nullptr, *X = nullptr;
+    uint64_t *ids = nullptr, *seed = nullptr;
+    int nfe = 0;
+    int64_t launches_per_replay = 0;
+    bool warmed = false, failed = false;
+    Pool pool;      // workspace the captured nodes point into: owned by the graph, never handed to anybody else
+  };
+  std::vector<TrajGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool graph_on = true;
+  int64_t graph_replays = 0;
   struct ProfRec { cudaEvent_t a, b; int eng; double flops; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_free;
@@ -277,7 +293,18 @@ static int dev_alloc(StormHandle* h, size_t floats, float** out) {
   return 0;
 }
 
+// captured trajectories bake device pointers into their nodes: drop them whenever something they point at is re-allocated
+static void invalidate_graphs(StormHandle* h) {
+  for (auto& g : h->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (void* q : {(void*)g.Y, (void*)g.c0, (void*)g.c1, (void*)g.X, (void*)g.ids, (void*)g.seed}) if (q) cudaFree(q);
+    g.pool.destroy();
+  }
+  h->graphs.clear();
+}
+
 static void free_packed(StormHandle* h) {
+  invalidate_graphs(h);
   for (void* p : h->packed) cudaFree(p);
   h->packed.clear();
   h->res.clear(); h->attn.clear(); h->conv_in.clear(); h->conv_out.clear(); h->combine.clear();
@@ -662,6 +689,18 @@ struct Fwd {
   }
 };
 
+// per-step cache of the time-embedding biases; re-allocation drops the captured trajectories that point at the old buffer
+static int ensure_temb_cache(StormHandle* h, int B) {
+  if (h->temb_cache_B >= B) return 0;
+  invalidate_graphs(h);
+  if (h->temb_cache) cudaFree(h->temb_cache);
+  h->temb_cache = nullptr;
+  STORM_CUDA_TRY(cudaMalloc((void**)&h->temb_cache, (size_t)B * h->dense_total * sizeof(float)));
+  h->temb_cache_B = B;
+  h->temb_cache_valid = false;
+  return 0;
+}
+
 // t_uniform: when non-null, every batch element has this time value (the PC sampler's vec_t) and the
 // time-embedding biases are reused across calls with the same value
 static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out, int B, int F, int T, cudaStream_t st,
@@ -694,13 +733,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     void* p;
     bool hit = false;
     if (t_uniform) {
-      if (h->temb_cache_B < B) {
-        if (h->temb_cache) cudaFree(h->temb_cache);
-        h->temb_cache = nullptr;
-        STORM_CUDA_TRY(cudaMalloc((void**)&h->temb_cache, (size_t)B * h->dense_total * sizeof(float)));
-        h->temb_cache_B = B;
-        h->temb_cache_valid = false;
-      }
+      STORM_TRY(ensure_temb_cache(h, B));
       tembias = h->temb_cache;
       hit = h->temb_cache_valid && h->temb_cache_t == *t_uniform && h->temb_cache_rows >= B;
     } else {
@@ -903,9 +936,11 @@ static int check_sampler(const StormSamplerConfig* sc) {
   return 0;
 }
 
-static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int B, int F, int T,
-                     const StormSamplerConfig& sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int* nfe_out,
-                     cudaStream_t st) {
+// The N-step loop.  ids_dev / seed_dev: device copies of the utterance ids and the seed (null: row index / `seed`); everything
+// this function enqueues is stream work on device-resident operands, so it can run eagerly or under stream capture.
+static int pc_sample_body(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int B, int F, int T,
+                          const StormSamplerConfig& sc, uint64_t seed, const uint64_t* seed_dev, const uint64_t* ids_dev,
+                          const float* noise, int* nfe_out, cudaStream_t st) {
   const int64_t n = (int64_t)F * T;
   const int ncplx = h->in_ch() / 2;
   if (ncplx == 3 && !cond1) return fail(STORM_E_INVALID, "6-channel score net needs two conditioning spectrograms");
@@ -914,17 +949,12 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
   if (!cond0) cond0 = Y;
   void* p;
   float *xt, *xm, *d, *tdev;
-  uint64_t* ids_dev = nullptr;
   double* scratch = nullptr;
   UpdateCoef* coef_dev = nullptr;
   STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xt = (float*)p;
   STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xm = (float*)p;
   STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); d = (float*)p;
   STORM_TRY(h->pool.get((size_t)B * sizeof(float), &p)); tdev = (float*)p;
-  if (utt_ids) {
-    STORM_TRY(h->pool.get((size_t)B * sizeof(uint64_t), &p)); ids_dev = (uint64_t*)p;
-    STORM_CUDA_TRY(cudaMemcpyAsync(ids_dev, utt_ids, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  }
   if (sc.corrector == STORM_CORR_LANGEVIN) {
     STORM_TRY(h->pool.get((size_t)B * 64 * 2 * sizeof(double), &p)); scratch = (double*)p;
     STORM_TRY(h->pool.get(sizeof(UpdateCoef), &p)); coef_dev = (UpdateCoef*)p;
@@ -942,7 +972,7 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
   // prior: x_T = y + randn * std(T=1) (sdes.py:233-237); StoRM uses the same form around its mean
   {
     UpdateCoef c{0.f, 1.f, 0.f, (float)ouve_std(sc, 1.0)};
-    LAUNCH(h, launch_sampler_update(nullptr, Y, nullptr, nullptr, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+    LAUNCH(h, launch_sampler_update(nullptr, Y, nullptr, nullptr, xt, c, nullptr, noise_at(draw), seed, seed_dev, ids_dev, draw, B, n, st));
     ++draw;
   }
   const int N = sc.N;
@@ -957,12 +987,12 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
         const double std = ouve_std(sc, t);
         const double step = (sc.snr * std) * (sc.snr * std) * 2.0;
         UpdateCoef c{1.f, 0.f, (float)(-step), (float)sqrt(step * 2.0)};
-        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, nullptr, noise_at(draw), seed, seed_dev, ids_dev, draw, B, n, st));
       } else {
-        STORM_TRY(launch_langevin_coef(d, noise_at(draw), seed, ids_dev, draw, sc.snr, B, n, scratch, coef_dev, st));
+        STORM_TRY(launch_langevin_coef(d, noise_at(draw), seed, seed_dev, ids_dev, draw, sc.snr, B, n, scratch, coef_dev, st));
         h->launches += 2;
         UpdateCoef c{1.f, 0.f, 0.f, 1.f};
-        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, coef_dev, noise_at(draw), seed, ids_dev, draw, B, n, st));
+        LAUNCH(h, launch_sampler_update(xt, nullptr, d, xm, xt, c, coef_dev, noise_at(draw), seed, seed_dev, ids_dev, draw, B, n, st));
       }
       ++draw;
       have_mean = true;
@@ -974,14 +1004,14 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
       const double G = ouve_diffusion(sc, t) * sqrt(dt);
       const double pf = sc.probability_flow ? 0.5 : 1.0;
       UpdateCoef c{(float)(1.0 + sc.theta * dt), (float)(-sc.theta * dt), (float)(-G * G * pf), sc.probability_flow ? 0.f : (float)G};
-      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, seed_dev, ids_dev, draw, B, n, st));
       ++draw;
       have_mean = true;
     } else if (sc.predictor == STORM_PRED_EULER_MARUYAMA) {
       STORM_TRY(score(t));
       const double g = ouve_diffusion(sc, t);
       UpdateCoef c{(float)(1.0 + sc.theta / N), (float)(-sc.theta / N), (float)(-g * g / N), (float)(g * sqrt(1.0 / N))};
-      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, ids_dev, draw, B, n, st));
+      LAUNCH(h, launch_sampler_update(xt, Y, d, xm, xt, c, nullptr, noise_at(draw), seed, seed_dev, ids_dev, draw, B, n, st));
       ++draw;
       have_mean = true;
     } else {
@@ -994,7 +1024,149 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
   STORM_CUDA_TRY(cudaMemcpyAsync(X, result, (size_t)B * n * 8, cudaMemcpyDeviceToDevice, st));
   if (nfe_out) *nfe_out = N * (n_corr + 1);
   h->pool.put(xt); h->pool.put(xm); h->pool.put(d); h->pool.put(tdev);
-  h->pool.put(ids_dev); h->pool.put(scratch); h->pool.put(coef_dev);
+  h->pool.put(scratch); h->pool.put(coef_dev);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-graph replay of whole trajectories (removes the host loop of sampling/__init__.py:59)
+// ---------------------------------------------------------------------------------------------------
+// One graph per (B, F, T, sampler configuration, number of conditioning spectrograms): the ~6 800 launches of an N = 30
+// trajectory are captured ONCE from the eager code above and replayed with cudaGraphLaunch.  Everything that changes between
+// calls lives in graph-owned device buffers: mean / conditioning / result spectrograms, utterance ids and the seed (the noise
+// kernels read both from device memory).  Workspace pointers are baked into the nodes, so every captured trajectory owns its
+// workspace pool (the handle's pool hands buffers to whoever asks next - e.g. the `norm` vector storm_enhance keeps alive
+// ACROSS the sampler call - and a replay would scribble over them).
+static bool graphs_enabled(const StormHandle* h) {
+  static const int env = [] { const char* e = getenv("STORM_B200_GRAPH"); return e ? atoi(e) : 1; }();
+  return env != 0 && h->graph_on && !h->taps_on && !h->profile_on;
+}
+
+static void destroy_graph(StormHandle::TrajGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (void* q : {(void*)g.Y, (void*)g.c0, (void*)g.c1, (void*)g.X, (void*)g.ids, (void*)g.seed}) if (q) cudaFree(q);
+  g.pool.destroy();
+  g = StormHandle::TrajGraph();
+}
+
+static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int B, int F, int T,
+                     const StormSamplerConfig& sc, uint64_t seed, const uint64_t* utt_ids, const float* noise, int* nfe_out,
+                     cudaStream_t st) {
+  const size_t spec_bytes = (size_t)B * F * T * 8;
+  if (noise || !graphs_enabled(h)) {
+    // ---- eager: injected noise (parity tests), debug taps, profiling, STORM_B200_GRAPH=0
+    uint64_t* ids_dev = nullptr;
+    if (utt_ids) {
+      void* p;
+      STORM_TRY(h->pool.get((size_t)B * sizeof(uint64_t), &p)); ids_dev = (uint64_t*)p;
+      STORM_CUDA_TRY(cudaMemcpyAsync(ids_dev, utt_ids, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    const int rc = pc_sample_body(h, Y, cond0, cond1, X, B, F, T, sc, seed, nullptr, ids_dev, noise, nfe_out, st);
+    h->pool.put(ids_dev);
+    return rc;
+  }
+  if (h->conditional()) STORM_TRY(ensure_temb_cache(h, B));      // before any graph is looked up: growing it invalidates them
+  StormHandle::TrajKey key{};
+  key.B = B; key.F = F; key.T = T; key.sc = sc; key.ncond = (cond0 ? 1 : 0) + (cond1 ? 1 : 0);
+  StormHandle::TrajGraph* g = nullptr;
+  for (auto& e : h->graphs)
+    if (memcmp(&e.key, &key, sizeof(key)) == 0) { g = &e; break; }
+  if (!g) {
+    if (h->graphs.size() >= 8) { destroy_graph(h->graphs.front()); h->graphs.erase(h->graphs.begin()); }
+    h->graphs.emplace_back();
+    g = &h->graphs.back();
+    g->key = key;
+  }
+  if (!g->exec && !g->failed) {
+    // ---- first call of this shape: one eager trajectory sizes the workspace pool (no allocation may happen under capture),
+    // the second call captures
+    if (!g->warmed) {
+      g->warmed = true;
+      std::swap(h->pool, g->pool);                       // this run allocates the graph's own workspace
+      uint64_t* ids_dev = nullptr;
+      int rc = 0;
+      if (utt_ids) {
+        void* p;
+        rc = h->pool.get((size_t)B * sizeof(uint64_t), &p);
+        if (rc == 0) {
+          ids_dev = (uint64_t*)p;
+          if (cudaMemcpyAsync(ids_dev, utt_ids, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            rc = fail(STORM_E_CUDA, "utterance id upload failed");
+        }
+      }
+      if (rc == 0) rc = pc_sample_body(h, Y, cond0, cond1, X, B, F, T, sc, seed, nullptr, ids_dev, nullptr, nfe_out, st);
+      h->pool.put(ids_dev);
+      std::swap(h->pool, g->pool);
+      return rc;
+    }
+    bool ok = cudaMalloc((void**)&g->Y, spec_bytes) == cudaSuccess && cudaMalloc((void**)&g->X, spec_bytes) == cudaSuccess &&
+              cudaMalloc((void**)&g->ids, (size_t)B * sizeof(uint64_t)) == cudaSuccess && cudaMalloc((void**)&g->seed, sizeof(uint64_t)) == cudaSuccess;
+    if (ok && cond0) ok = cudaMalloc((void**)&g->c0, spec_bytes) == cudaSuccess;
+    if (ok && cond1) ok = cudaMalloc((void**)&g->c1, spec_bytes) == cudaSuccess;
+    cudaGraph_t graph = nullptr;
+    if (ok) {
+      h->temb_cache_valid = false;                       // the captured sequence must not depend on what ran before it
+      std::swap(h->pool, g->pool);                       // nodes point into the graph's own workspace (sized by the warm run)
+      const size_t pool_before = h->pool.total;
+      // capture on a private stream: the caller's stream may be the legacy default stream (torch's default), which cannot
+      // be captured; nothing executes during capture, the instantiated graph is launched on the caller's stream
+      if (!h->cap_stream) ok = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+      cudaError_t e = cudaSuccess;
+      if (ok) { e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed); ok = e == cudaSuccess; }
+      if (ok) {
+        int nfe = 0;
+        const int64_t l0 = h->launches;
+        const int rc = pc_sample_body(h, g->Y, g->c0, g->c1, g->X, B, F, T, sc, 0, g->seed, g->ids, nullptr, &nfe, h->cap_stream);
+        g->nfe = nfe;
+        g->launches_per_replay = h->launches - l0;
+        h->launches = l0;                                // captured, not executed
+        e = cudaStreamEndCapture(h->cap_stream, &graph);
+        ok = rc == 0 && e == cudaSuccess && graph != nullptr && h->pool.total == pool_before;
+        if (!ok && getenv("STORM_B200_GRAPH_DEBUG"))
+          fprintf(stderr, "storm_b200: trajectory capture failed: rc=%d (%s) cuda=%s pool %zu -> %zu\n", rc, rc ? g_last_error.c_str() : "ok",
+                  cudaGetErrorString(e), pool_before, h->pool.total);
+        h->temb_cache_valid = false;                     // ... and nothing after it may trust what the capture pretended to compute
+      }
+      std::swap(h->pool, g->pool);
+      if (ok) {
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        ok = e == cudaSuccess;
+        if (!ok && getenv("STORM_B200_GRAPH_DEBUG")) fprintf(stderr, "storm_b200: graph instantiation failed: %s\n", cudaGetErrorString(e));
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (!ok) {
+      cudaGetLastError();
+      StormHandle::TrajKey k2 = g->key;
+      destroy_graph(*g);
+      g->key = k2; g->failed = true; g->warmed = true;
+    }
+  }
+  if (g->failed || !g->exec) {
+    uint64_t* ids_dev = nullptr;
+    if (utt_ids) {
+      void* p;
+      STORM_TRY(h->pool.get((size_t)B * sizeof(uint64_t), &p)); ids_dev = (uint64_t*)p;
+      STORM_CUDA_TRY(cudaMemcpyAsync(ids_dev, utt_ids, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    const int rc = pc_sample_body(h, Y, cond0, cond1, X, B, F, T, sc, seed, nullptr, ids_dev, nullptr, nfe_out, st);
+    h->pool.put(ids_dev);
+    return rc;
+  }
+  // ---- replay
+  std::vector<uint64_t> ids(B);
+  for (int b = 0; b < B; ++b) ids[b] = utt_ids ? utt_ids[b] : (uint64_t)b;
+  STORM_CUDA_TRY(cudaMemcpyAsync(g->ids, ids.data(), (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, st));   // pageable source: staged
+  STORM_CUDA_TRY(cudaMemcpyAsync(g->seed, &seed, sizeof(uint64_t), cudaMemcpyHostToDevice, st));                    // before the call returns
+  STORM_CUDA_TRY(cudaMemcpyAsync(g->Y, Y, spec_bytes, cudaMemcpyDeviceToDevice, st));
+  if (cond0) STORM_CUDA_TRY(cudaMemcpyAsync(g->c0, cond0, spec_bytes, cudaMemcpyDeviceToDevice, st));
+  if (cond1) STORM_CUDA_TRY(cudaMemcpyAsync(g->c1, cond1, spec_bytes, cudaMemcpyDeviceToDevice, st));
+  STORM_CUDA_TRY(cudaGraphLaunch(g->exec, st));
+  STORM_CUDA_TRY(cudaMemcpyAsync(X, g->X, spec_bytes, cudaMemcpyDeviceToDevice, st));
+  h->temb_cache_valid = false;
+  h->launches += g->launches_per_replay;
+  ++h->graph_replays;
+  if (nfe_out) *nfe_out = g->nfe;
   return 0;
 }
 
@@ -1032,7 +1204,8 @@ int storm_destroy(StormHandle* h) {
   if (!h) return 0;
   DeviceGuard dg(h);
   cudaDeviceSynchronize();
-  free_packed(h);
+  free_packed(h);          // also drops the captured trajectories
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (auto& kv : h->taps) cudaFree(kv.second.p);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_free) cudaEventDestroy(e);
@@ -1162,6 +1335,13 @@ int storm_ode_drift(StormHandle* h, const float* X, const float* Y, float t, flo
   h->pool.put(d); h->pool.put(tdev);
   return 0;
 }
+
+int storm_set_graph(StormHandle* h, int32_t enable) {
+  if (!h) return fail(STORM_E_INVALID, "null handle");
+  h->graph_on = enable != 0;
+  return 0;
+}
+int64_t storm_graph_replays(const StormHandle* h) { return h ? h->graph_replays : 0; }
 
 int storm_set_profile(StormHandle* h, int32_t enable) {
   if (!h) return fail(STORM_E_INVALID, "null handle");

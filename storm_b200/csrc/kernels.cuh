@@ -71,14 +71,15 @@ int launch_attention_tc(const float* q, const float* k, const float* vT, float* 
 // ---- sampler elementwise updates (sdes.py:233-237, predictors.py:41-69, correctors.py:37-93) ----------
 struct UpdateCoef { float a, b, c, e; };   // x_mean = a x + b y + c d ; x = x_mean + e z
 // x, y, d: complex [B][n]; z from `noise` (complex [B][n]) or Philox(seed, utt_ids[b], draw)
-// coef_dev (optional): device UpdateCoef overriding `coef` (langevin)
+// coef_dev (optional): device UpdateCoef overriding `coef` (langevin); seed_dev (optional): device seed overriding `seed`
+// (CUDA-graph replays of a captured trajectory read seed and utterance ids from device memory)
 int launch_sampler_update(const float* x, const float* y, const float* d, float* x_mean, float* x_new,
-                          UpdateCoef coef, const UpdateCoef* coef_dev, const float* noise, uint64_t seed,
+                          UpdateCoef coef, const UpdateCoef* coef_dev, const float* noise, uint64_t seed, const uint64_t* seed_dev,
                           const uint64_t* utt_ids_dev, uint32_t draw, int B, int64_t n, cudaStream_t st);
 int launch_philox_fill(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n, float* out, cudaStream_t st);
 // langevin step size from batch-mean norms (correctors.py:52-58): coef = {1, 0, -step, sqrt(2 step)}
-int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* utt_ids_dev, uint32_t draw,
-                         float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st);
+int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* seed_dev, const uint64_t* utt_ids_dev,
+                         uint32_t draw, float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st);
 // drift = theta (y - x) + 0.5 g2 d   (PF-ODE drift with score = -d)
 int launch_ode_drift(const float* x, const float* y, const float* d, float* out, float theta, float half_g2,
                      int64_t n_total, cudaStream_t st);

@@ -966,9 +966,10 @@ __device__ __forceinline__ float2 philox_cnormal(uint64_t seed, uint64_t utt, ui
 __global__ void sampler_update_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ d,
                                       float2* __restrict__ x_mean, float2* __restrict__ x_new, UpdateCoef coef,
                                       const UpdateCoef* __restrict__ coef_dev, const float2* __restrict__ noise, uint64_t seed,
-                                      const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n) {
+                                      const uint64_t* __restrict__ seed_dev, const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n) {
   const int b = blockIdx.y;
   if (coef_dev) coef = *coef_dev;
+  if (seed_dev) seed = *seed_dev;             // captured trajectories read the seed from device memory
   const uint64_t utt = utt_ids ? utt_ids[b] : (uint64_t)b;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const size_t g = (size_t)b * n + i;
@@ -985,13 +986,13 @@ __global__ void sampler_update_kernel(const float2* __restrict__ x, const float2
   }
 }
 int launch_sampler_update(const float* x, const float* y, const float* d, float* x_mean, float* x_new, UpdateCoef coef,
-                          const UpdateCoef* coef_dev, const float* noise, uint64_t seed, const uint64_t* utt_ids_dev,
-                          uint32_t draw, int B, int64_t n, cudaStream_t st) {
+                          const UpdateCoef* coef_dev, const float* noise, uint64_t seed, const uint64_t* seed_dev,
+                          const uint64_t* utt_ids_dev, uint32_t draw, int B, int64_t n, cudaStream_t st) {
   unsigned bx = (unsigned)((n + 255) / 256 > 148 * 4 ? 148 * 4 : (n + 255) / 256);
   sampler_update_kernel<<<dim3(bx, B), 256, 0, st>>>(
       reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), reinterpret_cast<const float2*>(d),
       reinterpret_cast<float2*>(x_mean), reinterpret_cast<float2*>(x_new), coef, coef_dev,
-      reinterpret_cast<const float2*>(noise), seed, utt_ids_dev, draw, n);
+      reinterpret_cast<const float2*>(noise), seed, seed_dev, utt_ids_dev, draw, n);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1009,8 +1010,10 @@ int launch_philox_fill(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n,
 
 // scratch: [B][64][2] doubles
 __global__ void sqnorm_partial_kernel(const float2* __restrict__ d, const float2* __restrict__ noise, uint64_t seed,
-                                      const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n, double* scratch) {
+                                      const uint64_t* __restrict__ seed_dev, const uint64_t* __restrict__ utt_ids, uint32_t draw,
+                                      int64_t n, double* scratch) {
   const int b = blockIdx.y;
+  if (seed_dev) seed = *seed_dev;
   const uint64_t utt = utt_ids ? utt_ids[b] : (uint64_t)b;
   double sd = 0, sz = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1044,11 +1047,11 @@ __global__ void langevin_coef_kernel(const double* scratch, int B, int nblk, flo
   float step = r * r * 2.0f;
   out->a = 1.f; out->b = 0.f; out->c = -step; out->e = sqrtf(step * 2.0f);
 }
-int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* utt_ids_dev, uint32_t draw,
-                         float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st) {
+int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* seed_dev, const uint64_t* utt_ids_dev,
+                         uint32_t draw, float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st) {
   const int nblk = 64;
   sqnorm_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(reinterpret_cast<const float2*>(d), reinterpret_cast<const float2*>(noise),
-                                                       seed, utt_ids_dev, draw, n, scratch);
+                                                       seed, seed_dev, utt_ids_dev, draw, n, scratch);
   STORM_LAUNCH_CHECK();
   langevin_coef_kernel<<<1, 32, 0, st>>>(scratch, B, nblk, snr, coef_out);
   STORM_LAUNCH_CHECK();

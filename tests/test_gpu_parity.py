@@ -509,6 +509,44 @@ def test_reference_checkpoint_with_ema_runs_on_the_engine(tmp_path, frozen_has_s
     assert other > 10 * TOL        # the two weight sets really differ: a mis-assigned shadow list could not pass both checks
 
 
+@pytest.mark.parametrize("pred,corr", [("reverse_diffusion", "ald"), ("euler_maruyama", "langevin"), ("reverse_diffusion", "none")])
+def test_graph_replay_is_bit_identical_to_the_eager_loop(pred, corr):
+    """the N-step loop captured into a CUDA graph (second call of a shape) and replayed (later calls) gives
+    the eager loop's result bit for bit, with seed and utterance ids - read from device memory by the replayed noise
+    kernels - changing between calls."""
+    from storm_b200 import _native, ncsnpp_spec
+    m = _model("ncsnpp", nf=32)
+    m.load_state_dict(ncsnpp_spec.random_state_dict(m.cfg, seed=8, init_scale=1.0, bias_std=0.05))
+    eng = m.engine()
+    _, _, Y = _synth_Y(3, 8000)
+    sc = _native.make_sampler_config(pred, corr, 4, 1, 0.5, 0.03)
+    calls = [(1, [0, 1, 2]), (2, [7, 8, 9]), (3, [4, 4, 6]), (2, [7, 8, 9])]
+    eng.set_graph(False)
+    eager = [eng.pc_sample(Y * (1.0 + 0.1 * i), sc, seed=sd, utt_ids=ids)[0].clone() for i, (sd, ids) in enumerate(calls)]
+    eng.set_graph(True)
+    r0 = eng.graph_replays()
+    for i, (sd, ids) in enumerate(calls):
+        X, nfe = eng.pc_sample(Y * (1.0 + 0.1 * i), sc, seed=sd, utt_ids=ids)
+        assert nfe == 4 * (2 if corr != "none" else 1)
+        assert torch.equal(X, eager[i]), f"call {i}: graph path differs from the eager path"
+    assert eng.graph_replays() - r0 == len(calls) - 1          # first call eager (sizes the workspace), then capture + replays
+    # a new batch size gets its own graph; the old one keeps working
+    X1, _ = eng.pc_sample(Y[:1], sc, seed=2, utt_ids=[7])
+    X1b, _ = eng.pc_sample(Y[:1], sc, seed=2, utt_ids=[7])
+    assert torch.equal(X1, X1b)
+    if corr != "langevin":                                      # langevin couples the batch (correctors.py:53-55)
+        assert torch.equal(X1[0], eager[1][0] if False else eng.pc_sample(Y, sc, seed=2, utt_ids=[7, 8, 9])[0][0])
+    # the whole enhance() call (STFT -> replayed sampler -> iSTFT)
+    y = torch.stack([O.synth_utterance(b, 8000) for b in range(3)]).cuda()
+    sp = _native.make_spec_config()
+    a, _ = eng.enhance(y, sc, sp, seed=5, utt_ids=[1, 2, 3])
+    b, _ = eng.enhance(y, sc, sp, seed=5, utt_ids=[1, 2, 3])
+    eng.set_graph(False)
+    c, _ = eng.enhance(y, sc, sp, seed=5, utt_ids=[1, 2, 3])
+    eng.set_graph(True)
+    assert torch.equal(a, c) and torch.equal(b, c)
+
+
 def test_engine_follows_the_weights_to_another_device_or_complains():
     """Operands on a device other than the engine's are reported, not launched on (device handling)."""
     from storm_b200 import ncsnpp_spec
