@@ -1392,13 +1392,16 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
     if (o.prec == 1) {   // a stage = one 32-channel chunk: four activation planes / four weight planes of the same sizes
       o.a_stage = 4 * o.a_plane;
       o.w_stage = 4 * o.w_plane;
-      budget = o.per_sm == 2 ? 112 * 1024 : 222 * 1024;
+      budget = o.per_sm == 2 ? 112 * 1024 : 229400;          // of the 231 424 bytes the kernels may ask for
     }
     o.sa = (o.a_stage <= 24 * 1024) ? 3 : 2;
-    {
-      const char* e = getenv("STORM_B200_TC_SA");
-      if (e && atoi(e) >= 2) o.sa = atoi(e);
-    }
+    // a launch with a 1x1 skip segment alternates long (3x3: 9 taps of MMAs per staged chunk) and short (1x1: one tap) stages;
+    // two activation stages cannot smooth that (the producers idle while a 3x3 chunk is multiplied, then the tensor pipe idles
+    // while the next 1x1 chunk is converted).  Where three stages AND three weight stages fit (256-pixel x 256-channel tiles) the
+    // third stage pays: profiles/r2_bench_history.md
+    static const int env_sa = [] { const char* e = getenv("STORM_B200_TC_SA"); return e ? atoi(e) : 0; }();
+    if (env_sa >= 2) o.sa = env_sa;
+    else if (env_sa == 0 && p.nseg == 2 && o.prec == 1 && k.npt == 1 && k.nmb == 2 && o.per_sm == 1) o.sa = 3;
     int sw = (budget - o.sa * o.a_stage - 256) / o.w_stage;
     if (sw < 2 && o.sa == 3) {     // rather two activation stages than too few weight stages
       o.sa = 2;
@@ -1470,7 +1473,9 @@ static bool choose_cfg_q(const ConvParams& p, TcqCfg& c) {
   if (c.ss_c > 1024) return false;
   c.a_plane = Q_NP * 32;
   c.w_plane = 4096;
-  if (c.prec == 1) { c.a_stage = 4 * c.a_plane; c.w_stage = 4 * c.w_plane; c.sa = 3; c.sw = 5; }
+  if (c.prec == 1) {
+    c.a_stage = 4 * c.a_plane; c.w_stage = 4 * c.w_plane; c.sa = 3; c.sw = 5;
+  }
   else { c.a_stage = 2 * c.a_plane; c.w_stage = 2 * c.w_plane; c.sa = 4; c.sw = 8; }
   c.tiles_x = ceil_div(p.W, 8);
   c.tiles_y = ceil_div(p.H, 32);
