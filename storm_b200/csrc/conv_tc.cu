@@ -230,8 +230,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 }
 
 // ---- weight packing ------------------------------------------------------------------------------------
-// out: for q = chunk*taps + tap: [hi image][lo image], each image Mpad rows (Cout rounded up to a multiple of 128,
-// zero rows beyond Cout); byte offset of element (n, k) inside an image: (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
+// out: for q = chunk*taps + tap, for every 128-row block mb of the Mpad rows (Cout rounded up to a multiple of 128, zero rows
+// beyond Cout): [hi plane][lo plane] of 128 rows x 32 B = 4096 B each, i.e. ONE contiguous 8 KB piece per weight stage and
+// channel block (one cp.async.bulk: the issuing thread pays ~240 cycles per bulk copy); byte offset of element (n, k) inside a
+// plane: ((n%128)/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
 __host__ __device__ inline int tc_mpad(int Cout) { return (Cout + 127) / 128 * 128; }
 
 __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout) {
@@ -247,16 +249,17 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict
     const float v = io_layout ? w[(size_t)ci * Cout + n] : w[((size_t)n * Cin + ci) * taps + tap];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    const size_t img = (size_t)(n / 8) * 128 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);     // in 2-byte units
-    uint16_t* base = out + q * (size_t)32 * Mpad;                                          // 64*Mpad bytes per q
+    const int nl = n % 128;
+    const size_t img = (size_t)(nl / 8) * 128 + (k / 8) * 64 + (nl % 8) * 8 + (k % 8);   // in 2-byte units
+    uint16_t* base = out + (q * (size_t)(Mpad / 128) + n / 128) * 4096;                    // 2 planes x 4096 B per (q, 128-row block)
     base[img] = __bfloat16_as_ushort(hi);
-    base[(size_t)16 * Mpad + img] = __bfloat16_as_ushort(lo);
+    base[2048 + img] = __bfloat16_as_ushort(lo);
   }
 }
 
-// Precision mode 1 image, per q = chunk32 * taps + tap: four planes of Mpad rows x 32 bytes (W = beta w):
-//   [Wh fp16, channels 0-15][Wh fp16, channels 16-31][e4m3(Wl), 32 channels][e4m3(W 2^-10), 32 channels]
-// byte offset of (row n, byte kb) inside a plane: (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16  (same core-matrix layout)
+// Precision mode 1 image, per q = chunk32 * taps + tap and 128-row block: four planes of 128 rows x 32 bytes (W = beta w),
+// 16 KB contiguous:   [Wh fp16, channels 0-15][Wh fp16, channels 16-31][e4m3(Wl), 32 channels][e4m3(W 2^-10), 32 channels]
+// byte offset of (row n, byte kb) inside a plane: ((n%128)/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16  (same core-matrix layout)
 __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout,
                                   float beta) {
   const int Mpad = tc_mpad(Cout);
@@ -271,9 +274,10 @@ __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restri
     const float v = beta * (io_layout ? w[(size_t)ci * Cout + n] : w[((size_t)n * Cin + ci) * taps + tap]);
     const __half wh = __float2half_rn(v);
     const float wl = v - __half2float(wh);
-    const size_t plane = (size_t)32 * Mpad;
-    uint8_t* base = out + q * 4 * plane;
-    const size_t row = (size_t)(n / 8) * 256 + (n % 8) * 16;
+    const size_t plane = 4096;
+    const int nl = n % 128;
+    uint8_t* base = out + (q * (size_t)(Mpad / 128) + n / 128) * 4 * plane;             // 4 planes x 4096 B per (q, 128-row block)
+    const size_t row = (size_t)(nl / 8) * 256 + (nl % 8) * 16;
     const int k16 = k % 16;
     *reinterpret_cast<uint16_t*>(base + (k / 16) * plane + row + (k16 / 8) * 128 + (k16 % 8) * 2) = __half_as_ushort(wh);
     const size_t o8 = row + (k / 16) * 128 + k16;
@@ -398,10 +402,11 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
                                            uint32_t tmem_base) {
   const uint32_t idesc = PREC ? make_idesc_fmt(c.ncol, 0, 0) : make_idesc(c.ncol);          // f16 x f16 | bf16 x bf16
   const uint32_t idesc8 = make_idesc_fmt(c.ncol, 0, 1);                                      // e4m3 (weights) x e5m2 (activations)
-  const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = (uint32_t)c.w_plane >> 4;
+  const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = 256u;                       // weight planes: 4096 B each
+  const uint32_t w_mb16 = PREC ? 1024u : 512u;                                           // one 128-row block: 4 | 2 planes
   const uint64_t pd_const = make_desc(0, (uint32_t)c.np * 16u, (uint32_t)c.hx * 16u);   // pixel operand (B)
   const uint64_t wd_const = make_desc(0, 128, 256);                                      // weight operand (A)
-  const uint32_t a_half16 = (uint32_t)c.a_half >> 4, w_half16 = (uint32_t)c.w_half >> 4;
+  const uint32_t a_half16 = (uint32_t)c.a_half >> 4, w_half16 = 256u;
   const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
   // the descriptor start-address field is 14 bits of (address >> 4); mask explicitly (measured: in a cluster launch
   // the shared::cta address of a CTA with rank > 0 carries bits above 256 KB that would spill into the LBO field)
@@ -438,7 +443,7 @@ __device__ __forceinline__ void issue_mmas(const ConvParams& p, const TcpCfg& c,
           const uint64_t p_lo = p_hi + a_half16;
 #pragma unroll
           for (int mb = 0; mb < NMB; ++mb) {
-            const uint64_t w_hi = wd_const + (uint64_t)(w16 + 256u * mb);   // 4096 B per 128-channel block
+            const uint64_t w_hi = wd_const + (uint64_t)(w16 + w_mb16 * mb);  // [128-channel block][plane][128 rows x 32 B]
             const uint32_t d = tmem_base + (uint32_t)(pt * NMB + mb) * ncol;
             if constexpr (PREC == 1) {
               umma_bf16(d, w_hi, p_hi, idesc, acc);                                          // wh x h, channels 0-15
@@ -876,24 +881,17 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const size_t q_stride = (size_t)(PREC ? 128 : 64) * Mpad;      // bytes per (K chunk, tap): 4 | 2 planes of 32 * Mpad
+      const size_t q_stride = (size_t)(PREC ? 128 : 64) * Mpad;      // bytes per (K chunk, tap): Mpad / 128 blocks of 4 | 2 planes
       ChunkIter it(p, PREC);
       int si, ch;
       while (it.next(si, ch)) {
         const ConvSeg& s = p.seg[si];
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32 + (size_t)ch * s.taps * q_stride;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * (PREC ? 128 : 64) + (size_t)ch * s.taps * q_stride;
         for (int tap = 0; tap < s.taps; ++tap) {
           mbar_wait(w_empty(stage), phase ^ 1);
           const uint32_t dst = w_base + stage * c.w_stage;
           mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-          if constexpr (PREC == 1) {
-#pragma unroll
-            for (int pl = 0; pl < 4; ++pl)
-              bulk_g2s(dst + pl * c.w_plane, base + tap * q_stride + (size_t)pl * 32 * Mpad, (uint32_t)c.w_plane, w_full(stage));
-          } else {
-            bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_half, w_full(stage));
-            bulk_g2s(dst + c.w_half, base + tap * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_half, w_full(stage));
-          }
+          bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_stage, w_full(stage));      // the CTA's nmb channel blocks are adjacent
           if (++stage == c.sw) { stage = 0; phase ^= 1; }
         }
       }
@@ -1158,7 +1156,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
     if (lane == 0) {
       const uint32_t idesc = PREC ? make_idesc_fmt(Q_NCOL, 0, 0) : make_idesc(Q_NCOL);
       const uint32_t idesc8 = make_idesc_fmt(Q_NCOL, 0, 1);
-      const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = (uint32_t)c.w_plane >> 4;
+      const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = 256u;
       const uint64_t pd_const = make_desc(0, (uint32_t)Q_NP * 16u, (uint32_t)Q_HX * 16u);   // pixel operand (B)
       const uint64_t wd_const = make_desc(0, 128, 256);                                    // weight operand (A)
       const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
@@ -1246,19 +1244,12 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
         int si, ch;
         while (it.next(si, ch)) {
           const ConvSeg& s = p.seg[si];
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 32 + (size_t)ch * s.taps * q_stride;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * (PREC ? 128 : 64) + (size_t)ch * s.taps * q_stride;
           for (int tap = 0; tap < s.taps; ++tap) {
             mbar_wait(w_empty(stage), phase ^ 1);
             const uint32_t dst = w_base + stage * c.w_stage;
             mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-            if constexpr (PREC == 1) {
-#pragma unroll
-              for (int pl = 0; pl < 4; ++pl)
-                bulk_g2s(dst + pl * c.w_plane, base + tap * q_stride + (size_t)pl * 32 * Mpad, (uint32_t)c.w_plane, w_full(stage));
-            } else {
-              bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_plane, w_full(stage));
-              bulk_g2s(dst + c.w_plane, base + tap * q_stride + (size_t)32 * Mpad, (uint32_t)c.w_plane, w_full(stage));
-            }
+            bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_stage, w_full(stage));    // one contiguous piece per (tap, channel block)
             if (++stage == c.sw) { stage = 0; phase ^= 1; }
           }
         }
@@ -1335,6 +1326,350 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
   tc_fence_before();
   __syncthreads();
   if (warp == Q_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================
+// Mode R: CTA PAIRS (tcgen05 cta_group::2) for layers with 129..256 output channels.  A cluster of two CTAs (two SMs of
+// one TPC) owns one 256-pixel tile (32 rows x 8 columns) and ALL 256 output channels:
+//   * A operand (weights): CTA r holds the rows of output channels [128 r, 128 r + 128) of every tap;
+//   * B operand (pixels):  CTA r stages the halo tile of tile rows [16 r, 16 r + 16)  (18 x 10 = 180 halo pixels);
+//   * ONE tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16 | 32) issued by the leader CTA drives both SMs' tensor cores; every
+//     CTA's TMEM ends up with its 128 channels x all 256 pixels and drains them itself.
+// Against mode P's 256-pixel x 256-channel tile on one SM (two M = 128 MMAs per k-step, 12 KB of shared-memory operand reads
+// per 128 tensor cycles: measured 155-170 cycles per MMA) each SM reads 8 KB per MMA, converts half as many halo pixels per
+// MMA and streams the same weight bytes.  Synchronisation: the peer's producers arrive REMOTELY on the leader's `a_full`
+// barriers; a forwarding warp in the peer reports landed weight stages to the leader; stage / accumulator releases are
+// tcgen05.commit multicasts into both CTAs.
+// =====================================================================================================
+constexpr int R_NPW = 8;                                   // producer warps (then epilogue): 256 threads, 180 halo pixels
+constexpr int R_WARP_W = 8, R_WARP_MMA = 9, R_WARP_FWD = 10;
+constexpr int R_THREADS = 11 * 32;
+constexpr int R_HX = 10, R_HY = 18, R_NP = R_HX * R_HY;   // halo tile of 16 rows x 8 columns
+constexpr int R_NCOL = 256;
+
+struct TcrCfg {
+  int sa, sw;
+  int a_plane, a_stage, w_plane, w_stage;
+  int tiles_x, tiles_y;
+  int ss_c;
+  float acc_scale;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of every MMA issued so far -> one arrival on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor of the pair MMA: D = f32, M = 256 (both CTAs), N = n
+__host__ __device__ __forceinline__ uint32_t make_idesc2_fmt(int n, int afmt, int bfmt) {
+  return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, TcrCfg c) {
+  constexpr int PREC = 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();                  // 0 = leader
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t w_base = a_base + c.sa * c.a_stage;
+  const uint32_t ss_base = w_base + c.sw * c.w_stage;
+  const uint32_t bar_base = ss_base + (uint32_t)c.ss_c * 8u;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };                               // leader's copy is the one in use
+  auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
+  auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };                  // local weights landed
+  auto w_peer = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };           // leader: the peer's weights landed
+  auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + 2 * c.sw + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 3 * c.sw);
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int tile = blockIdx.x >> 1;
+  const int ty0 = (tile / c.tiles_x) * 32;                  // tile origin; this CTA stages rows ty0 + 16 rank ..
+  const int tx0 = (tile % c.tiles_x) * 8;
+  const int b = blockIdx.z;
+  const int m_lo = (int)rank * 128;
+  const int Mpad = tc_mpad(p.Cout);
+
+  if (tid == 0) {
+    for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), 2 * R_NPW); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_peer(i), 1); mbar_init(w_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (c.ss_c) {                                             // GroupNorm scale / shift of this sample -> shared memory
+    const float2* gs = reinterpret_cast<const float2*>(p.seg[0].ss) + (size_t)b * c.ss_c;
+    for (int i = tid; i < c.ss_c; i += R_THREADS) {
+      const float2 v = __ldg(gs + i);
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ss_base + 8u * i), "f"(v.x), "f"(v.y) : "memory");
+    }
+  }
+  if (warp == R_WARP_MMA) tmem_alloc2(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // both CTAs' barriers exist before anything arrives remotely
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < R_NPW) {
+    // =================================== activation producers ==========================================
+    float alpha = 1.0f, inv_alpha = 1.0f;
+    if (p.raw_ms) {
+      float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (m > 262144.0f && m < 3.0e38f) {
+        const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
+        int e = (ex + 1) / 2 - 9;
+        e = e < 0 ? 0 : (e > 60 ? 60 : e);
+        alpha = __uint_as_float((uint32_t)(127 - e) << 23);
+        inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
+      }
+    }
+    const int ps = tid;
+    const bool present = ps < R_NP;
+    const int hy = ps / R_HX, hxx = ps - hy * R_HX;
+    const bool interior = present && !(hy == 0 || hy == R_HY - 1 || hxx == 0 || hxx == R_HX - 1);
+    const uint32_t uoff = (uint32_t)ps * 16u;
+    const int y = ty0 + 16 * (int)rank + hy - 1, x = tx0 + hxx - 1;
+    const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
+    const bool valid = upix >= 0;
+    const uint32_t a_full_leader0 = mapa_rank(a_full(0), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    ChunkIter it(p, PREC);
+    int si, chk;
+    while (it.next(si, chk)) {
+      const ConvSeg& s = p.seg[si];
+      const bool active = present && (s.taps == 9 || interior);
+      const int c0 = chk * 32;
+      float4 raw[8];
+      if (active && valid) {
+        const float* src;
+        int Cs, cl;
+        if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
+        const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) raw[j] = __ldg(gp + j);
+      }
+      {
+        ChunkIter peek = it;
+        int nsi, nch;
+        if (valid && peek.next(nsi, nch)) {
+          const ConvSeg& ns = p.seg[nsi];
+          if (ns.taps == 9 || interior) {
+            const int n0c = nch * 32;
+            const float* nsrc;
+            int nCs, ncl;
+            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix * nCs + ncl));
+          }
+        }
+      }
+      mbar_wait_relaxed(a_empty(stage), phase ^ 1);
+      const uint32_t st_base = a_base + stage * c.a_stage;
+      if (active) {
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const uint32_t tab = ss_base + 8u * (uint32_t)(c0 + 16 * hsel);
+          uint2 a8[2], l8[2];
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const uint32_t off = st_base + (uint32_t)(kh * R_NP) * 16u + uoff;
+            const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint4 h16 = make_uint4(0, 0, 0, 0);
+            a8[kh] = make_uint2(0, 0);
+            l8[kh] = make_uint2(0, 0);
+            if (valid) {
+              if (s.ss) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float4 t4;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                               : "r"(tab + (uint32_t)(kh * 8 + 2 * j) * 8u));
+                  v[2 * j] = fmaf(v[2 * j], t4.x, t4.y);
+                  v[2 * j + 1] = fmaf(v[2 * j + 1], t4.z, t4.w);
+                }
+              }
+              if (s.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+              }
+              if (alpha != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= alpha;
+              }
+              split_f16f8(v, h16, a8[kh], l8[kh]);
+            }
+            st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);
+          }
+          const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * R_NP) * 16u + uoff;
+          st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
+          st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
+        }
+      }
+      fence_async_shared();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_full_leader0 + 8u * stage);      // one arrival per warp on the LEADER's barrier
+      if (++stage == c.sa) { stage = 0; phase ^= 1; }
+    }
+    // =================================== epilogue (every producer warp) ==================================
+    {
+      const int q = warp & 3, grp = warp >> 2;               // TMEM lane quadrant / which half of the 8 units
+      mbar_wait_relaxed(acc_full, 0);
+      tc_fence_after();
+      const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
+      const float asc = c.acc_scale * inv_alpha;
+      const int cout = m_lo + q * 32 + lane;
+      double s_sum = 0.0, s_sq = 0.0;
+#pragma unroll 1
+      for (int u = grp; u < 8; u += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 32), r);
+        const float2 st = epilogue_unit(p, r, cout, b, tembp, asc, ty0 + u * 4, tx0);
+        s_sum += (double)st.x;
+        s_sq += (double)st.y;
+      }
+      if (p.stats_out && cout < p.Cout) {
+        double* o = p.stats_out + (((size_t)b * p.stats_chunks + tile * 2 + grp) * p.Cout + cout) * 2;
+        o[0] = s_sum;
+        o[1] = s_sq;
+      }
+    }
+  } else if (warp == R_WARP_W) {
+    // =================================== weight producer (this CTA's 128 channel rows) ====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t q_stride = (size_t)128 * Mpad;
+      ChunkIter it(p, PREC);
+      int si, ch;
+      while (it.next(si, ch)) {
+        const ConvSeg& s = p.seg[si];
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 128 + (size_t)ch * s.taps * q_stride;
+        for (int tap = 0; tap < s.taps; ++tap) {
+          mbar_wait(w_empty(stage), phase ^ 1);
+          const uint32_t dst = w_base + stage * c.w_stage;
+          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
+          bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_stage, w_full(stage));
+          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == R_WARP_FWD) {
+    // =================================== peer: report landed weight stages to the leader ==================
+    if (rank == 1 && lane == 0) {
+      const uint32_t w_peer_leader0 = mapa_rank(w_peer(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      ChunkIter it(p, PREC);
+      int si, ch;
+      while (it.next(si, ch)) {
+        for (int tap = 0; tap < p.seg[si].taps; ++tap) {
+          mbar_wait(w_full(stage), phase);
+          mbar_arrive_remote(w_peer_leader0 + 8u * stage);
+          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =================================== MMA issuer (leader CTA only) ====================================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc2_fmt(R_NCOL, 0, 0);
+      const uint32_t idesc8 = make_idesc2_fmt(R_NCOL, 0, 1);
+      const uint32_t a_pl16 = (uint32_t)c.a_plane >> 4, w_pl16 = 256u;
+      const uint64_t pd_const = make_desc(0, (uint32_t)R_NP * 16u, (uint32_t)R_HX * 16u);
+      const uint64_t wd_const = make_desc(0, 128, 256);
+      const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
+      const uint32_t a_base16 = (a_base >> 4) & 0x3FFFu, w_base16 = (w_base >> 4) & 0x3FFFu;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0, acc = 0;
+      const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.z == 0;
+      long long t_wa = 0, t_ww = 0;
+      const long long t_start = dbg ? clock64() : 0;
+      ChunkIter it(p, PREC);
+      int si, ch;
+      while (it.next(si, ch)) {
+        const bool k3 = p.seg[si].taps == 9;
+        long long t0 = dbg ? clock64() : 0;
+        mbar_wait(a_full(sa), pa);                           // both CTAs' halves of this K chunk are staged (default-scope wait:
+                                                             // an acquire.cluster per wait costs this thread several hundred cycles)
+        if (dbg) t_wa += clock64() - t0;
+        tc_fence_after();
+        const uint32_t a16 = a_base16 + sa * a_stage16;
+        const int ntap = k3 ? 9 : 1;
+        uint32_t toff = k3 ? 0u : (uint32_t)(R_HX + 1);
+        int dx = 0;
+        for (int tap = 0; tap < ntap; ++tap) {
+          t0 = dbg ? clock64() : 0;
+          mbar_wait(w_full(sw), pw);                         // my weight rows ...
+          mbar_wait(w_peer(sw), pw);                         // ... and the peer's
+          if (dbg) t_ww += clock64() - t0;
+          tc_fence_after();
+          const uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
+          const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff);
+          umma2_f16(tmem_base, w_hi, p_hi, idesc, acc);
+          umma2_f16(tmem_base, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
+          umma2_f8(tmem_base, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
+          umma2_f8(tmem_base, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
+          acc = 1u;
+          umma_commit2(w_empty(sw));
+          if (++sw == c.sw) { sw = 0; pw ^= 1; }
+          if (++dx == 3) { dx = 0; toff += (uint32_t)R_HX - 2u; } else { toff += 1u; }
+        }
+        umma_commit2(a_empty(sa));
+        if (++sa == c.sa) { sa = 0; pa ^= 1; }
+      }
+      umma_commit2(acc_full);
+      if (dbg) {
+        p.dbg[0] = clock64() - t_start;
+        p.dbg[1] = t_wa;
+        p.dbg[2] = t_ww;
+        mbar_wait(acc_full, 0);
+        p.dbg[3] = clock64() - t_start;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // nobody leaves while the pair may still touch its shared memory / TMEM
+  if (warp == R_WARP_MMA) tmem_dealloc2(tmem_base, 256);
 }
 
 int g_tc_force_per_sm = 3;   // see choose_cfg_p (STORM_B200_TC_PER_SM)
@@ -1502,10 +1837,44 @@ static bool tcq_policy(const ConvParams& p, const TcqCfg& c) {
 }
 static int tcq_smem_bytes(const TcqCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 2 * c.sw + 4) + 16; }
 
+// ---- mode R (CTA pairs) ----------------------------------------------------------------------------------
+static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
+  if (tc_mpad(p.Cout) != 256) return false;                  // 129 .. 256 output channels: one 128-row block per CTA of the pair
+  if (p.H < 17 || p.W < 8) return false;
+  for (int i = 0; i < p.nseg; ++i) {
+    const ConvSeg& s = p.seg[i];
+    if (!s.wtc || s.wprec != 1 || s.C0 % 32 != 0 || s.C1 % 32 != 0 || s.C0 < 32 || (s.taps != 9 && s.taps != 1)) return false;
+    if (s.wscale != p.seg[0].wscale) return false;
+  }
+  if (p.nseg == 2 && p.seg[1].ss) return false;
+  if (p.res && p.res_up) return false;
+  if (p.res_up && ((p.H | p.W) & 1)) return false;
+  c.acc_scale = 1.0f / p.seg[0].wscale;
+  c.ss_c = p.seg[0].ss ? p.seg[0].C0 + p.seg[0].C1 : 0;
+  if (c.ss_c > 1024) return false;
+  c.a_plane = R_NP * 32;
+  c.a_stage = 4 * c.a_plane;
+  c.w_plane = 4096;
+  c.w_stage = 4 * c.w_plane;
+  c.sa = 4;
+  c.sw = 6;
+  c.tiles_x = ceil_div(p.W, 8);
+  c.tiles_y = ceil_div(p.H, 32);
+  return true;
+}
+static int tcr_smem_bytes(const TcrCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + c.ss_c * 8 + 8 * (2 * c.sa + 3 * c.sw + 1) + 16; }
+// STORM_B200_TCR: 0 = never, 1 = wherever eligible, 2 (default) = measured policy
+static bool use_mode_r(const ConvParams& p, TcrCfg& cr) {
+  static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 0; }();
+  if (mode == 0 || !choose_cfg_r(p, cr)) return false;
+  return true;
+}
+
 // which kernel runs a launch.  STORM_B200_TCQ: 0 = mode P only, 1 = mode Q wherever it is eligible, 2 (default) = the measured
 // policy below.
 static bool use_mode_q(const ConvParams& p, TcqCfg& cq) {
   static const int mode = [] { const char* e = getenv("STORM_B200_TCQ"); return e ? atoi(e) : 2; }();
+  { TcrCfg cr; if (use_mode_r(p, cr)) return false; }
   if (mode == 0 || !choose_cfg_q(p, cq)) return false;
   if (mode == 1) return true;
   return tcq_policy(p, cq);
@@ -1520,6 +1889,8 @@ bool conv_tc_eligible(const ConvParams& p) {
 }
 
 int conv_tc_stats_chunks(const ConvParams& p) {
+  TcrCfg cr;
+  if (use_mode_r(p, cr)) return 2 * cr.tiles_x * cr.tiles_y;
   TcqCfg cq;
   if (use_mode_q(p, cq)) return cq.tiles_x * cq.tiles_y;
   TcpCfg cp;
@@ -1538,6 +1909,7 @@ int conv_tc_init_device() {
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   if (dev >= 0 && dev < 64) done[dev] = true;
@@ -1547,6 +1919,22 @@ int conv_tc_init_device() {
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   STORM_TRY(conv_tc_init_device());
   if (p.out_cm && (p.res || p.res_up)) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
+  TcrCfg cr;
+  if (use_mode_r(p, cr)) {
+    if (p.stats_out && p.stats_chunks != 2 * cr.tiles_x * cr.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(2 * cr.tiles_x * cr.tiles_y, 1, p.B);
+    lc.blockDim = dim3(R_THREADS);
+    lc.dynamicSmemBytes = tcr_smem_bytes(cr);
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    STORM_CUDA_TRY(cudaLaunchKernelEx(&lc, conv_tcr_kernel, p, cr));
+    return 0;
+  }
   TcqCfg cq;
   if (use_mode_q(p, cq)) {
     if (p.stats_out && p.stats_chunks != cq.tiles_x * cq.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-STORM_B200_TCQ_SA=4 timeout 300 python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -3
-STORM_B200_TCQ_SA=4 STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_qsa4.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_qsa4.json 2> gpurun_out/r2_bench_qsa4.err
+timeout 300 python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -3
+STORM_B200_TC_SA=3 STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_qsa4.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_qsa4.json 2> gpurun_out/r2_bench_qsa4.err
 STORM_B200_PROFILE_DUMP=gpurun_out/r2_dump_qsa3.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r2_bench_qsa3.json 2> gpurun_out/r2_bench_qsa3.err
 for f in qsa3 qsa4; do python - <<PY
 import json
