@@ -1341,16 +1341,16 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
 // barriers; a forwarding warp in the peer reports landed weight stages to the leader; stage / accumulator releases are
 // tcgen05.commit multicasts into both CTAs.
 // =====================================================================================================
-constexpr int R_NPW = 8;                                   // producer warps (then epilogue): 256 threads, 180 halo pixels
-constexpr int R_WARP_W = 8, R_WARP_MMA = 9, R_WARP_FWD = 10;
-constexpr int R_THREADS = 11 * 32;
+constexpr int R_NPW = 6;                                   // producer warps: 192 threads, 180 halo pixels
+constexpr int R_WARP_W = 6, R_WARP_MMA = 7, R_WARP_EPI = 8, R_WARP_FWD = 12;      // epilogue warps 8-11 (TMEM lane quadrants 0-3)
+constexpr int R_THREADS = 13 * 32;
 constexpr int R_HX = 10, R_HY = 18, R_NP = R_HX * R_HY;   // halo tile of 16 rows x 8 columns
 constexpr int R_NCOL = 256;
 
 struct TcrCfg {
   int sa, sw;
   int a_plane, a_stage, w_plane, w_stage;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, ntiles;      // 256-pixel tiles per row / column of a sample; B * tiles_y * tiles_x
   int ss_c;
   float acc_scale;
 };
@@ -1401,6 +1401,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc2_fmt(int n, int afmt, in
   return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+__device__ __forceinline__ void bar_sync_r_producers() { asm volatile("bar.sync 1, %0;" ::"n"(R_NPW * 32) : "memory"); }
+
+// Persistent: cluster k of gridDim.x / 2 walks over tiles k, k + nclusters, ...; the accumulator (256 of the 512 TMEM columns) is double
+// buffered, so the epilogue of a tile (both CTAs drain their own 128 channels) overlaps the main loop of the next one.
 __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, TcrCfg c) {
   constexpr int PREC = 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1408,37 +1412,29 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
   const uint32_t rank = cluster_ctarank();                  // 0 = leader
   const uint32_t a_base = smem_u32(smem);
   const uint32_t w_base = a_base + c.sa * c.a_stage;
-  const uint32_t ss_base = w_base + c.sw * c.w_stage;
-  const uint32_t bar_base = ss_base + (uint32_t)c.ss_c * 8u;
+  const uint32_t ss_base = w_base + c.sw * c.w_stage;                                   // two tables of ss_c (scale, shift) pairs
+  const uint32_t bar_base = ss_base + 2u * (uint32_t)c.ss_c * 8u;
   auto a_full = [&](int i) { return bar_base + 8u * i; };                               // leader's copy is the one in use
   auto a_empty = [&](int i) { return bar_base + 8u * (c.sa + i); };
   auto w_full = [&](int i) { return bar_base + 8u * (2 * c.sa + i); };                  // local weights landed
   auto w_peer = [&](int i) { return bar_base + 8u * (2 * c.sa + c.sw + i); };           // leader: the peer's weights landed
   auto w_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + 2 * c.sw + i); };
-  const uint32_t acc_full = bar_base + 8u * (2 * c.sa + 3 * c.sw);
-  const uint32_t tmem_slot = acc_full + 8;
-
-  const int tile = blockIdx.x >> 1;
-  const int ty0 = (tile / c.tiles_x) * 32;                  // tile origin; this CTA stages rows ty0 + 16 rank ..
-  const int tx0 = (tile % c.tiles_x) * 8;
-  const int b = blockIdx.z;
+  auto acc_full = [&](int i) { return bar_base + 8u * (2 * c.sa + 3 * c.sw + i); };
+  auto acc_empty = [&](int i) { return bar_base + 8u * (2 * c.sa + 3 * c.sw + 2 + i); };   // leader's copy: both CTAs' epilogues arrive
+  const uint32_t tmem_slot = bar_base + 8u * (2 * c.sa + 3 * c.sw + 4);
   const int m_lo = (int)rank * 128;
   const int Mpad = tc_mpad(p.Cout);
+  const int ncl = (int)gridDim.x >> 1, cl0 = (int)blockIdx.x >> 1;
+  const int per_b = c.tiles_x * c.tiles_y;
 
   if (tid == 0) {
     for (int i = 0; i < c.sa; ++i) { mbar_init(a_full(i), 2 * R_NPW); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), 1); mbar_init(w_peer(i), 1); mbar_init(w_empty(i), 1); }
-    mbar_init(acc_full, 1);
+    // leader: a weight stage is full when its own bulk copy has landed (expect_tx arrival) AND the peer has reported its copy
+    for (int i = 0; i < c.sw; ++i) { mbar_init(w_full(i), rank == 0 ? 2 : 1); mbar_init(w_peer(i), 1); mbar_init(w_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
     fence_barrier_init();
   }
-  if (c.ss_c) {                                             // GroupNorm scale / shift of this sample -> shared memory
-    const float2* gs = reinterpret_cast<const float2*>(p.seg[0].ss) + (size_t)b * c.ss_c;
-    for (int i = tid; i < c.ss_c; i += R_THREADS) {
-      const float2 v = __ldg(gs + i);
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ss_base + 8u * i), "f"(v.x), "f"(v.y) : "memory");
-    }
-  }
-  if (warp == R_WARP_MMA) tmem_alloc2(tmem_slot, 256);
+  if (warp == R_WARP_MMA) tmem_alloc2(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                       // both CTAs' barriers exist before anything arrives remotely
@@ -1448,128 +1444,119 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
 
   if (warp < R_NPW) {
     // =================================== activation producers ==========================================
-    float alpha = 1.0f, inv_alpha = 1.0f;
-    if (p.raw_ms) {
-      float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (m > 262144.0f && m < 3.0e38f) {
-        const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
-        int e = (ex + 1) / 2 - 9;
-        e = e < 0 ? 0 : (e > 60 ? 60 : e);
-        alpha = __uint_as_float((uint32_t)(127 - e) << 23);
-        inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
-      }
-    }
     const int ps = tid;
     const bool present = ps < R_NP;
     const int hy = ps / R_HX, hxx = ps - hy * R_HX;
     const bool interior = present && !(hy == 0 || hy == R_HY - 1 || hxx == 0 || hxx == R_HX - 1);
     const uint32_t uoff = (uint32_t)ps * 16u;
-    const int y = ty0 + 16 * (int)rank + hy - 1, x = tx0 + hxx - 1;
-    const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
-    const bool valid = upix >= 0;
     const uint32_t a_full_leader0 = mapa_rank(a_full(0), 0);
     int stage = 0;
     uint32_t phase = 0;
-    ChunkIter it(p, PREC);
-    int si, chk;
-    while (it.next(si, chk)) {
-      const ConvSeg& s = p.seg[si];
-      const bool active = present && (s.taps == 9 || interior);
-      const int c0 = chk * 32;
-      float4 raw[8];
-      if (active && valid) {
-        const float* src;
-        int Cs, cl;
-        if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
-        const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) raw[j] = __ldg(gp + j);
-      }
-      {
-        ChunkIter peek = it;
-        int nsi, nch;
-        if (valid && peek.next(nsi, nch)) {
-          const ConvSeg& ns = p.seg[nsi];
-          if (ns.taps == 9 || interior) {
-            const int n0c = nch * 32;
-            const float* nsrc;
-            int nCs, ncl;
-            if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix * nCs + ncl));
-          }
+    int ntile = 0;
+    for (int tile = cl0; tile < c.ntiles; tile += ncl) {
+      const int b = tile / per_b, pt = tile - b * per_b;
+      const int ty0 = (pt / c.tiles_x) * 32, tx0 = (pt % c.tiles_x) * 8;
+      const int y = ty0 + 16 * (int)rank + hy - 1, x = tx0 + hxx - 1;
+      const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
+      const bool valid = upix >= 0;
+      const uint32_t tab0 = ss_base + (uint32_t)(ntile & 1) * (uint32_t)c.ss_c * 8u;
+      if (c.ss_c) {                                         // GroupNorm scale / shift of this tile's sample -> shared memory
+        const float2* gs = reinterpret_cast<const float2*>(p.seg[0].ss) + (size_t)b * c.ss_c;
+        for (int i = tid; i < c.ss_c; i += R_NPW * 32) {
+          const float2 v = __ldg(gs + i);
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab0 + 8u * i), "f"(v.x), "f"(v.y) : "memory");
         }
       }
-      mbar_wait_relaxed(a_empty(stage), phase ^ 1);
-      const uint32_t st_base = a_base + stage * c.a_stage;
-      if (active) {
+      float alpha = 1.0f;
+      if (p.raw_ms) {
+        float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
 #pragma unroll
-        for (int hsel = 0; hsel < 2; ++hsel) {
-          const uint32_t tab = ss_base + 8u * (uint32_t)(c0 + 16 * hsel);
-          uint2 a8[2], l8[2];
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > 262144.0f && m < 3.0e38f) {
+          const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
+          int e = (ex + 1) / 2 - 9;
+          e = e < 0 ? 0 : (e > 60 ? 60 : e);
+          alpha = __uint_as_float((uint32_t)(127 - e) << 23);
+        }
+      }
+      bar_sync_r_producers();
+      ++ntile;
+      ChunkIter it(p, PREC);
+      int si, chk;
+      while (it.next(si, chk)) {
+        const ConvSeg& s = p.seg[si];
+        const bool active = present && (s.taps == 9 || interior);
+        const int c0 = chk * 32;
+        float4 raw[8];
+        if (active && valid) {
+          const float* src;
+          int Cs, cl;
+          if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
+          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-            const uint32_t off = st_base + (uint32_t)(kh * R_NP) * 16u + uoff;
-            const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
-            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            uint4 h16 = make_uint4(0, 0, 0, 0);
-            a8[kh] = make_uint2(0, 0);
-            l8[kh] = make_uint2(0, 0);
-            if (valid) {
-              if (s.ss) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float4 t4;
-                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
-                               : "r"(tab + (uint32_t)(kh * 8 + 2 * j) * 8u));
-                  v[2 * j] = fmaf(v[2 * j], t4.x, t4.y);
-                  v[2 * j + 1] = fmaf(v[2 * j + 1], t4.z, t4.w);
-                }
-              }
-              if (s.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
-              }
-              if (alpha != 1.0f) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= alpha;
-              }
-              split_f16f8(v, h16, a8[kh], l8[kh]);
+          for (int j = 0; j < 8; ++j) raw[j] = __ldg(gp + j);
+        }
+        {
+          ChunkIter peek = it;
+          int nsi, nch;
+          if (valid && peek.next(nsi, nch)) {
+            const ConvSeg& ns = p.seg[nsi];
+            if (ns.taps == 9 || interior) {
+              const int n0c = nch * 32;
+              const float* nsrc;
+              int nCs, ncl2;
+              if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl2 = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl2 = n0c - ns.C0; }
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix * nCs + ncl2));
             }
-            st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);
           }
-          const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * R_NP) * 16u + uoff;
-          st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
-          st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
         }
-      }
-      fence_async_shared();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(a_full_leader0 + 8u * stage);      // one arrival per warp on the LEADER's barrier
-      if (++stage == c.sa) { stage = 0; phase ^= 1; }
-    }
-    // =================================== epilogue (every producer warp) ==================================
-    {
-      const int q = warp & 3, grp = warp >> 2;               // TMEM lane quadrant / which half of the 8 units
-      mbar_wait_relaxed(acc_full, 0);
-      tc_fence_after();
-      const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
-      const float asc = c.acc_scale * inv_alpha;
-      const int cout = m_lo + q * 32 + lane;
-      double s_sum = 0.0, s_sq = 0.0;
-#pragma unroll 1
-      for (int u = grp; u < 8; u += 2) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 32), r);
-        const float2 st = epilogue_unit(p, r, cout, b, tembp, asc, ty0 + u * 4, tx0);
-        s_sum += (double)st.x;
-        s_sq += (double)st.y;
-      }
-      if (p.stats_out && cout < p.Cout) {
-        double* o = p.stats_out + (((size_t)b * p.stats_chunks + tile * 2 + grp) * p.Cout + cout) * 2;
-        o[0] = s_sum;
-        o[1] = s_sq;
+        mbar_wait_relaxed(a_empty(stage), phase ^ 1);
+        const uint32_t st_base = a_base + stage * c.a_stage;
+        if (active) {
+#pragma unroll
+          for (int hsel = 0; hsel < 2; ++hsel) {
+            const uint32_t tab = tab0 + 8u * (uint32_t)(c0 + 16 * hsel);
+            uint2 a8[2], l8[2];
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+              const uint32_t off = st_base + (uint32_t)(kh * R_NP) * 16u + uoff;
+              const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
+              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              uint4 h16 = make_uint4(0, 0, 0, 0);
+              a8[kh] = make_uint2(0, 0);
+              l8[kh] = make_uint2(0, 0);
+              if (valid) {
+                if (s.ss) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float4 t4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                                 : "r"(tab + (uint32_t)(kh * 8 + 2 * j) * 8u));
+                    v[2 * j] = fmaf(v[2 * j], t4.x, t4.y);
+                    v[2 * j + 1] = fmaf(v[2 * j + 1], t4.z, t4.w);
+                  }
+                }
+                if (s.silu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+                }
+                if (alpha != 1.0f) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= alpha;
+                }
+                split_f16f8(v, h16, a8[kh], l8[kh]);
+              }
+              st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);
+            }
+            const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * R_NP) * 16u + uoff;
+            st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
+            st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
+          }
+        }
+        fence_async_shared();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(a_full_leader0 + 8u * stage);      // one arrival per warp on the LEADER's barrier
+        if (++stage == c.sa) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == R_WARP_W) {
@@ -1578,37 +1565,46 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
       int stage = 0;
       uint32_t phase = 0;
       const size_t q_stride = (size_t)128 * Mpad;
-      ChunkIter it(p, PREC);
-      int si, ch;
-      while (it.next(si, ch)) {
-        const ConvSeg& s = p.seg[si];
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 128 + (size_t)ch * s.taps * q_stride;
-        for (int tap = 0; tap < s.taps; ++tap) {
-          mbar_wait(w_empty(stage), phase ^ 1);
-          const uint32_t dst = w_base + stage * c.w_stage;
-          mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-          bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_stage, w_full(stage));
-          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+      for (int tile = cl0; tile < c.ntiles; tile += ncl) {
+        ChunkIter it(p, PREC);
+        int si, ch;
+        while (it.next(si, ch)) {
+          const ConvSeg& s = p.seg[si];
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * 128 + (size_t)ch * s.taps * q_stride;
+          // one stage = one filter ROW (3 taps, 48 KB) of a 3x3 segment, or the single tap of a 1x1 segment: the MMA thread is
+          // issue bound at one barrier wait + commit per tap (149 cycles per pair MMA), not at one per row
+          const int rows = s.taps == 9 ? 3 : 1, per_row = s.taps == 9 ? 3 : 1;
+          for (int row = 0; row < rows; ++row) {
+            mbar_wait(w_empty(stage), phase ^ 1);
+            const uint32_t dst = w_base + stage * c.w_stage;
+            mbar_arrive_expect_tx(w_full(stage), (uint32_t)(per_row * 16384));
+            for (int dx = 0; dx < per_row; ++dx)
+              bulk_g2s(dst + dx * 16384, base + (size_t)(row * per_row + dx) * q_stride, 16384u, w_full(stage));
+            if (++stage == c.sw) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == R_WARP_FWD) {
     // =================================== peer: report landed weight stages to the leader ==================
     if (rank == 1 && lane == 0) {
-      const uint32_t w_peer_leader0 = mapa_rank(w_peer(0), 0);
+      const uint32_t w_peer_leader0 = mapa_rank(w_full(0), 0);
       int stage = 0;
       uint32_t phase = 0;
-      ChunkIter it(p, PREC);
-      int si, ch;
-      while (it.next(si, ch)) {
-        for (int tap = 0; tap < p.seg[si].taps; ++tap) {
-          mbar_wait(w_full(stage), phase);
-          mbar_arrive_remote(w_peer_leader0 + 8u * stage);
-          if (++stage == c.sw) { stage = 0; phase ^= 1; }
+      for (int tile = cl0; tile < c.ntiles; tile += ncl) {
+        ChunkIter it(p, PREC);
+        int si, ch;
+        while (it.next(si, ch)) {
+          const int rows = p.seg[si].taps == 9 ? 3 : 1;
+          for (int row = 0; row < rows; ++row) {
+            mbar_wait(w_full(stage), phase);
+            mbar_arrive_remote(w_peer_leader0 + 8u * stage);
+            if (++stage == c.sw) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
-  } else {
+  } else if (warp == R_WARP_MMA) {
     // =================================== MMA issuer (leader CTA only) ====================================
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = make_idesc2_fmt(R_NCOL, 0, 0);
@@ -1618,58 +1614,128 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
       const uint64_t wd_const = make_desc(0, 128, 256);
       const uint32_t a_stage16 = (uint32_t)c.a_stage >> 4, w_stage16 = (uint32_t)c.w_stage >> 4;
       const uint32_t a_base16 = (a_base >> 4) & 0x3FFFu, w_base16 = (w_base >> 4) & 0x3FFFu;
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0, acc = 0;
-      const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.z == 0;
-      long long t_wa = 0, t_ww = 0;
+      int sa = 0, sw = 0, buf = 0;
+      uint32_t pa = 0, pw = 0;
+      uint32_t eph[2] = {0, 0};
+      const bool dbg = p.dbg && blockIdx.x == 0;
+      long long t_wa = 0, t_ww = 0, t_we = 0;
       const long long t_start = dbg ? clock64() : 0;
-      ChunkIter it(p, PREC);
-      int si, ch;
-      while (it.next(si, ch)) {
-        const bool k3 = p.seg[si].taps == 9;
+      int ntile = 0;
+      for (int tile = cl0; tile < c.ntiles; tile += ncl) {
         long long t0 = dbg ? clock64() : 0;
-        mbar_wait(a_full(sa), pa);                           // both CTAs' halves of this K chunk are staged (default-scope wait:
-                                                             // an acquire.cluster per wait costs this thread several hundred cycles)
-        if (dbg) t_wa += clock64() - t0;
+        mbar_wait(acc_empty(buf), eph[buf] ^ 1);               // both CTAs have drained this accumulator buffer
+        if (dbg) t_we += clock64() - t0;
+        eph[buf] ^= 1;
         tc_fence_after();
-        const uint32_t a16 = a_base16 + sa * a_stage16;
-        const int ntap = k3 ? 9 : 1;
-        uint32_t toff = k3 ? 0u : (uint32_t)(R_HX + 1);
-        int dx = 0;
-        for (int tap = 0; tap < ntap; ++tap) {
+        const uint32_t d = tmem_base + (uint32_t)buf * R_NCOL;
+        uint32_t acc = 0;
+        ChunkIter it(p, PREC);
+        int si, ch;
+        while (it.next(si, ch)) {
+          const bool k3 = p.seg[si].taps == 9;
           t0 = dbg ? clock64() : 0;
-          mbar_wait(w_full(sw), pw);                         // my weight rows ...
-          mbar_wait(w_peer(sw), pw);                         // ... and the peer's
-          if (dbg) t_ww += clock64() - t0;
+          mbar_wait(a_full(sa), pa);                           // both CTAs' halves of this K chunk are staged (default-scope wait:
+                                                               // an acquire.cluster per wait costs this thread several hundred cycles)
+          if (dbg) t_wa += clock64() - t0;
           tc_fence_after();
-          const uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
-          const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff);
-          umma2_f16(tmem_base, w_hi, p_hi, idesc, acc);
-          umma2_f16(tmem_base, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
-          umma2_f8(tmem_base, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
-          umma2_f8(tmem_base, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
-          acc = 1u;
-          umma_commit2(w_empty(sw));
-          if (++sw == c.sw) { sw = 0; pw ^= 1; }
-          if (++dx == 3) { dx = 0; toff += (uint32_t)R_HX - 2u; } else { toff += 1u; }
+          const uint32_t a16 = a_base16 + sa * a_stage16;
+          const int nrow = k3 ? 3 : 1, per_row = k3 ? 3 : 1;
+          uint32_t toff = k3 ? 0u : (uint32_t)(R_HX + 1);
+          for (int row = 0; row < nrow; ++row) {
+            t0 = dbg ? clock64() : 0;
+            mbar_wait(w_full(sw), pw);                         // this filter row: my weight rows and (second arrival) the peer's
+            if (dbg) t_ww += clock64() - t0;
+            tc_fence_after();
+            uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
+            for (int dx = 0; dx < per_row; ++dx) {
+              const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff + (uint32_t)dx);
+              umma2_f16(d, w_hi, p_hi, idesc, acc);
+              umma2_f16(d, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
+              umma2_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
+              umma2_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
+              acc = 1u;
+              w_hi += 1024u;                                  // next tap of the row: 16 KB further
+            }
+            umma_commit2(w_empty(sw));
+            if (++sw == c.sw) { sw = 0; pw ^= 1; }
+            toff += (uint32_t)R_HX;
+          }
+          umma_commit2(a_empty(sa));
+          if (++sa == c.sa) { sa = 0; pa ^= 1; }
         }
-        umma_commit2(a_empty(sa));
-        if (++sa == c.sa) { sa = 0; pa ^= 1; }
+        umma_commit2(acc_full(buf));
+        buf ^= 1;
+        ++ntile;
       }
-      umma_commit2(acc_full);
       if (dbg) {
         p.dbg[0] = clock64() - t_start;
         p.dbg[1] = t_wa;
         p.dbg[2] = t_ww;
-        mbar_wait(acc_full, 0);
-        p.dbg[3] = clock64() - t_start;
+        p.dbg[3] = t_we;
+        p.dbg[4] = ntile;
       }
+    }
+  } else if (warp >= R_WARP_EPI && warp < R_WARP_EPI + 4) {
+    // =================================== epilogue warps: this CTA's 128 channels of every tile =============
+    const int q = warp & 3;
+    const uint32_t acc_empty_leader0 = mapa_rank(acc_empty(0), 0);
+    int buf = 0;
+    uint32_t fph[2] = {0, 0};
+    for (int tile = cl0; tile < c.ntiles; tile += ncl) {
+      const int b = tile / per_b, pt = tile - b * per_b;
+      const int ty0 = (pt / c.tiles_x) * 32, tx0 = (pt % c.tiles_x) * 8;
+      const int cout = m_lo + q * 32 + lane;
+      const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
+      float inv_alpha = 1.0f;
+      if (p.raw_ms) {
+        float m = lane < p.raw_ms_n ? __ldg(p.raw_ms + (size_t)b * p.raw_ms_n + lane) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > 262144.0f && m < 3.0e38f) {
+          const int ex = (int)((__float_as_uint(m) >> 23) & 255u) - 126;
+          int e = (ex + 1) / 2 - 9;
+          e = e < 0 ? 0 : (e > 60 ? 60 : e);
+          inv_alpha = __uint_as_float((uint32_t)(127 + e) << 23);
+        }
+      }
+      const float asc = c.acc_scale * inv_alpha;
+      if (p.res && !p.out_cm && m_lo + q * 32 < p.Cout) {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+          const int y = ty0 + u * 4 + (lane >> 3), x = tx0 + (lane & 7);
+          if (y < p.H && x < p.W)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + m_lo + q * 32));
+        }
+      }
+      mbar_wait_relaxed(acc_full(buf), fph[buf]);
+      fph[buf] ^= 1;
+      tc_fence_after();
+      double s_sum = 0.0, s_sq = 0.0;
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * R_NCOL + u * 32), r);
+        if (u == 7) {                                       // every column of this buffer is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(acc_empty_leader0 + 8u * buf);
+        }
+        const float2 st = epilogue_unit(p, r, cout, b, tembp, asc, ty0 + u * 4, tx0);
+        s_sum += (double)st.x;
+        s_sq += (double)st.y;
+      }
+      if (p.stats_out && cout < p.Cout) {
+        double* o = p.stats_out + (((size_t)b * p.stats_chunks + pt) * p.Cout + cout) * 2;
+        o[0] = s_sum;
+        o[1] = s_sq;
+      }
+      buf ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                       // nobody leaves while the pair may still touch its shared memory / TMEM
-  if (warp == R_WARP_MMA) tmem_dealloc2(tmem_base, 256);
+  if (warp == R_WARP_MMA) tmem_dealloc2(tmem_base, 512);
 }
 
 int g_tc_force_per_sm = 3;   // see choose_cfg_p (STORM_B200_TC_PER_SM)
@@ -1855,18 +1921,35 @@ static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
   c.a_plane = R_NP * 32;
   c.a_stage = 4 * c.a_plane;
   c.w_plane = 4096;
-  c.w_stage = 4 * c.w_plane;
-  c.sa = 4;
-  c.sw = 6;
+  c.w_stage = 3 * 4 * c.w_plane;              // one filter row: 3 taps x 16 KB
+  c.sa = 3;
+  c.sw = 3;
+  {
+    static const int esa = [] { const char* e = getenv("STORM_B200_TCR_SA"); return e ? atoi(e) : 0; }();
+    static const int esw = [] { const char* e = getenv("STORM_B200_TCR_SW"); return e ? atoi(e) : 0; }();
+    if (esa >= 2) c.sa = esa;
+    if (esw >= 2) c.sw = esw;
+  }
   c.tiles_x = ceil_div(p.W, 8);
   c.tiles_y = ceil_div(p.H, 32);
+  const long nt = (long)p.B * c.tiles_x * c.tiles_y;
+  if (nt > (1L << 30)) return false;
+  c.ntiles = (int)nt;
+  if (c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 3 * c.sw + 4) + 16 > 227 * 1024 - 1024) return false;
   return true;
 }
-static int tcr_smem_bytes(const TcrCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + c.ss_c * 8 + 8 * (2 * c.sa + 3 * c.sw + 1) + 16; }
-// STORM_B200_TCR: 0 = never, 1 = wherever eligible, 2 (default) = measured policy
+static int tcr_smem_bytes(const TcrCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 3 * c.sw + 4) + 16; }
+// STORM_B200_TCR: 0 = never, 1 = wherever eligible, 2 (default) = measured policy (per-launch times of whole benchmark runs,
+// profiles/r2_bench_history.md): the pair kernel wins on every 129..256-channel launch - by 15..20 % on the MMA-bound ones
+// (b31.conv0 953 -> 772 us = 801 TFLOP/s algorithmic, b27.conv0 482 -> 392) - except where a level offers between one and
+// four tiles per SM pair (64 x 64 at B = 8: 128 tiles on 74 pairs, the second wave is half empty) AND the launch is bound by its
+// producers (1x1 skip segment) or by HBM latency (1x1 only).
 static bool use_mode_r(const ConvParams& p, TcrCfg& cr) {
-  static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 0; }();
+  static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 2; }();
   if (mode == 0 || !choose_cfg_r(p, cr)) return false;
+  if (mode == 1) return true;
+  const int npairs = num_sms() / 2;
+  if (cr.ntiles > npairs && cr.ntiles < 4 * npairs && (p.nseg == 2 || p.seg[0].taps == 1)) return false;
   return true;
 }
 
@@ -1890,7 +1973,7 @@ bool conv_tc_eligible(const ConvParams& p) {
 
 int conv_tc_stats_chunks(const ConvParams& p) {
   TcrCfg cr;
-  if (use_mode_r(p, cr)) return 2 * cr.tiles_x * cr.tiles_y;
+  if (use_mode_r(p, cr)) return cr.tiles_x * cr.tiles_y;
   TcqCfg cq;
   if (use_mode_q(p, cq)) return cq.tiles_x * cq.tiles_y;
   TcpCfg cp;
@@ -1921,9 +2004,10 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (p.out_cm && (p.res || p.res_up)) return fail(-1, "conv_tc: channel-major output cannot be combined with a residual");
   TcrCfg cr;
   if (use_mode_r(p, cr)) {
-    if (p.stats_out && p.stats_chunks != 2 * cr.tiles_x * cr.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
+    if (p.stats_out && p.stats_chunks != cr.tiles_x * cr.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
     cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(2 * cr.tiles_x * cr.tiles_y, 1, p.B);
+    const int npairs = num_sms() / 2;
+    lc.gridDim = dim3(2 * (cr.ntiles < npairs ? cr.ntiles : npairs), 1, 1);
     lc.blockDim = dim3(R_THREADS);
     lc.dynamicSmemBytes = tcr_smem_bytes(cr);
     lc.stream = st;
