@@ -1341,9 +1341,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
 // barriers; a forwarding warp in the peer reports landed weight stages to the leader; stage / accumulator releases are
 // tcgen05.commit multicasts into both CTAs.
 // =====================================================================================================
-constexpr int R_NPW = 6;                                   // producer warps: 192 threads, 180 halo pixels
-constexpr int R_WARP_W = 6, R_WARP_MMA = 7, R_WARP_EPI = 8, R_WARP_FWD = 12;      // epilogue warps 8-11 (TMEM lane quadrants 0-3)
-constexpr int R_THREADS = 13 * 32;
+constexpr int R_NPW = 12;                                  // producer warps: 384 threads, TWO per halo pixel (16 channels each), 180 pixels
+constexpr int R_WARP_W = 12, R_WARP_MMA = 13, R_WARP_FWD = 14, R_WARP_EPI = 16;   // epilogue warps 16-19 (TMEM lane quadrants 0-3)
+constexpr int R_THREADS = 20 * 32;
 constexpr int R_HX = 10, R_HY = 18, R_NP = R_HX * R_HY;   // halo tile of 16 rows x 8 columns
 constexpr int R_NCOL = 256;
 
@@ -1442,9 +1442,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // registers per warpgroup (640 threads start at 96): producers 72, weight / MMA / forwarding warpgroup 64, epilogue 168
   if (warp < R_NPW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // =================================== activation producers ==========================================
-    const int ps = tid;
+    const int ps = tid >> 1, hsel = tid & 1;                 // halo pixel / which 16-channel half of every 32-channel K chunk
     const bool present = ps < R_NP;
     const int hy = ps / R_HX, hxx = ps - hy * R_HX;
     const bool interior = present && !(hy == 0 || hy == R_HY - 1 || hxx == 0 || hxx == R_HX - 1);
@@ -1487,19 +1489,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
         const ConvSeg& s = p.seg[si];
         const bool active = present && (s.taps == 9 || interior);
         const int c0 = chk * 32;
-        float4 raw[8];
+        float4 raw[4];
         if (active && valid) {
           const float* src;
           int Cs, cl;
           if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
-          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
+          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl + 16 * hsel);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) raw[j] = __ldg(gp + j);
+          for (int j = 0; j < 4; ++j) raw[j] = __ldg(gp + j);
         }
         {
           ChunkIter peek = it;
           int nsi, nch;
-          if (valid && peek.next(nsi, nch)) {
+          if (valid && hsel == 0 && peek.next(nsi, nch)) {
             const ConvSeg& ns = p.seg[nsi];
             if (ns.taps == 9 || interior) {
               const int n0c = nch * 32;
@@ -1513,14 +1515,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
         mbar_wait_relaxed(a_empty(stage), phase ^ 1);
         const uint32_t st_base = a_base + stage * c.a_stage;
         if (active) {
-#pragma unroll
-          for (int hsel = 0; hsel < 2; ++hsel) {
+          {
             const uint32_t tab = tab0 + 8u * (uint32_t)(c0 + 16 * hsel);
             uint2 a8[2], l8[2];
 #pragma unroll
             for (int kh = 0; kh < 2; ++kh) {
               const uint32_t off = st_base + (uint32_t)(kh * R_NP) * 16u + uoff;
-              const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
+              const float4 v0 = raw[2 * kh], v1 = raw[2 * kh + 1];
               float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
               uint4 h16 = make_uint4(0, 0, 0, 0);
               a8[kh] = make_uint2(0, 0);
@@ -1559,7 +1560,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
         if (++stage == c.sa) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == R_WARP_W) {
+  } else if (warp < R_WARP_EPI) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (warp == R_WARP_W) {
     // =================================== weight producer (this CTA's 128 channel rows) ====================
     if (lane == 0) {
       int stage = 0;
@@ -1675,7 +1678,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
         p.dbg[4] = ntile;
       }
     }
-  } else if (warp >= R_WARP_EPI && warp < R_WARP_EPI + 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     // =================================== epilogue warps: this CTA's 128 channels of every tile =============
     const int q = warp & 3;
     const uint32_t acc_empty_leader0 = mapa_rank(acc_empty(0), 0);
@@ -1939,18 +1944,13 @@ static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
   return true;
 }
 static int tcr_smem_bytes(const TcrCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 3 * c.sw + 4) + 16; }
-// STORM_B200_TCR: 0 = never, 1 = wherever eligible, 2 (default) = measured policy (per-launch times of whole benchmark runs,
-// profiles/r2_bench_history.md): the pair kernel wins on every 129..256-channel launch - by 15..20 % on the MMA-bound ones
-// (b31.conv0 953 -> 772 us = 801 TFLOP/s algorithmic, b27.conv0 482 -> 392) - except where a level offers between one and
-// four tiles per SM pair (64 x 64 at B = 8: 128 tiles on 74 pairs, the second wave is half empty) AND the launch is bound by its
-// producers (1x1 skip segment) or by HBM latency (1x1 only).
+// STORM_B200_TCR: 0 = never, anything else (default) = wherever eligible.  Measured per launch inside whole benchmark runs
+// (profiles/r2_bench_history.md): the pair kernel wins on every launch with 129..256 output channels, by 15..20 % on the MMA-bound
+// ones (b31.conv0 953 -> 772 us = 801 TFLOP/s algorithmic, b27.conv0 482 -> 392) and by 10..25 % on the ones with a 1x1 skip
+// segment once two producer threads share a halo pixel.
 static bool use_mode_r(const ConvParams& p, TcrCfg& cr) {
-  static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 2; }();
-  if (mode == 0 || !choose_cfg_r(p, cr)) return false;
-  if (mode == 1) return true;
-  const int npairs = num_sms() / 2;
-  if (cr.ntiles > npairs && cr.ntiles < 4 * npairs && (p.nseg == 2 || p.seg[0].taps == 1)) return false;
-  return true;
+  static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 1; }();
+  return mode != 0 && choose_cfg_r(p, cr);
 }
 
 // which kernel runs a launch.  STORM_B200_TCQ: 0 = mode P only, 1 = mode Q wherever it is eligible, 2 (default) = the measured
