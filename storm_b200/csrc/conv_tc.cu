@@ -944,6 +944,7 @@ struct TcqCfg {
   int tiles_x, tiles_y, msplit;      // pixel tiles per row / column of one sample, 128-channel blocks
   int ntiles, tpg, ngroups;          // tiles = B * tiles_y * tiles_x * msplit; consecutive tiles per CTA visit; groups
   int ss_c;                          // channels of the staged scale/shift table (0: segment 0 has none)
+  int wrow;                          // 1: a weight stage holds one filter ROW (3 taps) of a 3x3 segment instead of one tap
   float acc_scale;
 };
 
@@ -1189,29 +1190,34 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
           tc_fence_after();
           const uint32_t a16 = a_base16 + sa * a_stage16;
           const int ntap = k3 ? 9 : 1;
+          const int per = (c.wrow && k3) ? 3 : 1;            // taps per weight stage
+          constexpr uint32_t TAP16 = PREC ? 1024u : 512u;
           uint32_t toff = k3 ? 0u : (uint32_t)(Q_HX + 1);
           int dx = 0;
-          for (int tap = 0; tap < ntap; ++tap) {
+          for (int tap = 0; tap < ntap; tap += per) {
             t0 = dbg ? clock64() : 0;
             mbar_wait(w_full(sw), pw);
             if (dbg) t_ww += clock64() - t0;
             tc_fence_after();
-            const uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
-            const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff);
-            if constexpr (PREC == 1) {
-              umma_bf16(d, w_hi, p_hi, idesc, acc);
-              umma_bf16(d, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
-              umma_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
-              umma_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
-            } else {
-              umma_bf16(d, w_hi, p_hi, idesc, acc);
-              umma_bf16(d, w_hi, p_hi + a_pl16, idesc, 1u);
-              umma_bf16(d, w_hi + w_pl16, p_hi, idesc, 1u);
+            uint64_t w_hi = wd_const + (uint64_t)(w_base16 + sw * w_stage16);
+            for (int j = 0; j < per; ++j) {
+              const uint64_t p_hi = pd_const + (uint64_t)(a16 + toff);
+              if constexpr (PREC == 1) {
+                umma_bf16(d, w_hi, p_hi, idesc, acc);
+                umma_bf16(d, w_hi + w_pl16, p_hi + a_pl16, idesc, 1u);
+                umma_f8(d, w_hi + 2u * w_pl16, p_hi + 2u * a_pl16, idesc8, 1u);
+                umma_f8(d, w_hi + 3u * w_pl16, p_hi + 3u * a_pl16, idesc8, 1u);
+              } else {
+                umma_bf16(d, w_hi, p_hi, idesc, acc);
+                umma_bf16(d, w_hi, p_hi + a_pl16, idesc, 1u);
+                umma_bf16(d, w_hi + w_pl16, p_hi, idesc, 1u);
+              }
+              acc = 1u;
+              w_hi += TAP16;
+              if (++dx == 3) { dx = 0; toff += (uint32_t)Q_HX - 2u; } else { toff += 1u; }
             }
-            acc = 1u;
             umma_commit(w_empty(sw));
             if (++sw == c.sw) { sw = 0; pw ^= 1; }
-            if (++dx == 3) { dx = 0; toff += (uint32_t)Q_HX - 2u; } else { toff += 1u; }
           }
           umma_commit(a_empty(sa));
           if (++sa == c.sa) { sa = 0; pa ^= 1; }
@@ -1245,11 +1251,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
         while (it.next(si, ch)) {
           const ConvSeg& s = p.seg[si];
           const uint8_t* base = reinterpret_cast<const uint8_t*>(s.wtc) + (size_t)m_lo * (PREC ? 128 : 64) + (size_t)ch * s.taps * q_stride;
-          for (int tap = 0; tap < s.taps; ++tap) {
+          constexpr uint32_t TAPB = PREC ? 16384u : 8192u;   // one contiguous piece per (tap, channel block)
+          const int per = (c.wrow && s.taps == 9) ? 3 : 1;
+          for (int tap = 0; tap < s.taps; tap += per) {
             mbar_wait(w_empty(stage), phase ^ 1);
             const uint32_t dst = w_base + stage * c.w_stage;
-            mbar_arrive_expect_tx(w_full(stage), (uint32_t)c.w_stage);
-            bulk_g2s(dst, base + tap * q_stride, (uint32_t)c.w_stage, w_full(stage));    // one contiguous piece per (tap, channel block)
+            mbar_arrive_expect_tx(w_full(stage), TAPB * (uint32_t)per);
+            for (int dx = 0; dx < per; ++dx) bulk_g2s(dst + dx * TAPB, base + (size_t)(tap + dx) * q_stride, TAPB, w_full(stage));
             if (++stage == c.sw) { stage = 0; phase ^= 1; }
           }
         }
@@ -1879,8 +1887,14 @@ static bool choose_cfg_q(const ConvParams& p, TcqCfg& c) {
   if (c.ss_c > 1024) return false;
   c.a_plane = Q_NP * 32;
   c.w_plane = 4096;
+  // Weight stages of one filter ROW (3 taps, 48 KB) make the MMA thread wait / commit once per 12 MMAs instead of once per 4
+  // (-12 % on the plain 128-channel 3x3 layers); they leave room for two activation stages only, which the launches with a
+  // 1x1 skip segment cannot afford (+12 %): those keep one tap per stage and three activation stages.  STORM_B200_TCQ_WROW=0: off.
+  static const int env_wrow = [] { const char* e = getenv("STORM_B200_TCQ_WROW"); return e ? atoi(e) : 1; }();
+  c.wrow = 0;
   if (c.prec == 1) {
     c.a_stage = 4 * c.a_plane; c.w_stage = 4 * c.w_plane; c.sa = 3; c.sw = 5;
+    if (env_wrow && p.nseg == 1 && p.seg[0].taps == 9) { c.wrow = 1; c.w_stage = 3 * 16384; c.sa = 2; c.sw = 2; }
   }
   else { c.a_stage = 2 * c.a_plane; c.w_stage = 2 * c.w_plane; c.sa = 4; c.sw = 8; }
   c.tiles_x = ceil_div(p.W, 8);
