@@ -82,6 +82,19 @@ struct Pool {
   }
 };
 
+// returns its buffers to the pool when the scope ends, early error returns included
+struct PoolLease {
+  Pool* pool;
+  std::vector<void*> held;
+  explicit PoolLease(Pool* p) : pool(p) {}
+  ~PoolLease() { for (void* q : held) pool->put(q); }
+  int get(size_t bytes, void** out) {
+    const int rc = pool->get(bytes, out);
+    if (rc == 0) held.push_back(*out);
+    return rc;
+  }
+};
+
 struct ResPack {
   const float *gn0_g = nullptr, *gn0_b = nullptr, *gn1_g = nullptr, *gn1_b = nullptr;
   const float *b0 = nullptr;        // Conv_0.bias
@@ -951,13 +964,15 @@ static int pc_sample_body(StormHandle* h, const float* Y, const float* cond0, co
   float *xt, *xm, *d, *tdev;
   double* scratch = nullptr;
   UpdateCoef* coef_dev = nullptr;
-  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xt = (float*)p;
-  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); xm = (float*)p;
-  STORM_TRY(h->pool.get((size_t)B * n * 8, &p)); d = (float*)p;
-  STORM_TRY(h->pool.get((size_t)B * sizeof(float), &p)); tdev = (float*)p;
+  Pool* const pool0 = &h->pool;
+  PoolLease lease(pool0);                                // every early return below gives the buffers back
+  STORM_TRY(lease.get((size_t)B * n * 8, &p)); xt = (float*)p;
+  STORM_TRY(lease.get((size_t)B * n * 8, &p)); xm = (float*)p;
+  STORM_TRY(lease.get((size_t)B * n * 8, &p)); d = (float*)p;
+  STORM_TRY(lease.get((size_t)B * sizeof(float), &p)); tdev = (float*)p;
   if (sc.corrector == STORM_CORR_LANGEVIN) {
-    STORM_TRY(h->pool.get((size_t)B * 64 * 2 * sizeof(double), &p)); scratch = (double*)p;
-    STORM_TRY(h->pool.get(sizeof(UpdateCoef), &p)); coef_dev = (UpdateCoef*)p;
+    STORM_TRY(lease.get((size_t)B * 64 * 2 * sizeof(double), &p)); scratch = (double*)p;
+    STORM_TRY(lease.get(sizeof(UpdateCoef), &p)); coef_dev = (UpdateCoef*)p;
   }
   uint32_t draw = 0;
   auto noise_at = [&](uint32_t dr) -> const float* { return noise ? noise + (size_t)dr * B * n * 2 : nullptr; };
@@ -1023,8 +1038,6 @@ static int pc_sample_body(StormHandle* h, const float* Y, const float* cond0, co
   const float* result = (sc.denoise && have_mean) ? xm : xt;   // sampling/__init__.py:64
   STORM_CUDA_TRY(cudaMemcpyAsync(X, result, (size_t)B * n * 8, cudaMemcpyDeviceToDevice, st));
   if (nfe_out) *nfe_out = N * (n_corr + 1);
-  h->pool.put(xt); h->pool.put(xm); h->pool.put(d); h->pool.put(tdev);
-  h->pool.put(scratch); h->pool.put(coef_dev);
   return 0;
 }
 
@@ -1511,15 +1524,15 @@ int storm_enhance_ragged(StormHandle* h, const float* wav_in, float* wav_out, in
   const int F = sp->n_fft / 2 + 1;
   const int T_pad = storm_padded_frames(storm_num_frames(L, sp));
   void* p;
-  STORM_TRY(h->pool.get((size_t)B * 4, &p)); float* norm = (float*)p;
-  STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* Y = (float*)p;
-  STORM_TRY(h->pool.get((size_t)B * F * T_pad * 8, &p)); float* X = (float*)p;
+  PoolLease lease(&h->pool);
+  STORM_TRY(lease.get((size_t)B * 4, &p)); float* norm = (float*)p;
+  STORM_TRY(lease.get((size_t)B * F * T_pad * 8, &p)); float* Y = (float*)p;
+  STORM_TRY(lease.get((size_t)B * F * T_pad * 8, &p)); float* X = (float*)p;
   LAUNCH(h, launch_wave_norm(wav_in, B, L, lengths, norm, st));
   LAUNCH(h, launch_stft(wav_in, norm, B, L, lengths, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
                         sp->spec_abs_exponent, st));
   STORM_TRY(pc_sample(h, Y, nullptr, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
   STORM_TRY(storm_istft_ragged(h, X, norm, B, T_pad, wav_out, L, lengths, sp, stream));
-  h->pool.put(norm); h->pool.put(Y); h->pool.put(X);
   return 0;
 }
 int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const StormSamplerConfig* sc,

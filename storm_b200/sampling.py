@@ -117,13 +117,19 @@ class NoneCorrector(Corrector):
 
 
 def _native_model(score_fn):
-    """(model, backbone) when ``score_fn`` is one of this package's models (or a bound method of one)."""
-    from .model import ScoreModel, StochasticRegenerationModel   # local import: model imports this module
+    """(model, backbone) when ``score_fn`` is one of this package's models (or its stock score method): only then may the
+    native engine replace the Python loop.  A subclass that overrides ``forward`` / ``forward_score`` (guidance, wrappers)
+    or any other callable keeps the generic Python sampler below, which calls it like the reference does."""
+    from .model import DiscriminativeModel, ScoreModel, StochasticRegenerationModel   # local import: model imports this module
     owner = getattr(score_fn, "__self__", score_fn)
-    if isinstance(owner, ScoreModel):
-        return owner, owner.dnn
+    func = getattr(score_fn, "__func__", None)
+    if isinstance(owner, ScoreModel) and not isinstance(owner, DiscriminativeModel):
+        if type(owner).forward is ScoreModel.forward and func in (None, ScoreModel.forward):
+            return owner, owner.dnn
+        return None
     if isinstance(owner, StochasticRegenerationModel):
-        return owner, owner.score_net
+        if type(owner).forward_score is StochasticRegenerationModel.forward_score and func in (None, StochasticRegenerationModel.forward_score):
+            return owner, owner.score_net
     return None
 
 
@@ -150,8 +156,11 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
 
         return native_pc_sampler
 
-    predictor = predictor_cls(sde, score_fn, probability_flow=probability_flow)
-    corrector = corrector_cls(sde, score_fn, snr=snr, n_steps=corrector_steps)
+    # generic path: a conditional score function receives `conditioning=` exactly as in the reference
+    # (sampling/__init__.py:60-63: update_fn(xt, vec_t, y, conditioning=conditioning) -> score_fn(x, t, y, conditioning=...))
+    fn = score_fn if conditioning is None else (lambda x, t, *a, **k: score_fn(x, t, *a, conditioning=conditioning, **k))
+    predictor = predictor_cls(sde, fn, probability_flow=probability_flow)
+    corrector = corrector_cls(sde, fn, snr=snr, n_steps=corrector_steps)
 
     def pc_sampler():
         with torch.no_grad():

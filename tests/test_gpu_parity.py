@@ -333,6 +333,13 @@ def test_headline_batch_of_8_is_batch_invariant_and_matches_oracle():
     ids = [10, 11, 12, 13, 14, 15, 16, 17]
     X8, nfe = m.engine().pc_sample(Y, sc, seed=21, utt_ids=ids)
     assert nfe == 2
+    # the same call again: now captured into a CUDA graph (second call) and replayed (third) - full-width network, every conv
+    # schedule (CTA pairs, persistent tiles, one tile per CTA) inside the graph
+    r0 = m.engine().graph_replays()
+    for _ in range(2):
+        Xg, _ = m.engine().pc_sample(Y, sc, seed=21, utt_ids=ids)
+        assert torch.equal(Xg, X8), "graph replay differs from the eager trajectory"
+    assert m.engine().graph_replays() == r0 + 2
     for b in (0, 3, 7):
         X1, _ = m.engine().pc_sample(Y[b:b + 1], sc, seed=21, utt_ids=[ids[b]])
         assert torch.equal(X1[0], X8[b]), f"utterance {b} depends on the batch"
