@@ -39,6 +39,7 @@
 #define STORM_TC_PRODUCER_TIMING 0
 #endif
 
+
 namespace storm {
 
 namespace {
@@ -224,6 +225,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, flo
   ra = a - __uint_as_float(u << 16);
   rb = b - __uint_as_float(u & 0xFFFF0000u);
   return u;
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t x) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -1015,22 +1022,50 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
   asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
   if (warp < Q_NPW) {
     // =================================== activation producers ==========================================
-    const int ps = tid;                                     // halo pixel slot of this thread
-    const bool present = ps < Q_NP;
-    const int hy = ps / Q_HX, hxx = ps - hy * Q_HX;
-    const bool interior = present && !(hy == 0 || hy == Q_HY - 1 || hxx == 0 || hxx == Q_HX - 1);
-    const uint32_t uoff = (uint32_t)ps * 16u;
+    // Coalesced mapping: the 8 lanes of a lane group (4 with the bf16 x 3 split) read one pixel's 128-byte (64-byte) chunk line
+    // together, 16 bytes = 4 channels per lane, so one load instruction of a warp touches 4 (8) lines instead of 32.  The L1
+    // tag stage looks up one line per cycle; with one pixel per thread it was the producers' limit (ncu: l1tex 64-75 % busy
+    // on the launches with a 1x1 skip segment, profiles/r2_bench_history.md).  A lane then owns the same 4 channels of
+    // 8 (4) different pixels of a chunk: the GroupNorm scale / shift is read once per chunk instead of once per pixel.
+    constexpr int PIECES = 4 * NH;                 // 16-byte pieces per pixel and K chunk
+    constexpr int PPL = 32 / PIECES;               // pixels per load instruction
+    constexpr int J = PIECES;                      // load instructions per chunk: 32 pixel slots per warp
+    const int piece = lane % PIECES, grp = lane / PIECES;
+    uint32_t lane_off16, lane_off8 = 0;            // byte offset of this lane's 4 channels inside a stage (pixel term added per load)
+    if constexpr (PREC == 1) {
+      lane_off16 = (uint32_t)(piece >> 2) * (uint32_t)c.a_plane + (uint32_t)(((piece >> 1) & 1) * Q_NP) * 16u + (uint32_t)(piece & 1) * 8u;
+      lane_off8 = 2u * (uint32_t)c.a_plane + (uint32_t)((piece >> 2) * Q_NP) * 16u + (uint32_t)(piece & 3) * 4u;
+    } else {
+      lane_off16 = (uint32_t)((piece >> 1) * Q_NP) * 16u + (uint32_t)(piece & 1) * 8u;
+    }
+    const int slot0 = warp * 32 + grp;             // pixel slot of load j: slot0 + j * PPL
     int stage = 0;
     uint32_t phase = 0;
     int ntile_c = 0;
     QTileIter ti;
     int tile;
     while (ti.next(c, tile)) {
-      // ---- new tile: this thread's pixel, the sample's GroupNorm table (shared memory, double buffered), operand scale
+      // ---- new tile: this lane's pixels, the sample's GroupNorm table (shared memory, double buffered), operand scale
       const QTile t = q_tile(c, tile);
-      const int y = t.ty0 + hy - 1, x = t.tx0 + hxx - 1;
-      const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (t.b * p.H + y) * p.W + x : -1;
-      const bool valid = upix >= 0;
+      int upix[J];
+      uint32_t pmask = 0, imask = 0;               // bit j: slot exists / is an interior (non-halo) pixel
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int ps = slot0 + j * PPL;
+        const bool present = ps < Q_NP;
+        const int hy = ps / Q_HX, hxx = ps - hy * Q_HX;
+        const bool interior = present && !(hy == 0 || hy == Q_HY - 1 || hxx == 0 || hxx == Q_HX - 1);
+        const int y = t.ty0 + hy - 1, x = t.tx0 + hxx - 1;
+        upix[j] = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (t.b * p.H + y) * p.W + x : -1;
+        pmask |= (uint32_t)present << j;
+        imask |= (uint32_t)interior << j;
+      }
+      // L2 prefetch duty: lane (piece, grp) looks after the pixel of load j = piece, so the 32 lanes cover the warp's 32 slots
+      int upix_pf = -1;
+      bool interior_pf = false;
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        if (j == piece) { upix_pf = upix[j]; interior_pf = (imask >> j) & 1u; }
       const uint32_t tab0 = ss_base + (uint32_t)(ntile_c & 1) * (uint32_t)c.ss_c * 8u;
       if (c.ss_c) {
         const float2* gs = reinterpret_cast<const float2*>(p.seg[0].ss) + (size_t)t.b * c.ss_c;
@@ -1058,92 +1093,110 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
       int si, chk;
       while (it.next(si, chk)) {
         const ConvSeg& s = p.seg[si];
-        const bool active = present && (s.taps == 9 || interior);
+        const uint32_t amask = s.taps == 9 ? pmask : imask;  // a 1x1 segment only needs the interior pixels
         const int c0 = chk * (16 * NH);
-        // ---- all loads of this K chunk (one pixel, 16 * NH channels) at once: one round trip per stage
-        float4 raw[4 * NH];
-        if (active && valid) {
+        // ---- all loads of this K chunk at once: one round trip per stage
+        float4 raw[J];
+        {
           const float* src;
           int Cs, cl;
           if (c0 < s.C0) { src = s.src0; Cs = s.C0; cl = c0; } else { src = s.src1; Cs = s.C1; cl = c0 - s.C0; }
-          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)upix * Cs + cl);
+          src += cl + 4 * piece;
 #pragma unroll
-          for (int j = 0; j < 4 * NH; ++j) raw[j] = __ldg(gp + j);
+          for (int j = 0; j < J; ++j) {
+            raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((amask >> j) & 1u) && upix[j] >= 0) raw[j] = __ldg(reinterpret_cast<const float4*>(src + (size_t)upix[j] * Cs));
+          }
         }
         // ---- L2 prefetch of the next chunk in schedule order (a 32-channel chunk is one 128-byte line per pixel)
         {
           ChunkIter peek = it;
           int nsi, nch;
-          if (valid && peek.next(nsi, nch)) {
+          if (upix_pf >= 0 && peek.next(nsi, nch)) {
             const ConvSeg& ns = p.seg[nsi];
-            if (ns.taps == 9 || interior) {
+            if (ns.taps == 9 || interior_pf) {
               const int n0c = nch * (16 * NH);
               const float* nsrc;
               int nCs, ncl;
               if (n0c < ns.C0) { nsrc = ns.src0; nCs = ns.C0; ncl = n0c; } else { nsrc = ns.src1; nCs = ns.C1; ncl = n0c - ns.C0; }
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix * nCs + ncl));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (size_t)upix_pf * nCs + ncl));
             }
           }
         }
+        float4 t0 = make_float4(1.f, 0.f, 1.f, 0.f), t1 = t0;            // (scale, shift) of this lane's 4 channels
+        if (s.ss) {
+          const uint32_t tab = tab0 + 8u * (uint32_t)(c0 + 4 * piece);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0.x), "=f"(t0.y), "=f"(t0.z), "=f"(t0.w) : "r"(tab));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t1.x), "=f"(t1.y), "=f"(t1.z), "=f"(t1.w) : "r"(tab + 16u));
+        }
         mbar_wait_relaxed(a_empty(stage), phase ^ 1);
-        const uint32_t st_base = a_base + stage * c.a_stage;
-        if (active) {
+        const uint32_t st_base = a_base + stage * c.a_stage + (uint32_t)slot0 * 16u;
+        if constexpr (PREC == 1) {
 #pragma unroll
-          for (int hsel = 0; hsel < NH; ++hsel) {
-            const uint32_t tab = tab0 + 8u * (uint32_t)(c0 + 16 * hsel);
-            uint2 a8[2], l8[2];
+          for (int jp = 0; jp < J / 2; ++jp) {               // two pixels (loads 2jp, 2jp + 1) per 8-wide conversion
+            const float4 v0 = raw[2 * jp], v1 = raw[2 * jp + 1];
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (s.ss) {
 #pragma unroll
-            for (int kh = 0; kh < 2; ++kh) {
-              const uint32_t off = st_base + (uint32_t)(kh * Q_NP) * 16u + uoff;
-              const float4 v0 = raw[4 * hsel + 2 * kh], v1 = raw[4 * hsel + 2 * kh + 1];
-              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-              if (valid) {
-                if (s.ss) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float4 t4;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
-                                 : "r"(tab + (uint32_t)(kh * 8 + 2 * j) * 8u));
-                    v[2 * j] = fmaf(v[2 * j], t4.x, t4.y);
-                    v[2 * j + 1] = fmaf(v[2 * j + 1], t4.z, t4.w);
-                  }
-                }
-                if (s.silu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
-                }
-                if (alpha != 1.0f) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] *= alpha;
-                }
-              }
-              if constexpr (PREC == 1) {
-                uint4 h16 = make_uint4(0, 0, 0, 0);
-                a8[kh] = make_uint2(0, 0);
-                l8[kh] = make_uint2(0, 0);
-                if (valid) split_f16f8(v, h16, a8[kh], l8[kh]);
-                st_shared_v4(off + (uint32_t)hsel * (uint32_t)c.a_plane, h16);          // f16 plane of this half, k-core kh
-              } else {
-                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-                if (valid) {
-                  float rr[8], d0, d1;
-                  hi.x = pack_bf16x2(v[0], v[1], rr[0], rr[1]);
-                  hi.y = pack_bf16x2(v[2], v[3], rr[2], rr[3]);
-                  hi.z = pack_bf16x2(v[4], v[5], rr[4], rr[5]);
-                  hi.w = pack_bf16x2(v[6], v[7], rr[6], rr[7]);
-                  lo.x = pack_bf16x2(rr[0], rr[1], d0, d1);
-                  lo.y = pack_bf16x2(rr[2], rr[3], d0, d1);
-                  lo.z = pack_bf16x2(rr[4], rr[5], d0, d1);
-                  lo.w = pack_bf16x2(rr[6], rr[7], d0, d1);
-                }
-                st_shared_v4(off, hi);
-                st_shared_v4(off + (uint32_t)c.a_plane, lo);
+              for (int h = 0; h < 2; ++h) {
+                v[4 * h] = fmaf(v[4 * h], t0.x, t0.y);
+                v[4 * h + 1] = fmaf(v[4 * h + 1], t0.z, t0.w);
+                v[4 * h + 2] = fmaf(v[4 * h + 2], t1.x, t1.y);
+                v[4 * h + 3] = fmaf(v[4 * h + 3], t1.z, t1.w);
               }
             }
-            if constexpr (PREC == 1) {       // fp8 planes: k-core hsel holds the 16 channels of this half
-              const uint32_t o8 = st_base + 2u * (uint32_t)c.a_plane + (uint32_t)(hsel * Q_NP) * 16u + uoff;
-              st_shared_v4(o8, make_uint4(a8[0].x, a8[0].y, a8[1].x, a8[1].y));
-              st_shared_v4(o8 + (uint32_t)c.a_plane, make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y));
+            if (s.silu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = silu_fast(v[j]);
+            }
+            if (alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= alpha;
+            }
+            uint4 h16;
+            uint2 a8, l8;
+            split_f16f8(v, h16, a8, l8);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = 2 * jp + h;
+              if ((amask >> j) & 1u) {
+                const bool valid = upix[j] >= 0;               // pixels outside the image are the conv's zero padding
+                const uint32_t po = st_base + (uint32_t)(j * PPL) * 16u;
+                st_shared_v2(po + lane_off16, valid ? (h ? h16.z : h16.x) : 0u, valid ? (h ? h16.w : h16.y) : 0u);
+                st_shared_b32(po + lane_off8, valid ? (h ? a8.y : a8.x) : 0u);
+                st_shared_b32(po + lane_off8 + (uint32_t)c.a_plane, valid ? (h ? l8.y : l8.x) : 0u);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            float v[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+            if (s.ss) {
+              v[0] = fmaf(v[0], t0.x, t0.y);
+              v[1] = fmaf(v[1], t0.z, t0.w);
+              v[2] = fmaf(v[2], t1.x, t1.y);
+              v[3] = fmaf(v[3], t1.z, t1.w);
+            }
+            if (s.silu) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] = silu_fast(v[k]);
+            }
+            if (alpha != 1.0f) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] *= alpha;
+            }
+            if ((amask >> j) & 1u) {
+              const bool valid = upix[j] >= 0;
+              float rr[4], d0, d1;
+              uint32_t hx = pack_bf16x2(v[0], v[1], rr[0], rr[1]);
+              uint32_t hy2 = pack_bf16x2(v[2], v[3], rr[2], rr[3]);
+              uint32_t lx = pack_bf16x2(rr[0], rr[1], d0, d1);
+              uint32_t ly = pack_bf16x2(rr[2], rr[3], d0, d1);
+              if (!valid) { hx = hy2 = lx = ly = 0u; }
+              const uint32_t po = st_base + (uint32_t)(j * PPL) * 16u + lane_off16;
+              st_shared_v2(po, hx, hy2);
+              st_shared_v2(po + (uint32_t)c.a_plane, lx, ly);
             }
           }
         }
@@ -1718,6 +1771,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
           const int y = ty0 + u * 4 + (lane >> 3), x = tx0 + (lane & 7);
           if (y < p.H && x < p.W)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + m_lo + q * 32));
+        }
+      } else if (p.res_up && m_lo + q * 32 < p.Cout) {
+        // half-resolution residual: the tile's 32 x 8 pixels need 18 x 6 low-resolution pixels (one 128-byte line each for this
+        // warp's 32 channels); pull them into L2 while the tile's MMAs are still running
+        const int Hl = p.H >> 1, Wl = p.W >> 1;
+        for (int i = lane; i < 18 * 6; i += 32) {
+          const int y = (ty0 >> 1) - 1 + i / 6, x = (tx0 >> 1) - 1 + i % 6;
+          if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + m_lo + q * 32));
         }
       }
       mbar_wait_relaxed(acc_full(buf), fph[buf]);
