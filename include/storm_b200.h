@@ -238,6 +238,12 @@ int storm_debug_conv_ex(int32_t engine, const float* x0, const float* x1, int32_
                         const float* bias, const float* res, const float* res_up, float out_scale, float* out, int32_t B,
                         int32_t H, int32_t W, int32_t max_prec, long long* dbg_dev, float* ms_out, void* stream);
 
+/* Test hook: the FIR resampling pass of a BigGAN res block (layerspp.py:245-258, up_or_down_sampling.py:195-257, taps
+ * [1,3,3,1]): x [B][H][W][C] fp32 NHWC; mode 1 = x2 up, 2 = x2 down; h_out = FIR(SiLU(x * scale + shift)) with
+ * ss = [B][C] (scale, shift) pairs (NULL: FIR of x itself), x_out = FIR(x); either output may be NULL. */
+int storm_debug_resample(const float* x, const float* ss, float* h_out, float* x_out, int32_t B, int32_t H, int32_t W, int32_t C,
+                         int32_t mode, void* stream);
+
 /* Test hook: single-head attention o = softmax(q k^T / sqrt(C)) v on [B][N][C] fp32 device tensors
  * (AttnBlockpp core, layerspp.py:82-86).  engine 0 = tcgen05 kernel (v must be given channel-major [B][C][N]),
  * 1 = SIMT kernel (v token-major [B][N][C]). */

@@ -93,6 +93,8 @@ _PROTOS = {
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.POINTER(C.c_float), C.c_void_p]),
+    "storm_debug_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
     "storm_debug_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]),
     "storm_set_graph": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -518,6 +520,20 @@ def debug_attention(engine: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
     vv = v.transpose(1, 2).contiguous() if engine == 0 else v
     _check(lib().storm_debug_attention(engine, q.data_ptr(), k.data_ptr(), vv.data_ptr(), o.data_ptr(), B, N, Cc, _stream()))
     return o
+
+
+def debug_resample(x: torch.Tensor, ss=None, mode: int = 2, want_h: bool = True, want_x: bool = True):
+    """Test hook: FIR resampling pass ([B, H, W, C] fp32 NHWC CUDA; mode 1 = up, 2 = down) -> (FIR(SiLU(x * scale + shift)), FIR(x))."""
+    x = _cf(x, "x")
+    B, H, W, Cc = x.shape
+    OH, OW = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
+    ss_t = _cf(ss, "ss") if ss is not None else None
+    h = torch.empty((B, OH, OW, Cc), device=x.device) if want_h else None
+    xo = torch.empty((B, OH, OW, Cc), device=x.device) if want_x else None
+    with torch.cuda.device(x.device):
+        _check(lib().storm_debug_resample(x.data_ptr(), ss_t.data_ptr() if ss_t is not None else None, h.data_ptr() if want_h else None,
+                                          xo.data_ptr() if want_x else None, B, H, W, Cc, mode, _stream()))
+    return h, xo
 
 
 def philox_normal(seed: int, utt_id: int, draw: int, n: int, device=None) -> torch.Tensor:

@@ -806,7 +806,7 @@ static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out
     if (lvl != nres - 1) {
       Act pd;      // input pyramid one level down (ncsnpp.py:353)
       STORM_TRY(f.alloc(pd, pyr_in.H / 2, pyr_in.W / 2, PYR_DOWN_CH));
-      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, pyr_in.C, PYR_DOWN_CH, st));
+      LAUNCH(h, launch_fir_down_small(pyr_in.p, pd.p, B, pyr_in.H, pyr_in.W, pyr_in.C, PYR_DOWN_CH, inch, st));
       f.release(pyr_in);
       pyr_in = pd;
       const Mod& dm = h->mods[mi];
@@ -1452,6 +1452,18 @@ int storm_debug_conv_ex(int32_t engine, const float* x0, const float* x1, int32_
   cudaError_t e = cudaStreamSynchronize(st);
   for (void* q : owned) cudaFree(q);
   if (rc == 0 && e != cudaSuccess) return fail(STORM_E_CUDA, std::string("storm_debug_conv: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int storm_debug_resample(const float* x, const float* ss, float* h_out, float* x_out, int32_t B, int32_t H, int32_t W, int32_t C,
+                         int32_t mode, void* stream) {
+  if (!x || (!h_out && !x_out) || (mode != 1 && mode != 2)) return fail(STORM_E_INVALID, "storm_debug_resample: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Act a{};
+  a.p = const_cast<float*>(x); a.B = B; a.H = H; a.W = W; a.C = C;
+  int rc = launch_resample(a, ss, h_out, x_out, mode, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) return fail(STORM_E_CUDA, std::string("storm_debug_resample: ") + cudaGetErrorString(e));
   return rc;
 }
 

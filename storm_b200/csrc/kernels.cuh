@@ -31,7 +31,7 @@ int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const f
 // h_out = FIR(SiLU(x*scale+shift)) (if ss) and x_out = FIR(x); mode: 1 = up x2, 2 = down x2.  C % 4 == 0.
 int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, int mode, cudaStream_t st);
 // small-channel scalar variant (input pyramid): C input channels -> CO >= C output channels, the extra ones zero
-int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, int CO, cudaStream_t st);
+int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, int CO, int Creal, cudaStream_t st);
 
 // ---- input / pyramid / head ---------------------------------------------------------------------------
 // complex planes -> NHWC real [B][F][T][2nc] with 2x-1 (ncsnpp.py:290-296,321-323); plane ch of sample b

@@ -417,22 +417,36 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const float* __rest
   // first staged input pixel
   const int iy0 = MODE == 1 ? tyi * 8 - 1 : tyi * 16 - 1;
   const int ix0 = MODE == 1 ? txi * 8 - 1 : txi * 16 - 1;
-  for (int e = threadIdx.x; e < TI * TI * C4; e += 256) {
+  // all loads of the staged tile are issued before the first is consumed: one DRAM round trip per CTA instead of one per
+  // loop iteration (the kernel was latency-bound: 1.4 TB/s on the down variant)
+  constexpr int NE = TI * TI * C4, NIT = (NE + 255) / 256;
+  float4 rawv[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int e = threadIdx.x + it * 256;
     const int c4 = e % C4, pix = e / C4;
     const int py = pix / TI, px = pix - py * TI;
     const int y = iy0 + py, xx = ix0 + px;
-    float4 raw = make_float4(0, 0, 0, 0), act = make_float4(0, 0, 0, 0);
-    if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) {
-      raw = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + y) * W + xx) * C + c0) + c4);
-      act = raw;
-      if (ss) {
-        const float4* sp = reinterpret_cast<const float4*>(ss + ((size_t)b * C + c0 + c4 * 4) * 2);
-        const float4 a = __ldg(sp), d = __ldg(sp + 1);
-        act.x = silu_fast(fmaf(raw.x, a.x, a.y));
-        act.y = silu_fast(fmaf(raw.y, a.z, a.w));
-        act.z = silu_fast(fmaf(raw.z, d.x, d.y));
-        act.w = silu_fast(fmaf(raw.w, d.z, d.w));
-      }
+    rawv[it] = make_float4(0, 0, 0, 0);
+    if (e < NE && (unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W)
+      rawv[it] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + y) * W + xx) * C + c0) + c4);
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int e = threadIdx.x + it * 256;
+    if (e >= NE) break;
+    const int c4 = e % C4, pix = e / C4;
+    const int py = pix / TI, px = pix - py * TI;
+    const int y = iy0 + py, xx = ix0 + px;
+    const float4 raw = rawv[it];
+    float4 act = raw;
+    if (ss && (unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) {   // outside the image both tensors are the FIR's zero padding
+      const float4* sp = reinterpret_cast<const float4*>(ss + ((size_t)b * C + c0 + c4 * 4) * 2);
+      const float4 a = __ldg(sp), d = __ldg(sp + 1);
+      act.x = silu_fast(fmaf(raw.x, a.x, a.y));
+      act.y = silu_fast(fmaf(raw.y, a.z, a.w));
+      act.z = silu_fast(fmaf(raw.z, d.x, d.y));
+      act.w = silu_fast(fmaf(raw.w, d.z, d.w));
     }
     *reinterpret_cast<float4*>(sAct + pix * PS + c4 * 4) = act;
     *reinterpret_cast<float4*>(sRaw + pix * PS + c4 * 4) = raw;
@@ -480,9 +494,176 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const float* __rest
   }
 }
 
+// DOWN, separable and streamed through registers: warp = one output column, lane = 4 channels (a warp reads 512 contiguous
+// bytes per pixel), every thread walks R output rows = 2R + 2 input rows; per input row 4 loads (columns 2ox-1 .. 2ox+2, shared
+// with the neighbouring warp through L1), the horizontal FIR, and two vertical accumulations.  9 loads per output instead of 16
+// shared-memory reads, no staging pass, no barrier; GroupNorm scale / shift of the thread's channels live in registers.
+template <int R>
+__global__ void __launch_bounds__(256) resample_down_strip_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+                                                                  float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OH = H / 2, OW = W / 2;
+  const int ncg = C / 128;
+  const int cg = blockIdx.z % ncg, b = blockIdx.z / ncg;
+  const int c = cg * 128 + lane * 4;
+  const int ox = blockIdx.x * 8 + warp;
+  if (ox >= OW) return;
+  const int oy0 = blockIdx.y * R;
+  float4 s0 = make_float4(1.f, 0.f, 1.f, 0.f), s1 = s0;          // (scale, shift) pairs of the 4 channels
+  if (ss) {
+    const float4* sp = reinterpret_cast<const float4*>(ss + ((size_t)b * C + c) * 2);
+    s0 = __ldg(sp);
+    s1 = __ldg(sp + 1);
+  }
+  const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  const float* xb = x + (size_t)b * H * W * C + c;
+  float4 aH = make_float4(0, 0, 0, 0), aX = aH, bH = aH, bX = aH;     // a: output row r, b: output row r - 1
+#pragma unroll
+  for (int r = 0; r <= R; ++r) {
+    float4 v[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int y = 2 * (oy0 + r) - 1 + t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xx = 2 * ox - 1 + j;
+        v[t][j] = make_float4(0, 0, 0, 0);
+        if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) v[t][j] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)y * W + xx) * C));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int y = 2 * (oy0 + r) - 1 + t;
+      float4 hx = make_float4(0, 0, 0, 0), hh = hx;                // horizontal FIR of the raw / activated row
+      if ((unsigned)y < (unsigned)H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int xx = 2 * ox - 1 + j;
+          const float4 raw = v[t][j];
+          hx.x = fmaf(k[j], raw.x, hx.x); hx.y = fmaf(k[j], raw.y, hx.y); hx.z = fmaf(k[j], raw.z, hx.z); hx.w = fmaf(k[j], raw.w, hx.w);
+          if (h_out && (unsigned)xx < (unsigned)W) {                // outside the image the activated tensor is zero padding too
+            float4 a = raw;
+            if (ss) {
+              a.x = silu_fast(fmaf(raw.x, s0.x, s0.y));
+              a.y = silu_fast(fmaf(raw.y, s0.z, s0.w));
+              a.z = silu_fast(fmaf(raw.z, s1.x, s1.y));
+              a.w = silu_fast(fmaf(raw.w, s1.z, s1.w));
+            }
+            hh.x = fmaf(k[j], a.x, hh.x); hh.y = fmaf(k[j], a.y, hh.y); hh.z = fmaf(k[j], a.z, hh.z); hh.w = fmaf(k[j], a.w, hh.w);
+          }
+        }
+      }
+      // input row 2(oy0+r)-1+t is tap t of output row r and tap t + 2 of output row r - 1
+      aH.x = fmaf(k[t], hh.x, aH.x); aH.y = fmaf(k[t], hh.y, aH.y); aH.z = fmaf(k[t], hh.z, aH.z); aH.w = fmaf(k[t], hh.w, aH.w);
+      aX.x = fmaf(k[t], hx.x, aX.x); aX.y = fmaf(k[t], hx.y, aX.y); aX.z = fmaf(k[t], hx.z, aX.z); aX.w = fmaf(k[t], hx.w, aX.w);
+      bH.x = fmaf(k[t + 2], hh.x, bH.x); bH.y = fmaf(k[t + 2], hh.y, bH.y); bH.z = fmaf(k[t + 2], hh.z, bH.z); bH.w = fmaf(k[t + 2], hh.w, bH.w);
+      bX.x = fmaf(k[t + 2], hx.x, bX.x); bX.y = fmaf(k[t + 2], hx.y, bX.y); bX.z = fmaf(k[t + 2], hx.z, bX.z); bX.w = fmaf(k[t + 2], hx.w, bX.w);
+    }
+    if (r > 0 && oy0 + r - 1 < OH) {
+      const size_t o = (((size_t)b * OH + oy0 + r - 1) * OW + ox) * C + c;
+      if (h_out) *reinterpret_cast<float4*>(h_out + o) = bH;
+      if (x_out) *reinterpret_cast<float4*>(x_out + o) = bX;
+    }
+    bH = aH; bX = aX;
+    aH = make_float4(0, 0, 0, 0); aX = aH;
+  }
+}
+
+// UP, streamed the same way: warp = one input column (two output columns), lane = 4 channels, R input rows (+ one halo row on
+// each side) per thread; per input row 3 loads, the horizontal pair H0 = a[i-1]/4 + 3a[i]/4, H1 = 3a[i]/4 + a[i+1]/4, and with the
+// previous row's pair the two output rows 2(i-1)+1 = 3H[i-1]/4 + H[i]/4 and 2i = H[i-1]/4 + 3H[i]/4.
+template <int R>
+__global__ void __launch_bounds__(256) resample_up_strip_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+                                                                float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OW = 2 * W;
+  const int ncg = C / 128;
+  const int cg = blockIdx.z % ncg, b = blockIdx.z / ncg;
+  const int c = cg * 128 + lane * 4;
+  const int ix = blockIdx.x * 8 + warp;
+  if (ix >= W) return;
+  const int iy0 = blockIdx.y * R;
+  float4 s0 = make_float4(1.f, 0.f, 1.f, 0.f), s1 = s0;
+  if (ss) {
+    const float4* sp = reinterpret_cast<const float4*>(ss + ((size_t)b * C + c) * 2);
+    s0 = __ldg(sp);
+    s1 = __ldg(sp + 1);
+  }
+  const float* xb = x + (size_t)b * H * W * C + c;
+  auto lin = [](float wa, const float4& a, float wb, const float4& bq) {
+    return make_float4(fmaf(wb, bq.x, wa * a.x), fmaf(wb, bq.y, wa * a.y), fmaf(wb, bq.z, wa * a.z), fmaf(wb, bq.w, wa * a.w));
+  };
+  const float4 zero = make_float4(0, 0, 0, 0);
+  float4 pH0 = zero, pH1 = zero, pX0 = zero, pX1 = zero;           // horizontal pairs of the previous input row
+#pragma unroll
+  for (int r = -1; r <= R; ++r) {
+    const int y = iy0 + r;
+    float4 v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int xx = ix - 1 + j;
+      v[j] = zero;
+      if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) v[j] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)y * W + xx) * C));
+    }
+    float4 cH0 = zero, cH1 = zero, cX0 = zero, cX1 = zero;
+    if ((unsigned)y < (unsigned)H) {
+      if (x_out) { cX0 = lin(0.25f, v[0], 0.75f, v[1]); cX1 = lin(0.75f, v[1], 0.25f, v[2]); }
+      if (h_out) {
+        float4 a[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int xx = ix - 1 + j;
+          a[j] = v[j];
+          if (ss && (unsigned)xx < (unsigned)W) {                  // outside the image the activated tensor is zero padding too
+            a[j].x = silu_fast(fmaf(v[j].x, s0.x, s0.y));
+            a[j].y = silu_fast(fmaf(v[j].y, s0.z, s0.w));
+            a[j].z = silu_fast(fmaf(v[j].z, s1.x, s1.y));
+            a[j].w = silu_fast(fmaf(v[j].w, s1.z, s1.w));
+          }
+        }
+        cH0 = lin(0.25f, a[0], 0.75f, a[1]);
+        cH1 = lin(0.75f, a[1], 0.25f, a[2]);
+      }
+    }
+    // output rows 2(y-1)+1 (belongs to input row y-1) and 2y (input row y)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int iy = y - 1 + half;                                 // owning input row
+      if (iy < iy0 || iy >= iy0 + R || iy >= H) continue;
+      const int oy = 2 * iy + (half ? 0 : 1);
+      const float wp = half ? 0.25f : 0.75f, wc = half ? 0.75f : 0.25f;
+      const size_t o = (((size_t)b * 2 * H + oy) * OW + 2 * ix) * C + c;
+      if (h_out) {
+        *reinterpret_cast<float4*>(h_out + o) = lin(wp, pH0, wc, cH0);
+        *reinterpret_cast<float4*>(h_out + o + C) = lin(wp, pH1, wc, cH1);
+      }
+      if (x_out) {
+        *reinterpret_cast<float4*>(x_out + o) = lin(wp, pX0, wc, cX0);
+        *reinterpret_cast<float4*>(x_out + o + C) = lin(wp, pX1, wc, cX1);
+      }
+    }
+    pH0 = cH0; pH1 = cH1; pX0 = cX0; pX1 = cX1;
+  }
+}
+
 int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, int mode, cudaStream_t st) {
   if (x.C % 4 != 0) return fail(-1, "resample: C must be a multiple of 4");
   if (mode == 2 && ((x.H | x.W) & 1)) return fail(-1, "resample: downsampling needs even extents");
+  static const bool no_strip = getenv("STORM_B200_RESAMPLE_TILED") && atoi(getenv("STORM_B200_RESAMPLE_TILED")) != 0;
+  if (mode == 1 && x.C % 128 == 0 && !no_strip) {
+    constexpr int R = 8;
+    dim3 grid(ceil_div(x.W, 8), ceil_div(x.H, R), x.B * (x.C / 128));
+    resample_up_strip_kernel<R><<<grid, 256, 0, st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
+  if (mode == 2 && x.C % 128 == 0 && !no_strip) {
+    constexpr int R = 8;
+    dim3 grid(ceil_div(x.W / 2, 8), ceil_div(x.H / 2, R), x.B * (x.C / 128));
+    resample_down_strip_kernel<R><<<grid, 256, 0, st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    STORM_LAUNCH_CHECK();
+    return 0;
+  }
   if (mode == 1 && x.C % 32 == 0) {
     dim3 grid(ceil_div(x.H, 8) * ceil_div(x.W, 8), x.C / 32, x.B);
     resample_tiled_kernel<1><<<grid, 256, 2 * 10 * 10 * 32 * sizeof(float), st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
@@ -508,37 +689,54 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
   return 0;
 }
 
-// C input channels -> CO >= C output channels (channels beyond C are written as zeros: K padding of the tensor-core kernel)
-__global__ void fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C, int CO) {
+// C input channels -> CO >= C output channels (channels beyond C are written as zeros: K padding of the tensor-core kernel).
+// Only the first Creal input channels carry data (the rest are that same zero padding): one thread per output pixel and
+// group of 4 real channels issues its 16 tap loads together, the remaining channels are stored as zeros.
+__global__ void __launch_bounds__(256) fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W,
+                                                             int C, int CO, int Creal) {
   const int OH = H / 2, OW = W / 2;
-  const size_t total = (size_t)B * OH * OW * CO;
+  const int n4 = (Creal + 3) / 4;                                  // float4 groups with data
+  const size_t total = (size_t)B * OH * OW * n4;
   const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % CO;
-    size_t r = i / CO;
+    const int c4 = i % n4;
+    size_t r = i / n4;
     const int ox = r % OW; r /= OW;
     const int oy = r % OH;
     const int b = r / OH;
-    float acc = 0.f;
-    if (c < C) {
-      for (int jy = 0; jy < 4; ++jy) {
-        int y = 2 * oy - 1 + jy;
-        if ((unsigned)y >= (unsigned)H) continue;
-        for (int jx = 0; jx < 4; ++jx) {
-          int xx = 2 * ox - 1 + jx;
-          if ((unsigned)xx >= (unsigned)W) continue;
-          acc = fmaf(k[jy] * k[jx], __ldg(x + (((size_t)b * H + y) * W + xx) * C + c), acc);
-        }
+    float4 v[16];
+#pragma unroll
+    for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+      for (int jx = 0; jx < 4; ++jx) {
+        const int y = 2 * oy - 1 + jy, xx = 2 * ox - 1 + jx;
+        v[jy * 4 + jx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W)
+          v[jy * 4 + jx] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + y) * W + xx) * C) + c4);
       }
-    }
-    out[i] = acc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int jy = 0; jy < 4; ++jy)                                   // same tap order as the scalar loop it replaces
+#pragma unroll
+      for (int jx = 0; jx < 4; ++jx) {
+        const float wgt = k[jy] * k[jx];
+        acc.x = fmaf(wgt, v[jy * 4 + jx].x, acc.x);
+        acc.y = fmaf(wgt, v[jy * 4 + jx].y, acc.y);
+        acc.z = fmaf(wgt, v[jy * 4 + jx].z, acc.z);
+        acc.w = fmaf(wgt, v[jy * 4 + jx].w, acc.w);
+      }
+    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * OH + oy) * OW + ox) * CO);
+    o[c4] = acc;
+    if (c4 == 0)
+      for (int q = n4; q < CO / 4; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, int CO, cudaStream_t st) {
-  size_t total = (size_t)B * (H / 2) * (W / 2) * CO;
+int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C, int CO, int Creal, cudaStream_t st) {
+  if ((C & 3) || (CO & 3) || Creal > C || Creal < 1 || CO < C) return fail(-1, "fir_down_small: channel counts must be multiples of 4, Creal <= C <= CO");
+  size_t total = (size_t)B * (H / 2) * (W / 2) * ((Creal + 3) / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   if (blocks == 0) blocks = 1;
-  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C, CO);
+  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C, CO, Creal);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -551,16 +749,22 @@ __global__ void unpack_input_kernel(UnpackSrc src, float* __restrict__ out, int 
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i / HW;
     const int p = i % HW;
-    for (int ch = 0; ch < nc; ++ch) {
-      float2 v = __ldg(reinterpret_cast<const float2*>(src.p[ch]) + (size_t)b * src.bstride[ch] + p);
-      out[i * CP + 2 * ch] = 2.0f * v.x - 1.0f;
-      out[i * CP + 2 * ch + 1] = 2.0f * v.y - 1.0f;
-    }
-    for (int ch = 2 * nc; ch < CP; ++ch) out[i * CP + ch] = 0.f;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // 2x - 1 of the up to 3 complex channels, then zeros
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      if (ch < nc) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src.p[ch]) + (size_t)b * src.bstride[ch] + p);
+        f[2 * ch] = 2.0f * v.x - 1.0f;
+        f[2 * ch + 1] = 2.0f * v.y - 1.0f;
+      }
+    float4* o = reinterpret_cast<float4*>(out + i * CP);
+    o[0] = make_float4(f[0], f[1], f[2], f[3]);
+    o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    for (int q = 2; q < CP / 4; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int CP, int HW, cudaStream_t st) {
-  if (nc < 1 || nc > 3 || CP < 2 * nc) return fail(-1, "unpack_input: 1..3 complex channels");
+  if (nc < 1 || nc > 3 || CP < 8 || (CP & 3)) return fail(-1, "unpack_input: 1..3 complex channels, padded width a multiple of 4 and >= 8");
   size_t total = (size_t)B * HW;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   unpack_input_kernel<<<blocks, 256, 0, st>>>(src, out, B, nc, CP, HW);

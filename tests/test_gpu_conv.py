@@ -147,3 +147,45 @@ def test_half_resolution_residual(B, H, W, C0, Cout, max_prec):
     err = _rel(out, ref)
     print(f"res_up {B, H, W, C0, Cout} prec={max_prec}: rel-L2={err:.3e}")
     assert err < (4e-5 if max_prec else 1e-5)
+
+
+def _fir_ref(x_nhwc, mode):
+    """torch reference of upfirdn with taps [1,3,3,1] (up_or_down_sampling.py:195-257): x2 down (pad 1, stride 2, kernel / 64)
+    or x2 up (zero insertion, kernel * 4 / 64, pad 2/1)."""
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0], device=x_nhwc.device, dtype=torch.float64)
+    k2 = torch.outer(k1, k1)
+    x = x_nhwc.permute(0, 3, 1, 2).double()
+    C = x.shape[1]
+    if mode == 2:
+        w = (k2 / k2.sum())[None, None].repeat(C, 1, 1, 1)
+        y = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), w, stride=2, groups=C)
+    else:
+        w = (k2 / k2.sum() * 4.0)[None, None].repeat(C, 1, 1, 1)
+        B, _, H, W = x.shape
+        z = torch.zeros(B, C, 2 * H, 2 * W, device=x.device, dtype=torch.float64)
+        z[:, :, ::2, ::2] = x
+        y = torch.nn.functional.conv2d(torch.nn.functional.pad(z, (2, 1, 2, 1)), w.flip(-1, -2), groups=C)
+    return y.permute(0, 2, 3, 1).float()
+
+
+@pytest.mark.parametrize("mode,B,H,W,C", [
+    (2, 2, 32, 16, 128),      # streamed separable kernel (C % 128 == 0)
+    (2, 1, 20, 12, 256),      # output rows not a multiple of the strip length, odd column tiles
+    (2, 2, 16, 16, 48),       # tiled shared-memory kernel
+    (2, 1, 6, 10, 12),        # generic kernel
+    (1, 2, 16, 8, 128),
+    (1, 1, 10, 6, 96),
+    (1, 1, 6, 10, 12),
+])
+def test_fir_resample(mode, B, H, W, C):
+    """FIR resampling pass of the res blocks against a float64 torch reference: activated and raw outputs, image borders."""
+    from storm_b200 import _native
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    ss = torch.stack([1.0 + 0.3 * torch.randn(B, C, device="cuda", generator=g), 0.2 * torch.randn(B, C, device="cuda", generator=g)], dim=-1).contiguous()
+    h, xo = _native.debug_resample(x, ss, mode)
+    act = torch.nn.functional.silu(x * ss[:, None, None, :, 0] + ss[:, None, None, :, 1])
+    for got, want, name in ((h, _fir_ref(act, mode), "activated"), (xo, _fir_ref(x, mode), "raw")):
+        err = _rel(got, want)
+        print(f"fir resample mode {mode} {name} [{B},{H},{W},{C}]: rel-L2 {err:.2e}")
+        assert err < 2e-6, f"{name} mode {mode}: rel-L2 {err:.2e}"
