@@ -114,6 +114,7 @@ __device__ __forceinline__ void stage_row16(const float* __restrict__ src, uint3
 __global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                               const float* __restrict__ vT, float* __restrict__ o, int N, int C,
                                                               float scale) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * TQ;
@@ -315,7 +316,7 @@ int launch_attention_tc(const float* q, const float* k, const float* vT, float* 
     STORM_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  attn_tc_kernel<<<dim3(N / TQ, B), A_THREADS, smem, st>>>(q, k, vT, o, N, C, 1.0f / sqrtf((float)C));
+  storm_launch_m(2, attn_tc_kernel, dim3(N / TQ, B), A_THREADS, smem, st, q, k, vT, o, N, C, 1.0f / sqrtf((float)C));
   STORM_LAUNCH_CHECK();
   return 0;
 }

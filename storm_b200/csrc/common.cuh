@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 namespace storm {
 
@@ -106,5 +107,37 @@ __device__ __forceinline__ float silu_fast(float v) {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ----------------------------------------------------------------------
+// Every kernel of the engine starts with pdl_enter(): it lets the NEXT kernel of the stream be scheduled as soon as this grid's
+// CTAs are all resident (the next kernel's CTAs take the SMs this grid's tail leaves idle and run their prologue there), then
+// waits until the PREVIOUS grid has completed and its memory is visible.  Nothing global is read or written before the wait,
+// so the stream keeps its serial semantics; without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+int pdl_mode();          // STORM_B200_PDL (default 0 = off) bit 0: small kernels, bit 1: conv kernels carry the launch attribute; engine.cu
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute when enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t storm_launch_m(int mask, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = (pdl_mode() & mask) ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t storm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return storm_launch_m(1, kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
 
 }  // namespace storm

@@ -34,6 +34,7 @@ __device__ __forceinline__ float load_act(const ConvSeg& s, int b, int y, int x,
 }
 
 __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(ConvParams p) {
+  pdl_enter();
   extern __shared__ float smem[];
   float* sA = smem;               // [KC][HH][HWD]
   float* sW = smem + SA_FLOATS;   // [9][KC][BN]
@@ -182,7 +183,7 @@ int launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(ceil_div(p.W, TW) * ceil_div(p.H, TH), ceil_div(p.Cout, BN), p.B);
-  conv_simt_kernel<<<grid, NT, SMEM_BYTES, st>>>(p);
+  storm_launch(conv_simt_kernel, grid, NT, SMEM_BYTES, st, p);
   STORM_LAUNCH_CHECK();
   return 0;
 }

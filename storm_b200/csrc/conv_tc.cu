@@ -244,6 +244,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 __host__ __device__ inline int tc_mpad(int Cout) { return (Cout + 127) / 128 * 128; }
 
 __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout) {
+  pdl_enter();
   const int Mpad = tc_mpad(Cout);
   const size_t total = (size_t)(Cin / 16) * taps * Cout * 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -269,6 +270,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint16_t* __restrict
 // byte offset of (row n, byte kb) inside a plane: ((n%128)/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16  (same core-matrix layout)
 __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int taps, int io_layout,
                                   float beta) {
+  pdl_enter();
   const int Mpad = tc_mpad(Cout);
   const size_t total = (size_t)(Cin / 32) * taps * Cout * 32;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -294,6 +296,7 @@ __global__ void tc_pack_kernel_p1(const float* __restrict__ w, uint8_t* __restri
 }
 
 __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+  pdl_enter();
   float m = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float a = fabsf(w[i]);
@@ -341,8 +344,8 @@ int pack_common(const float* w, int Cout, int Cin, int taps, int io, int max_pre
   STORM_CUDA_TRY(cudaMemsetAsync(p, 0, bytes, st));
   const size_t total = (size_t)(Cin / 16) * taps * Cout * 16;
   const unsigned blocks = (unsigned)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
-  if (prec) tc_pack_kernel_p1<<<blocks, 256, 0, st>>>(w, (uint8_t*)p, Cout, Cin, taps, io, beta);
-  else tc_pack_kernel<<<blocks, 256, 0, st>>>(w, (uint16_t*)p, Cout, Cin, taps, io);
+  if (prec) storm_launch(tc_pack_kernel_p1, blocks, 256, 0, st, w, (uint8_t*)p, Cout, Cin, taps, io, beta);
+  else storm_launch(tc_pack_kernel, blocks, 256, 0, st, w, (uint16_t*)p, Cout, Cin, taps, io);
   STORM_LAUNCH_CHECK();
   out->img = p;
   out->prec = prec;
@@ -614,6 +617,7 @@ __device__ __forceinline__ float2 epilogue_unit(const ConvParams& p, const uint3
 // PREC: operand split (TcpCfg::prec), compiled in so that each instantiation only carries its own conversion code.
 template <int MAXU, int MINB, int NPW, int PREC>
 __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvParams p, TcpCfg c) {
+  pdl_launch_dependents();
   constexpr int P_PRODUCERS = NPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -647,6 +651,9 @@ __global__ void __launch_bounds__((NPW + 2) * 32, MINB) conv_tcp_kernel(ConvPara
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // Everything above (barrier init, TMEM allocation) and the weight stream (weights are constants of the model) may overlap
+  // the previous kernel's tail; every warp that reads or writes activations waits for the previous grid here.
+  if (warp != NPW) pdl_wait();
 
   if (warp < NPW) {
     // ---- per-sample operand scale alpha = 2^-e <= 1 (ConvParams::raw_ms): rms of the largest raw group brought down to <= 2^9,
@@ -987,6 +994,7 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 
 template <int PREC>
 __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, TcqCfg c) {
+  pdl_launch_dependents();
   constexpr int NH = PREC ? 2 : 1;                // 16-channel halves per K chunk
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1015,6 +1023,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // Everything above (barrier init, TMEM allocation) and the weight stream (weights are constants of the model) may overlap
+  // the previous kernel's tail; every warp that reads or writes activations waits for the previous grid here.
+  if (warp != Q_WARP_W) pdl_wait();
 
   // register re-allocation per warpgroup: every warp of a warpgroup executes the same setmaxnreg, and each role's code
   // sits INSIDE the branch that holds its setmaxnreg (ptxas budgets registers by dominance)
@@ -1405,13 +1416,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_tcq_kernel(ConvParams p, Tc
 constexpr int R_NPW = 12;                                  // producer warps: 384 threads, TWO per halo pixel (16 channels each), 180 pixels
 constexpr int R_WARP_W = 12, R_WARP_MMA = 13, R_WARP_FWD = 14, R_WARP_EPI = 16;   // epilogue warps 16-19 (TMEM lane quadrants 0-3)
 constexpr int R_THREADS = 20 * 32;
-constexpr int R_HX = 10, R_HY = 18, R_NP = R_HX * R_HY;   // halo tile of 16 rows x 8 columns
-constexpr int R_NCOL = 256;
+constexpr int R_HX = 10;                                   // halo tile of one CTA: (RH + 2) rows x 10 columns, RH = 16 or 8 tile rows per CTA
 
 struct TcrCfg {
   int sa, sw;
   int a_plane, a_stage, w_plane, w_stage;
-  int tiles_x, tiles_y, ntiles;      // 256-pixel tiles per row / column of a sample; B * tiles_y * tiles_x
+  int tiles_x, tiles_y, ntiles;      // (2 rh x 8)-pixel tiles per row / column of a sample; B * tiles_y * tiles_x
+  int rh;                            // tile rows per CTA: 16 (256-pixel tiles) or 8 (128-pixel tiles, when the full tiles would leave pairs idle)
   int ss_c;
   float acc_scale;
 };
@@ -1466,8 +1477,13 @@ __device__ __forceinline__ void bar_sync_r_producers() { asm volatile("bar.sync 
 
 // Persistent: cluster k of gridDim.x / 2 walks over tiles k, k + nclusters, ...; the accumulator (256 of the 512 TMEM columns) is double
 // buffered, so the epilogue of a tile (both CTAs drain their own 128 channels) overlaps the main loop of the next one.
+template <int RH>
 __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, TcrCfg c) {
+  pdl_launch_dependents();
   constexpr int PREC = 1;
+  constexpr int R_HY = RH + 2, R_NP = R_HX * R_HY;          // halo pixels staged per CTA
+  constexpr int R_NCOL = 16 * RH;                           // accumulator columns = pixels of the pair's tile (2 RH rows x 8)
+  constexpr int R_UNITS = R_NCOL / 32;                      // 32-pixel (4 rows x 8) groups per accumulator
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();                  // 0 = leader
@@ -1502,6 +1518,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // Everything above (barrier init, TMEM allocation) and the weight stream (weights are constants of the model) may overlap
+  // the previous kernel's tail; every warp that reads or writes activations waits for the previous grid here.
+  if (warp != R_WARP_W) pdl_wait();
 
   // registers per warpgroup (640 threads start at 96): producers 72, weight / MMA / forwarding warpgroup 64, epilogue 168
   if (warp < R_NPW) {
@@ -1518,8 +1537,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
     int ntile = 0;
     for (int tile = cl0; tile < c.ntiles; tile += ncl) {
       const int b = tile / per_b, pt = tile - b * per_b;
-      const int ty0 = (pt / c.tiles_x) * 32, tx0 = (pt % c.tiles_x) * 8;
-      const int y = ty0 + 16 * (int)rank + hy - 1, x = tx0 + hxx - 1;
+      const int ty0 = (pt / c.tiles_x) * (2 * RH), tx0 = (pt % c.tiles_x) * 8;
+      const int y = ty0 + RH * (int)rank + hy - 1, x = tx0 + hxx - 1;
       const int upix = (present && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) ? (b * p.H + y) * p.W + x : -1;
       const bool valid = upix >= 0;
       const uint32_t tab0 = ss_base + (uint32_t)(ntile & 1) * (uint32_t)c.ss_c * 8u;
@@ -1749,7 +1768,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
     uint32_t fph[2] = {0, 0};
     for (int tile = cl0; tile < c.ntiles; tile += ncl) {
       const int b = tile / per_b, pt = tile - b * per_b;
-      const int ty0 = (pt / c.tiles_x) * 32, tx0 = (pt % c.tiles_x) * 8;
+      const int ty0 = (pt / c.tiles_x) * (2 * RH), tx0 = (pt % c.tiles_x) * 8;
       const int cout = m_lo + q * 32 + lane;
       const float* tembp = p.temb ? p.temb + (size_t)b * p.temb_stride : nullptr;
       float inv_alpha = 1.0f;
@@ -1767,16 +1786,16 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
       const float asc = c.acc_scale * inv_alpha;
       if (p.res && !p.out_cm && m_lo + q * 32 < p.Cout) {
 #pragma unroll 1
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < R_UNITS; ++u) {
           const int y = ty0 + u * 4 + (lane >> 3), x = tx0 + (lane & 7);
           if (y < p.H && x < p.W)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (((size_t)b * p.H + y) * p.W + x) * p.Cout + m_lo + q * 32));
         }
       } else if (p.res_up && m_lo + q * 32 < p.Cout) {
-        // half-resolution residual: the tile's 32 x 8 pixels need 18 x 6 low-resolution pixels (one 128-byte line each for this
+        // half-resolution residual: the tile's 2 RH x 8 pixels need (RH + 2) x 6 low-resolution pixels (one 128-byte line each for this
         // warp's 32 channels); pull them into L2 while the tile's MMAs are still running
         const int Hl = p.H >> 1, Wl = p.W >> 1;
-        for (int i = lane; i < 18 * 6; i += 32) {
+        for (int i = lane; i < (RH + 2) * 6; i += 32) {
           const int y = (ty0 >> 1) - 1 + i / 6, x = (tx0 >> 1) - 1 + i % 6;
           if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_up + (((size_t)b * Hl + y) * Wl + x) * p.Cout + m_lo + q * 32));
@@ -1787,10 +1806,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_tcr_kernel(ConvParams p, Tc
       tc_fence_after();
       double s_sum = 0.0, s_sq = 0.0;
 #pragma unroll 1
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < R_UNITS; ++u) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * R_NCOL + u * 32), r);
-        if (u == 7) {                                       // every column of this buffer is in registers: hand it back
+        if (u == R_UNITS - 1) {                             // every column of this buffer is in registers: hand it back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(acc_empty_leader0 + 8u * buf);
@@ -1985,7 +2004,7 @@ static bool tcq_policy(const ConvParams& p, const TcqCfg& c) {
 static int tcq_smem_bytes(const TcqCfg& c) { return c.sa * c.a_stage + c.sw * c.w_stage + 2 * c.ss_c * 8 + 8 * (2 * c.sa + 2 * c.sw + 4) + 16; }
 
 // ---- mode R (CTA pairs) ----------------------------------------------------------------------------------
-static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
+static bool choose_cfg_r(const ConvParams& p, TcrCfg& c, int rh) {
   if (tc_mpad(p.Cout) != 256) return false;                  // 129 .. 256 output channels: one 128-row block per CTA of the pair
   if (p.H < 17 || p.W < 8) return false;
   for (int i = 0; i < p.nseg; ++i) {
@@ -1999,7 +2018,8 @@ static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
   c.acc_scale = 1.0f / p.seg[0].wscale;
   c.ss_c = p.seg[0].ss ? p.seg[0].C0 + p.seg[0].C1 : 0;
   if (c.ss_c > 1024) return false;
-  c.a_plane = R_NP * 32;
+  c.rh = rh;
+  c.a_plane = R_HX * (rh + 2) * 32;
   c.a_stage = 4 * c.a_plane;
   c.w_plane = 4096;
   c.w_stage = 3 * 4 * c.w_plane;              // one filter row: 3 taps x 16 KB
@@ -2012,7 +2032,7 @@ static bool choose_cfg_r(const ConvParams& p, TcrCfg& c) {
     if (esw >= 2) c.sw = esw;
   }
   c.tiles_x = ceil_div(p.W, 8);
-  c.tiles_y = ceil_div(p.H, 32);
+  c.tiles_y = ceil_div(p.H, 2 * rh);
   const long nt = (long)p.B * c.tiles_x * c.tiles_y;
   if (nt > (1L << 30)) return false;
   c.ntiles = (int)nt;
@@ -2024,9 +2044,20 @@ static int tcr_smem_bytes(const TcrCfg& c) { return c.sa * c.a_stage + c.sw * c.
 // (profiles/r2_bench_history.md): the pair kernel wins on every launch with 129..256 output channels, by 15..20 % on the MMA-bound
 // ones (b31.conv0 953 -> 772 us = 801 TFLOP/s algorithmic, b27.conv0 482 -> 392) and by 10..25 % on the ones with a 1x1 skip
 // segment once two producer threads share a halo pixel.
+// Tile height: 256-pixel tiles (16 rows per CTA) unless they would leave at least half of the pairs without a tile - the 32 x 32
+// levels at B = 8 are 32 such tiles for 74 pairs - in which case 128-pixel tiles (8 rows per CTA) spread the same work over twice
+// as many pairs.  STORM_B200_TCR_RH = 8 | 16 forces one (read per launch: the tests switch it).
 static bool use_mode_r(const ConvParams& p, TcrCfg& cr) {
   static const int mode = [] { const char* e = getenv("STORM_B200_TCR"); return e ? atoi(e) : 1; }();
-  return mode != 0 && choose_cfg_r(p, cr);
+  if (mode == 0 || !choose_cfg_r(p, cr, 16)) return false;
+  const char* e = getenv("STORM_B200_TCR_RH");
+  const int force = e ? atoi(e) : 0;
+  if (force == 16) return true;
+  if (force == 8 || 2 * cr.ntiles <= num_sms() / 2) {
+    TcrCfg c8;
+    if (choose_cfg_r(p, c8, 8)) cr = c8;
+  }
+  return true;
 }
 
 // which kernel runs a launch.  STORM_B200_TCQ: 0 = mode P only, 1 = mode Q wherever it is eligible, 2 (default) = the measured
@@ -2068,7 +2099,8 @@ int conv_tc_init_device() {
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 1, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcp_kernel<2, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)));
-  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcr_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
+  STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcr_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   STORM_CUDA_TRY((cudaFuncSetAttribute(conv_tcq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)));
   if (dev >= 0 && dev < 64) done[dev] = true;
@@ -2087,12 +2119,15 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     lc.blockDim = dim3(R_THREADS);
     lc.dynamicSmemBytes = tcr_smem_bytes(cr);
     lc.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
-    lc.numAttrs = 1;
-    STORM_CUDA_TRY(cudaLaunchKernelEx(&lc, conv_tcr_kernel, p, cr));
+    lc.numAttrs = (pdl_mode() & 2) ? 2 : 1;
+    if (cr.rh == 8) { STORM_CUDA_TRY(cudaLaunchKernelEx(&lc, conv_tcr_kernel<8>, p, cr)); }
+    else { STORM_CUDA_TRY(cudaLaunchKernelEx(&lc, conv_tcr_kernel<16>, p, cr)); }
     return 0;
   }
   TcqCfg cq;
@@ -2101,8 +2136,8 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     const int smem = tcq_smem_bytes(cq);
     if (smem > 227 * 1024 - 1024) return fail(-1, "conv_tc: mode Q shared-memory plan does not fit");
     const int grid = cq.ngroups < num_sms() ? cq.ngroups : num_sms();
-    if (cq.prec) conv_tcq_kernel<1><<<grid, Q_THREADS, smem, st>>>(p, cq);
-    else conv_tcq_kernel<0><<<grid, Q_THREADS, smem, st>>>(p, cq);
+    if (cq.prec) storm_launch_m(2, conv_tcq_kernel<1>, grid, Q_THREADS, smem, st, p, cq);
+    else storm_launch_m(2, conv_tcq_kernel<0>, grid, Q_THREADS, smem, st, p, cq);
     STORM_LAUNCH_CHECK();
     return 0;
   }
@@ -2111,10 +2146,10 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
   if (p.stats_out && p.stats_chunks != tc_ngrp(cp) * cp.tiles_x * cp.tiles_y) return fail(-1, "conv_tc: stats_chunks mismatch");
   const int smem = cp.sa * cp.a_stage + cp.sw * cp.w_stage + 8 * (2 * cp.sa + 2 * cp.sw + 1) + 16;
   dim3 grid(cp.tiles_x * cp.tiles_y, cp.msplit, p.B);
-  if (cp.per_sm == 2 && cp.prec) conv_tcp_kernel<2, 2, 8, 1><<<grid, 320, smem, st>>>(p, cp);
-  else if (cp.per_sm == 2) conv_tcp_kernel<2, 2, 8, 0><<<grid, 320, smem, st>>>(p, cp);
-  else if (cp.prec) conv_tcp_kernel<2, 1, 12, 1><<<grid, 448, smem, st>>>(p, cp);
-  else conv_tcp_kernel<2, 1, 12, 0><<<grid, 448, smem, st>>>(p, cp);      // np <= 612 <= 2 * 384
+  if (cp.per_sm == 2 && cp.prec) storm_launch_m(2, conv_tcp_kernel<2, 2, 8, 1>, grid, 320, smem, st, p, cp);
+  else if (cp.per_sm == 2) storm_launch_m(2, conv_tcp_kernel<2, 2, 8, 0>, grid, 320, smem, st, p, cp);
+  else if (cp.prec) storm_launch_m(2, conv_tcp_kernel<2, 1, 12, 1>, grid, 448, smem, st, p, cp);
+  else storm_launch_m(2, conv_tcp_kernel<2, 1, 12, 0>, grid, 448, smem, st, p, cp);      // np <= 612 <= 2 * 384
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -2124,7 +2159,7 @@ int tc_weight_absmax(const float* w, size_t n, float* out_host, cudaStream_t st)
   STORM_CUDA_TRY(cudaMalloc((void**)&d, sizeof(unsigned)));
   STORM_CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned), st));
   const unsigned blocks = (unsigned)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
-  absmax_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(w, n, d);
+  storm_launch(absmax_kernel, blocks ? blocks : 1, 256, 0, st, w, n, d);
   unsigned u = 0;
   cudaError_t e = cudaMemcpyAsync(&u, d, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -27,6 +27,16 @@ int fail(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch is wired through every kernel (pdl_enter / storm_launch, common.cuh) and was measured inside
+// whole benchmark runs: 0 (off) 13.34 utt/s, conv kernels only 13.27-13.34, small kernels only 13.20, everything 13.04 - with the
+// trajectory replayed as one CUDA graph the launch gaps are already hidden, and dependents that become resident early only
+// take issue slots from the running kernel.  Off by default; STORM_B200_PDL = 1 | 2 | 3 switches it on for the small kernels /
+// the conv kernels / both (profiles/r2_bench_history.md).
+int pdl_mode() {
+  static const int m = [] { const char* e = getenv("STORM_B200_PDL"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
 constexpr int PYR_CH = 16;   // channels of the (zero-padded) network input = level 0 of the input pyramid (one 16-channel K chunk)
 constexpr int PYR_DOWN_CH = 32;   // channels of the downsampled pyramid levels: a whole 32-channel K chunk, so that the down blocks'
                                   // Conv_1 + Conv_2 + Combine launches stay on the two-pass operand split

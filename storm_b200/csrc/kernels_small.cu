@@ -21,6 +21,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // weights
 // =====================================================================================================
 __global__ void pack_conv_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps) {
+  pdl_enter();
   size_t n = (size_t)Cout * Cin * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int co = i % Cout;
@@ -31,13 +32,14 @@ __global__ void pack_conv_simt_kernel(const float* __restrict__ w, float* __rest
 }
 int launch_pack_conv_simt(const float* w, float* out, int Cout, int Cin, int taps, cudaStream_t st) {
   size_t n = (size_t)Cout * Cin * taps;
-  pack_conv_simt_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, taps);
+  storm_launch(pack_conv_simt_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, w, out, Cout, Cin, taps);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void transpose_into_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int cols,
                                       int out_stride, int out_off) {
+  pdl_enter();
   size_t n = (size_t)rows * cols;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = i % rows;
@@ -47,12 +49,13 @@ __global__ void transpose_into_kernel(const float* __restrict__ w, float* __rest
 }
 int launch_transpose_into(const float* w, float* out, int rows, int cols, int out_stride, int out_off, cudaStream_t st) {
   size_t n = (size_t)rows * cols;
-  transpose_into_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, rows, cols, out_stride, out_off);
+  storm_launch(transpose_into_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, w, out, rows, cols, out_stride, out_off);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void pad_cin_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int CinPad, int taps) {
+  pdl_enter();
   const size_t n = (size_t)Cout * CinPad * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int tap = i % taps;
@@ -63,12 +66,13 @@ __global__ void pad_cin_kernel(const float* __restrict__ w, float* __restrict__ 
 }
 int launch_pad_cin(const float* w, float* out, int Cout, int Cin, int CinPad, int taps, cudaStream_t st) {
   size_t n = (size_t)Cout * CinPad * taps;
-  pad_cin_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, CinPad, taps);
+  storm_launch(pad_cin_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, w, out, Cout, Cin, CinPad, taps);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 __global__ void concat_1x1_kernel(const float* __restrict__ w2, int C2, const float* __restrict__ wc, int Cc, int CP, float scale,
                                   float* __restrict__ out, int Cout) {
+  pdl_enter();
   const int K = C2 + CP;
   const size_t n = (size_t)Cout * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -81,17 +85,18 @@ __global__ void concat_1x1_kernel(const float* __restrict__ w2, int C2, const fl
 }
 int launch_concat_1x1(const float* w2, int C2, const float* wc, int Cc, int CP, float scale, float* out, int Cout, cudaStream_t st) {
   size_t n = (size_t)Cout * (C2 + CP);
-  concat_1x1_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(w2, C2, wc, Cc, CP, scale, out, Cout);
+  storm_launch(concat_1x1_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, w2, C2, wc, Cc, CP, scale, out, Cout);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n, float sb) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? sb * b[i] : 0.f);
 }
 int launch_add_vec(const float* a, const float* b, float* out, int n, float scale_b, cudaStream_t st) {
-  add_vec_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, out, n, scale_b);
+  storm_launch(add_vec_kernel, ceil_div(n, 256), 256, 0, st, a, b, out, n, scale_b);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -102,6 +107,7 @@ int launch_add_vec(const float* a, const float* b, float* out, int n, float scal
 __global__ void temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ Wf, const float* __restrict__ W1t,
                                 const float* __restrict__ b1, const float* __restrict__ W2t, const float* __restrict__ b2,
                                 float* __restrict__ act, int nf) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int E = 2 * nf, D = 4 * nf;
   float* e = sm;        // [E]
@@ -144,7 +150,7 @@ __global__ void temb_mlp_kernel(const float* __restrict__ t, const float* __rest
 int launch_temb_mlp(const float* t, const float* Wf, const float* W1t, const float* b1, const float* W2t, const float* b2,
                     float* act, int B, int nf, cudaStream_t st) {
   if (nf % 4 != 0) return fail(-1, "temb_mlp: nf must be a multiple of 4");
-  temb_mlp_kernel<<<B, 512, 6 * nf * sizeof(float), st>>>(t, Wf, W1t, b1, W2t, b2, act, nf);
+  storm_launch(temb_mlp_kernel, B, 512, 6 * nf * sizeof(float), st, t, Wf, W1t, b1, W2t, b2, act, nf);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -156,6 +162,7 @@ constexpr int DENSE_KS = 8;   // at most; the launcher picks the largest power o
 __global__ void __launch_bounds__(64 * DENSE_KS) dense_all_kernel(const float* __restrict__ act, const float* __restrict__ Wt,
                                                                   const float* __restrict__ bias, float* __restrict__ out, int B,
                                                                   int in_dim, int out_dim) {
+  pdl_enter();
   extern __shared__ float s_act[];   // [8][in_dim] then [DENSE_KS][64][8] partials
   float* s_part = s_act + 8 * in_dim;
   const int tx = threadIdx.x & 63, ks = threadIdx.x >> 6;
@@ -202,7 +209,7 @@ int launch_dense_all(const float* act, const float* Wt, const float* bias, float
   int ks = DENSE_KS;
   while (ks > 1 && in_dim % (8 * ks) != 0) ks >>= 1;
   const size_t smem = (size_t)(8 * in_dim + ks * 64 * 8) * sizeof(float);
-  dense_all_kernel<<<ceil_div(out_dim, 64), 64 * ks, smem, st>>>(act, Wt, bias, out, B, in_dim, out_dim);
+  storm_launch(dense_all_kernel, ceil_div(out_dim, 64), 64 * ks, smem, st, act, Wt, bias, out, B, in_dim, out_dim);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -218,6 +225,7 @@ int gn_num_chunks(int HW) {
 }
 
 __global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int nchunk) {
+  pdl_enter();
   extern __shared__ double smd[];   // [rows][C4][8]
   const int chunk = blockIdx.x, b = blockIdx.y;
   const int C4 = C >> 2;
@@ -263,7 +271,7 @@ int launch_gn_partial(const Act& a, cudaStream_t st) {
     STORM_CUDA_TRY(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  gn_partial_kernel<<<dim3(a.nchunk, a.B), threads, smem, st>>>(a.p, a.part, a.H * a.W, a.C, a.nchunk);
+  storm_launch(gn_partial_kernel, dim3(a.nchunk, a.B), threads, smem, st, a.p, a.part, a.H * a.W, a.C, a.nchunk);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -272,6 +280,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
                                                           const double* __restrict__ part1, int C1, int nchunk1,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ ss, float* __restrict__ ms, int HW, int G) {
+  pdl_enter();
   const int g = blockIdx.x, b = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / G;
@@ -327,7 +336,7 @@ int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const f
   const int C = a0.C + (a1 ? a1->C : 0);
   const int G = gn_groups(C);
   if (G < 1 || C % G != 0) return fail(-1, "gn_finalize: channels not divisible into groups");
-  gn_finalize_kernel<<<dim3(G, a0.B), 128, 0, st>>>(a0.part, a0.C, a0.nchunk, a1 ? a1->part : nullptr, a1 ? a1->C : 0,
+  storm_launch(gn_finalize_kernel, dim3(G, a0.B), 128, 0, st, a0.part, a0.C, a0.nchunk, a1 ? a1->part : nullptr, a1 ? a1->C : 0,
                                                      a1 ? a1->nchunk : 0, gamma, beta, ss, ms, a0.H * a0.W, G);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -350,6 +359,7 @@ __device__ __forceinline__ float4 act4(float4 v, const float* ss4) {
 
 __global__ void resample_kernel(const float* __restrict__ x, const float* __restrict__ ss, float* __restrict__ h_out,
                                 float* __restrict__ x_out, int B, int H, int W, int C, int mode) {
+  pdl_enter();
   const int C4 = C >> 2;
   const int OH = mode == 1 ? 2 * H : H / 2, OW = mode == 1 ? 2 * W : W / 2;
   const size_t total = (size_t)B * OH * OW * C4;
@@ -402,6 +412,7 @@ __global__ void resample_kernel(const float* __restrict__ x, const float* __rest
 template <int MODE>
 __global__ void __launch_bounds__(256) resample_tiled_kernel(const float* __restrict__ x, const float* __restrict__ ss,
                                                              float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  pdl_enter();
   constexpr int CG = MODE == 1 ? 32 : 16;            // channels per CTA
   constexpr int C4 = CG / 4;
   constexpr int TI = MODE == 1 ? 10 : 18;            // staged input tile edge
@@ -501,6 +512,7 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const float* __rest
 template <int R>
 __global__ void __launch_bounds__(256) resample_down_strip_kernel(const float* __restrict__ x, const float* __restrict__ ss,
                                                                   float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OH = H / 2, OW = W / 2;
   const int ncg = C / 128;
@@ -575,6 +587,7 @@ __global__ void __launch_bounds__(256) resample_down_strip_kernel(const float* _
 template <int R>
 __global__ void __launch_bounds__(256) resample_up_strip_kernel(const float* __restrict__ x, const float* __restrict__ ss,
                                                                 float* __restrict__ h_out, float* __restrict__ x_out, int H, int W, int C) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OW = 2 * W;
   const int ncg = C / 128;
@@ -653,20 +666,20 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
   if (mode == 1 && x.C % 128 == 0 && !no_strip) {
     constexpr int R = 8;
     dim3 grid(ceil_div(x.W, 8), ceil_div(x.H, R), x.B * (x.C / 128));
-    resample_up_strip_kernel<R><<<grid, 256, 0, st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    storm_launch(resample_up_strip_kernel<R>, grid, 256, 0, st, x.p, ss, h_out, x_out, x.H, x.W, x.C);
     STORM_LAUNCH_CHECK();
     return 0;
   }
   if (mode == 2 && x.C % 128 == 0 && !no_strip) {
     constexpr int R = 8;
     dim3 grid(ceil_div(x.W / 2, 8), ceil_div(x.H / 2, R), x.B * (x.C / 128));
-    resample_down_strip_kernel<R><<<grid, 256, 0, st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    storm_launch(resample_down_strip_kernel<R>, grid, 256, 0, st, x.p, ss, h_out, x_out, x.H, x.W, x.C);
     STORM_LAUNCH_CHECK();
     return 0;
   }
   if (mode == 1 && x.C % 32 == 0) {
     dim3 grid(ceil_div(x.H, 8) * ceil_div(x.W, 8), x.C / 32, x.B);
-    resample_tiled_kernel<1><<<grid, 256, 2 * 10 * 10 * 32 * sizeof(float), st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    storm_launch(resample_tiled_kernel<1>, grid, 256, 2 * 10 * 10 * 32 * sizeof(float), st, x.p, ss, h_out, x_out, x.H, x.W, x.C);
     STORM_LAUNCH_CHECK();
     return 0;
   }
@@ -677,14 +690,14 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
       attr = true;
     }
     dim3 grid(ceil_div(x.H / 2, 8) * ceil_div(x.W / 2, 8), x.C / 16, x.B);
-    resample_tiled_kernel<2><<<grid, 256, 2 * 18 * 18 * 20 * sizeof(float), st>>>(x.p, ss, h_out, x_out, x.H, x.W, x.C);
+    storm_launch(resample_tiled_kernel<2>, grid, 256, 2 * 18 * 18 * 20 * sizeof(float), st, x.p, ss, h_out, x_out, x.H, x.W, x.C);
     STORM_LAUNCH_CHECK();
     return 0;
   }
   const int OH = mode == 1 ? 2 * x.H : x.H / 2, OW = mode == 1 ? 2 * x.W : x.W / 2;
   size_t total = (size_t)x.B * OH * OW * (x.C / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  resample_kernel<<<blocks, 256, 0, st>>>(x.p, ss, h_out, x_out, x.B, x.H, x.W, x.C, mode);
+  storm_launch(resample_kernel, blocks, 256, 0, st, x.p, ss, h_out, x_out, x.B, x.H, x.W, x.C, mode);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -694,6 +707,7 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
 // group of 4 real channels issues its 16 tap loads together, the remaining channels are stored as zeros.
 __global__ void __launch_bounds__(256) fir_down_small_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W,
                                                              int C, int CO, int Creal) {
+  pdl_enter();
   const int OH = H / 2, OW = W / 2;
   const int n4 = (Creal + 3) / 4;                                  // float4 groups with data
   const size_t total = (size_t)B * OH * OW * n4;
@@ -736,7 +750,7 @@ int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C
   size_t total = (size_t)B * (H / 2) * (W / 2) * ((Creal + 3) / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   if (blocks == 0) blocks = 1;
-  fir_down_small_kernel<<<blocks, 256, 0, st>>>(x, out, B, H, W, C, CO, Creal);
+  storm_launch(fir_down_small_kernel, blocks, 256, 0, st, x, out, B, H, W, C, CO, Creal);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -745,6 +759,7 @@ int launch_fir_down_small(const float* x, float* out, int B, int H, int W, int C
 // input / pyramid / head
 // =====================================================================================================
 __global__ void unpack_input_kernel(UnpackSrc src, float* __restrict__ out, int B, int nc, int CP, int HW) {
+  pdl_enter();
   const size_t total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i / HW;
@@ -767,22 +782,24 @@ int launch_unpack_input(UnpackSrc src, float* out, int B, int nc, int CP, int HW
   if (nc < 1 || nc > 3 || CP < 8 || (CP & 3)) return fail(-1, "unpack_input: 1..3 complex channels, padded width a multiple of 4 and >= 8");
   size_t total = (size_t)B * HW;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  unpack_input_kernel<<<blocks, 256, 0, st>>>(src, out, B, nc, CP, HW);
+  storm_launch(unpack_input_kernel, blocks, 256, 0, st, src, out, B, nc, CP, HW);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 __global__ void fill_kernel(float* p, float v, int n) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 int launch_fill(float* p, float v, int n, cudaStream_t st) {
-  fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p, v, n);
+  storm_launch(fill_kernel, ceil_div(n, 256), 256, 0, st, p, v, n);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void combine_kernel(const float* __restrict__ h, const float* __restrict__ pyr, int pstride, const float* __restrict__ w,
                                const float* __restrict__ bias, float* __restrict__ out, size_t npix, int C, int Cin) {
+  pdl_enter();
   const int C4 = C >> 2;
   const size_t total = npix * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -804,7 +821,7 @@ int launch_combine(const float* h, const float* pyr, int pyr_stride, const float
                    int Cin, cudaStream_t st) {
   size_t total = (size_t)B * HW * (C / 4);
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  combine_kernel<<<blocks, 256, 0, st>>>(h, pyr, pyr_stride, w, bias, out, (size_t)B * HW, C, Cin);
+  storm_launch(combine_kernel, blocks, 256, 0, st, h, pyr, pyr_stride, w, bias, out, (size_t)B * HW, C, Cin);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -823,6 +840,7 @@ __global__ void __launch_bounds__(128) conv_out_small_kernel(const float* __rest
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              const float* __restrict__ prev, float* __restrict__ out,
                                                              int H, int W, int C, int Co) {
+  pdl_enter();
   __shared__ __align__(16) float sA[OKC][OHH][OHP];
   __shared__ __align__(16) float sW[9][OKC][8];
   const int tiles_x = (W + OTW - 1) / OTW;
@@ -923,13 +941,14 @@ int launch_conv_out_small(const Act& h, const float* ss, const float* w, const f
                           int Co, cudaStream_t st) {
   if (Co > 8) return fail(-1, "conv_out_small: Co > 8");
   dim3 grid(ceil_div(h.W, OTW) * ceil_div(h.H, OTH), h.B);
-  if (Co <= 4) conv_out_small_kernel<4><<<grid, 128, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
-  else conv_out_small_kernel<8><<<grid, 128, 0, st>>>(h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
+  if (Co <= 4) storm_launch(conv_out_small_kernel<4>, grid, 128, 0, st, h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
+  else storm_launch(conv_out_small_kernel<8>, grid, 128, 0, st, h.p, ss, w, bias, prev, out, h.H, h.W, h.C, Co);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void pack_convout_gemm_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Cin, int Npad) {
+  pdl_enter();
   const int total = Cin * Npad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i % Npad, c = i / Npad;
@@ -942,13 +961,14 @@ __global__ void pack_convout_gemm_kernel(const float* __restrict__ w, float* __r
   }
 }
 int launch_pack_convout_gemm(const float* w_oihw, float* out_io, int Co, int Cin, int Npad, cudaStream_t st) {
-  pack_convout_gemm_kernel<<<ceil_div(Cin * Npad, 256), 256, 0, st>>>(w_oihw, out_io, Co, Cin, Npad);
+  storm_launch(pack_convout_gemm_kernel, ceil_div(Cin * Npad, 256), 256, 0, st, w_oihw, out_io, Co, Cin, Npad);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void tap_gather_kernel(const float* __restrict__ Z, int Npad, const float* __restrict__ bias, const float* __restrict__ prev,
                                   float* __restrict__ out, int B, int H, int W, int Co) {
+  pdl_enter();
   const size_t total = (size_t)B * H * W * Co;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int j = i % Co;
@@ -994,13 +1014,14 @@ int launch_tap_gather(const float* Z, int Npad, const float* bias, const float* 
                       cudaStream_t st) {
   size_t total = (size_t)B * H * W * Co;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  tap_gather_kernel<<<blocks, 256, 0, st>>>(Z, Npad, bias, prev, out, B, H, W, Co);
+  storm_launch(tap_gather_kernel, blocks, 256, 0, st, Z, Npad, bias, prev, out, B, H, W, Co);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void head_kernel(const float* __restrict__ pyr, const float* __restrict__ t, const float* __restrict__ w,
                             const float* __restrict__ bias, float2* __restrict__ out, int B, int HW, int Ci) {
+  pdl_enter();
   const size_t total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i / HW;
@@ -1019,7 +1040,7 @@ int launch_head(const float* pyr, const float* t, const float* w, const float* b
                 cudaStream_t st) {
   size_t total = (size_t)B * HW;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  head_kernel<<<blocks, 256, 0, st>>>(pyr, t, w, bias, reinterpret_cast<float2*>(out_c), B, HW, Ci);
+  storm_launch(head_kernel, blocks, 256, 0, st, pyr, t, w, bias, reinterpret_cast<float2*>(out_c), B, HW, Ci);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1033,6 +1054,7 @@ constexpr int AQ = 16, AK = 32;
 __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                              const float* __restrict__ v, float* __restrict__ o, int N, int C,
                                                              float scale) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int CP = C + 4;
   float* Qs = sm;                    // [AQ][CP]
@@ -1132,7 +1154,7 @@ int launch_attention_simt(const float* q, const float* k, const float* v, float*
     STORM_CUDA_TRY(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  attention_simt_kernel<<<dim3(ceil_div(N, AQ), B), 256, smem, st>>>(q, k, v, o, N, C, 1.0f / sqrtf((float)C));
+  storm_launch(attention_simt_kernel, dim3(ceil_div(N, AQ), B), 256, smem, st, q, k, v, o, N, C, 1.0f / sqrtf((float)C));
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1171,6 +1193,7 @@ __global__ void sampler_update_kernel(const float2* __restrict__ x, const float2
                                       float2* __restrict__ x_mean, float2* __restrict__ x_new, UpdateCoef coef,
                                       const UpdateCoef* __restrict__ coef_dev, const float2* __restrict__ noise, uint64_t seed,
                                       const uint64_t* __restrict__ seed_dev, const uint64_t* __restrict__ utt_ids, uint32_t draw, int64_t n) {
+  pdl_enter();
   const int b = blockIdx.y;
   if (coef_dev) coef = *coef_dev;
   if (seed_dev) seed = *seed_dev;             // captured trajectories read the seed from device memory
@@ -1193,7 +1216,7 @@ int launch_sampler_update(const float* x, const float* y, const float* d, float*
                           const UpdateCoef* coef_dev, const float* noise, uint64_t seed, const uint64_t* seed_dev,
                           const uint64_t* utt_ids_dev, uint32_t draw, int B, int64_t n, cudaStream_t st) {
   unsigned bx = (unsigned)((n + 255) / 256 > 148 * 4 ? 148 * 4 : (n + 255) / 256);
-  sampler_update_kernel<<<dim3(bx, B), 256, 0, st>>>(
+  storm_launch(sampler_update_kernel, dim3(bx, B), 256, 0, st, 
       reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), reinterpret_cast<const float2*>(d),
       reinterpret_cast<float2*>(x_mean), reinterpret_cast<float2*>(x_new), coef, coef_dev,
       reinterpret_cast<const float2*>(noise), seed, seed_dev, utt_ids_dev, draw, n);
@@ -1202,12 +1225,13 @@ int launch_sampler_update(const float* x, const float* y, const float* d, float*
 }
 
 __global__ void philox_fill_kernel(uint64_t seed, uint64_t utt, uint32_t draw, int64_t n, float2* out) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = philox_cnormal(seed, utt, draw, (uint32_t)i);
 }
 int launch_philox_fill(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n, float* out, cudaStream_t st) {
   unsigned bx = (unsigned)((n + 255) / 256 > 148 * 4 ? 148 * 4 : (n + 255) / 256);
-  philox_fill_kernel<<<bx, 256, 0, st>>>(seed, utt_id, draw, n, reinterpret_cast<float2*>(out));
+  storm_launch(philox_fill_kernel, bx, 256, 0, st, seed, utt_id, draw, n, reinterpret_cast<float2*>(out));
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1216,6 +1240,7 @@ int launch_philox_fill(uint64_t seed, uint64_t utt_id, uint32_t draw, int64_t n,
 __global__ void sqnorm_partial_kernel(const float2* __restrict__ d, const float2* __restrict__ noise, uint64_t seed,
                                       const uint64_t* __restrict__ seed_dev, const uint64_t* __restrict__ utt_ids, uint32_t draw,
                                       int64_t n, double* scratch) {
+  pdl_enter();
   const int b = blockIdx.y;
   if (seed_dev) seed = *seed_dev;
   const uint64_t utt = utt_ids ? utt_ids[b] : (uint64_t)b;
@@ -1238,6 +1263,7 @@ __global__ void sqnorm_partial_kernel(const float2* __restrict__ d, const float2
   }
 }
 __global__ void langevin_coef_kernel(const double* scratch, int B, int nblk, float snr, UpdateCoef* out) {
+  pdl_enter();
   if (threadIdx.x != 0) return;
   float gn = 0.f, zn = 0.f;   // mean over the batch of per-sample L2 norms (correctors.py:53-54)
   for (int b = 0; b < B; ++b) {
@@ -1254,16 +1280,17 @@ __global__ void langevin_coef_kernel(const double* scratch, int B, int nblk, flo
 int launch_langevin_coef(const float* d, const float* noise, uint64_t seed, const uint64_t* seed_dev, const uint64_t* utt_ids_dev,
                          uint32_t draw, float snr, int B, int64_t n, double* scratch, UpdateCoef* coef_out, cudaStream_t st) {
   const int nblk = 64;
-  sqnorm_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(reinterpret_cast<const float2*>(d), reinterpret_cast<const float2*>(noise),
+  storm_launch(sqnorm_partial_kernel, dim3(nblk, B), 256, 0, st, reinterpret_cast<const float2*>(d), reinterpret_cast<const float2*>(noise),
                                                        seed, seed_dev, utt_ids_dev, draw, n, scratch);
   STORM_LAUNCH_CHECK();
-  langevin_coef_kernel<<<1, 32, 0, st>>>(scratch, B, nblk, snr, coef_out);
+  storm_launch(langevin_coef_kernel, 1, 32, 0, st, scratch, B, nblk, snr, coef_out);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void ode_drift_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ d,
                                  float2* __restrict__ out, float theta, float half_g2, int64_t n) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float2 xv = x[i], yv = y[i], dv = d[i];
     out[i] = make_float2(fmaf(half_g2, dv.x, theta * (yv.x - xv.x)), fmaf(half_g2, dv.y, theta * (yv.y - xv.y)));
@@ -1272,7 +1299,7 @@ __global__ void ode_drift_kernel(const float2* __restrict__ x, const float2* __r
 int launch_ode_drift(const float* x, const float* y, const float* d, float* out, float theta, float half_g2, int64_t n_total,
                      cudaStream_t st) {
   unsigned bx = (unsigned)((n_total + 255) / 256 > 148 * 8 ? 148 * 8 : (n_total + 255) / 256);
-  ode_drift_kernel<<<bx, 256, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y),
+  storm_launch(ode_drift_kernel, bx, 256, 0, st, reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y),
                                        reinterpret_cast<const float2*>(d), reinterpret_cast<float2*>(out), theta, half_g2, n_total);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -1283,6 +1310,7 @@ int launch_ode_drift(const float* x, const float* y, const float* d, float* out,
 // =====================================================================================================
 // `lens` (optional, device): true length of every utterance inside its L-sample row (ragged batches of one frame bucket)
 __global__ void wave_norm_kernel(const float* __restrict__ wav, int L, const int* __restrict__ lens, float* __restrict__ norm) {
+  pdl_enter();
   const int b = blockIdx.x;
   const int Lb = lens ? min(lens[b], L) : L;
   float m = 0.f;
@@ -1298,7 +1326,7 @@ __global__ void wave_norm_kernel(const float* __restrict__ wav, int L, const int
   }
 }
 int launch_wave_norm(const float* wav, int B, int L, const int* lens, float* norm, cudaStream_t st) {
-  wave_norm_kernel<<<B, 1024, 0, st>>>(wav, L, lens, norm);
+  storm_launch(wave_norm_kernel, B, 1024, 0, st, wav, L, lens, norm);
   STORM_LAUNCH_CHECK();
   return 0;
 }
@@ -1315,6 +1343,7 @@ __device__ __forceinline__ float window_at(int n, int n_fft, int sqrt_window) {
 __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav, const float* __restrict__ norm, int Lrow,
                                                    const int* __restrict__ lens, float2* __restrict__ spec, int T_pad, int n_fft,
                                                    int hop, int sqrt_window, float factor, float expo) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* frame = sm;
   float2* tw = reinterpret_cast<float2*>(sm + n_fft + (n_fft & 1));
@@ -1372,7 +1401,7 @@ int launch_stft(const float* wav, const float* norm, int B, int L, const int* le
   const int n_frames = 1 + L / hop;
   if (T_pad < n_frames) return fail(-1, "stft: T_pad smaller than the frame count");
   size_t smem = (size_t)(n_fft + (n_fft & 1)) * sizeof(float) + (size_t)n_fft * sizeof(float2);
-  stft_kernel<<<dim3(T_pad, B), 256, smem, st>>>(wav, norm, L, lens, reinterpret_cast<float2*>(spec), T_pad, n_fft, hop,
+  storm_launch(stft_kernel, dim3(T_pad, B), 256, smem, st, wav, norm, L, lens, reinterpret_cast<float2*>(spec), T_pad, n_fft, hop,
                                                 sqrt_window, factor, expo);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -1381,6 +1410,7 @@ int launch_stft(const float* wav, const float* norm, int B, int L, const int* le
 // frames_buf[b][f][n] = window[n] * irfft(spec_back(spec[b][:, f]))[n]
 __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restrict__ spec, int T_pad, float* __restrict__ frames_buf,
                                                            int n_fft, int sqrt_window, float factor, float expo) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int nb = n_fft / 2 + 1;
   float2* X = reinterpret_cast<float2*>(sm);          // [nb]
@@ -1428,6 +1458,7 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restr
 }
 __global__ void istft_ola_kernel(const float* __restrict__ frames_buf, const float* __restrict__ norm, int T_pad,
                                  float* __restrict__ wav, int L, const int* __restrict__ lens, int n_fft, int hop, int sqrt_window) {
+  pdl_enter();
   const int b = blockIdx.y;
   const int Lb = lens ? min(lens[b], L) : L;           // torch.istft(length = this utterance's length); the row tail is zeroed
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < L; m += gridDim.x * blockDim.x) {
@@ -1454,10 +1485,10 @@ int launch_istft(const float* spec, const float* norm, int B, int T_pad, float* 
   if (n_fft & 1) return fail(-1, "istft: n_fft must be even");
   const int nb = n_fft / 2 + 1;
   size_t smem = (size_t)(nb + n_fft) * sizeof(float2);
-  istft_frames_kernel<<<dim3(T_pad, B), 256, smem, st>>>(reinterpret_cast<const float2*>(spec), T_pad, frames_buf, n_fft, sqrt_window,
+  storm_launch(istft_frames_kernel, dim3(T_pad, B), 256, smem, st, reinterpret_cast<const float2*>(spec), T_pad, frames_buf, n_fft, sqrt_window,
                                                         factor, expo);
   STORM_LAUNCH_CHECK();
-  istft_ola_kernel<<<dim3(ceil_div(L, 256) > 512 ? 512 : ceil_div(L, 256), B), 256, 0, st>>>(frames_buf, norm, T_pad, wav, L, lens, n_fft,
+  storm_launch(istft_ola_kernel, dim3(ceil_div(L, 256) > 512 ? 512 : ceil_div(L, 256), B), 256, 0, st, frames_buf, norm, T_pad, wav, L, lens, n_fft,
                                                                                        hop, sqrt_window);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -1482,6 +1513,7 @@ __device__ __forceinline__ double block_sum_1024(double v, double* sh) {
 }  // namespace
 __global__ void __launch_bounds__(1024) si_sdr_kernel(const float* __restrict__ s, const float* __restrict__ sh, int L,
                                                       const int* __restrict__ lens, double eps, float* __restrict__ out) {
+  pdl_enter();
   __shared__ double red[32];
   const int b = blockIdx.x;
   const int Lb = lens ? min(lens[b], L) : L;
@@ -1507,12 +1539,13 @@ __global__ void __launch_bounds__(1024) si_sdr_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) out[b] = (float)(10.0 * log10(eps + num / (eps + den)));
 }
 int launch_si_sdr(const float* s, const float* s_hat, int B, int L, const int* lens, double eps, float* out, cudaStream_t st) {
-  si_sdr_kernel<<<B, 1024, 0, st>>>(s, s_hat, L, lens, eps, out);
+  storm_launch(si_sdr_kernel, B, 1024, 0, st, s, s_hat, L, lens, eps, out);
   STORM_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C, size_t total) {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = i % C;
     const size_t r = i / C;
@@ -1524,7 +1557,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t st) {
   size_t total = (size_t)B * HW * C;
   unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  nhwc_to_nchw_kernel<<<blocks, 256, 0, st>>>(in, out, HW, C, total);
+  storm_launch(nhwc_to_nchw_kernel, blocks, 256, 0, st, in, out, HW, C, total);
   STORM_LAUNCH_CHECK();
   return 0;
 }

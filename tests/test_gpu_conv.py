@@ -73,6 +73,42 @@ def test_fused_conv(engine, case):
     assert err < (2e-5 if engine == 1 else 8e-5)
 
 
+@pytest.mark.parametrize("rh", [8, 16])
+@pytest.mark.parametrize("shape", [
+    # B, H, W, C0, C1, Cout, skip(C2), res: layers that run on CTA pairs (129..256 output channels)
+    (1, 32, 32, 256, 128, 256, 384, None),
+    (2, 40, 24, 128, 0, 192, 0, "full"),       # ragged tiles in both directions, padded channel block
+    (2, 32, 16, 256, 0, 256, 0, "up"),         # half-resolution residual in the epilogue
+    (3, 32, 32, 256, 0, 256, 0, None),
+])
+def test_pair_kernel_tile_heights(monkeypatch, rh, shape):
+    """Both tile heights of the CTA-pair schedule (256-pixel tiles; 128-pixel tiles for launches that would leave pairs idle)
+    against the float64 reference, including the GroupNorm partial sums' consumer-visible result (the output itself)."""
+    from storm_b200 import _native
+    monkeypatch.setenv("STORM_B200_TCR_RH", str(rh))
+    B, H, W, C0, C1, Cout, C2, res_kind = shape
+    g = torch.Generator(device="cuda").manual_seed(11 + rh)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)   # noqa: E731
+    x0 = rn(B, H, W, C0)
+    x1 = rn(B, H, W, C1) if C1 else None
+    Cin = C0 + C1
+    w = rn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5
+    ss = torch.stack([1.0 + 0.3 * rn(B, Cin), 0.2 * rn(B, Cin)], dim=-1).contiguous()
+    x2 = rn(B, H, W, C2) if C2 else None
+    w2 = rn(Cout, C2, 1, 1) / C2 ** 0.5 if C2 else None
+    bias = 0.1 * rn(Cout)
+    res = rn(B, H, W, Cout) if res_kind == "full" else None
+    res_up = rn(B, H // 2, W // 2, Cout) if res_kind == "up" else None
+    ref = _ref(x0, w, x1=x1, ss=ss, silu=True, x2=x2, w2=w2, bias=bias, res=res, out_scale=1.0)
+    if res_up is not None:
+        ref = ref + _fir_ref(res_up, 1)
+    ref = ref * 0.70710678
+    out = _native.debug_conv(0, x0, w, x1=x1, ss=ss, silu=True, x2=x2, w2=w2, bias=bias, res=res, res_up=res_up, out_scale=0.70710678)
+    err = _rel(out, ref)
+    print(f"pair kernel rh={rh} shape={shape} rel-L2={err:.3e}")
+    assert torch.isfinite(out).all() and err < 8e-5
+
+
 @pytest.mark.parametrize("engine", [1, 0])
 @pytest.mark.parametrize("B,N,C", [(2, 1024, 256), (1, 2048, 256), (3, 128, 192), (2, 256, 64)])
 def test_attention_core(engine, B, N, C):
