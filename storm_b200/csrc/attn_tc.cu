@@ -9,8 +9,8 @@
 //   pass 1: S~ = Qhi Khi^T only (1/3 of the MMAs) -> per-row shift m (softmax is shift invariant, the bf16 error of
 //           m is irrelevant); pass 2: exact S, P = exp((S - m)/sqrt(C)) written as bf16 hi/lo K-major tiles to
 //           shared memory, O += P V, l += row sums; finally O / l.
-// Warp roles: 0-3 softmax + epilogue (TMEM lane = query row), 4-7 operand producers (fp32 -> bf16 hi/lo,
-// no-swizzle K-major core-matrix layout), 8 TMEM alloc + single-thread MMA issue.
+// Warp roles: 0-3 softmax + epilogue (TMEM lane = query row), 4-19 operand producers in four groups that fill the stage
+// rings round-robin (fp32 -> bf16 hi/lo, no-swizzle K-major core-matrix layout), 20 TMEM alloc + single-thread MMA issue.
 #include <cuda_bf16.h>
 
 #include "kernels.cuh"
@@ -19,9 +19,14 @@ namespace storm {
 
 namespace {
 
-constexpr int A_THREADS = 288;
+constexpr int A_PGROUPS = 4;                          // producer groups of 4 warps (one query / key row per thread)
+constexpr int A_WARP_MMA = 4 + 4 * A_PGROUPS;         // warps 0-3 softmax, 4 .. 4 + 4 G - 1 producers, then the MMA warp
+constexpr int A_THREADS = (A_WARP_MMA + 1) * 32;      // 672
 constexpr int TQ = 128, TK = 128;         // queries per CTA, keys per tile
-constexpr int SQ = 4, SV = 3;             // ring depths
+constexpr int SQ = 4, SV = 4;             // ring depths
+// every ring slot belongs to ONE producer group (slot = item % depth, group = item % A_PGROUPS): groups are not synchronised
+// with each other, and a group that ran a whole ring revolution ahead of a slot's other users would alias the barrier parity
+static_assert(SQ % A_PGROUPS == 0 && SV % A_PGROUPS == 0, "ring depths must be multiples of the producer group count");
 constexpr int QK_STAGE = 16 * 1024;       // Q chunk hi/lo (2 x 4 KB) + K chunk hi/lo (2 x 4 KB)
 constexpr int V_STAGE_MAX = 16 * 1024;    // V chunk: C rows x 16 keys x hi/lo
 constexpr int P_BYTES = 64 * 1024;        // P tile 128 x 128, hi + lo
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __re
     mbar_init(s_full, 1); mbar_init(s_empty, 128); mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == A_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -220,33 +225,38 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __re
                                                                      __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < A_WARP_MMA) {
     // =================================== producers ======================================================
-    const int pt = tid - 128;                    // 0..127
-    int sq = 0, sv = 0;
-    uint32_t pq = 0, pvp = 0;
+    // A_PGROUPS groups of 128 threads share the two rings round-robin (item n of a ring belongs to group n % A_PGROUPS): one
+    // group alone pays a full global-memory round trip per stage (loads -> convert -> store -> arrive, 320 stages per CTA),
+    // which is what the kernel's time was; every group walks the whole schedule in the MMA's order and skips foreign items.
+    const int grp = (warp - 4) >> 2;
+    const int pt = (tid - 128) & 127;            // 0..127: row inside the tile
+    uint32_t nq = 0, nv = 0;                     // ring item counters (all groups count alike)
     const float* qrow = q + ((size_t)b * N + q0 + pt) * C;
     for (int pass = 0; pass < 2; ++pass) {
       for (int t = 0; t < NT; ++t) {
         const float* krow = k + ((size_t)b * N + t * TK + pt) * C;
-        for (int c = 0; c < NC; ++c) {
-          mbar_wait(qk_empty(sq), pq ^ 1);
+        for (int c = 0; c < NC; ++c, ++nq) {
+          if ((int)(nq % A_PGROUPS) != grp) continue;
+          const int sq = (int)(nq % SQ);
+          mbar_wait(qk_empty(sq), ((nq / SQ) & 1u) ^ 1u);
           const uint32_t st = qk_base + sq * QK_STAGE;
           stage_row16(qrow + c * 16, st, 4096, TQ, pt);                 // Q: hi at +0, lo at +4096
           stage_row16(krow + c * 16, st + 8192, 4096, TK, pt);          // K: hi at +8192, lo at +12288
           fence_async_shared();
           mbar_arrive(qk_full(sq));
-          if (++sq == SQ) { sq = 0; pq ^= 1; }
         }
         if (pass == 1) {
-          for (int ks = 0; ks < TK / 16; ++ks) {
-            mbar_wait(v_empty(sv), pvp ^ 1);
+          for (int ks = 0; ks < TK / 16; ++ks, ++nv) {
+            if ((int)(nv % A_PGROUPS) != grp) continue;
+            const int sv = (int)(nv % SV);
+            mbar_wait(v_empty(sv), ((nv / SV) & 1u) ^ 1u);
             const uint32_t st = v_base + sv * V_STAGE_MAX;
             for (int ch = pt; ch < C; ch += 128)
               stage_row16(vT + ((size_t)b * C + ch) * N + t * TK + ks * 16, st, (uint32_t)v_plane, C, ch);
             fence_async_shared();
             mbar_arrive(v_full(sv));
-            if (++sv == SV) { sv = 0; pvp ^= 1; }
           }
         }
       }
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_tc_kernel(const float* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == A_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 }  // namespace
