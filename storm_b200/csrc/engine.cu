@@ -2,6 +2,7 @@
 // sgmse/backbones/ncsnpp.py:110-273), weight arena + repacking, workspace pool, NCSN++ forward
 // (ncsnpp.py:281-450), PC sampler loop (sgmse/sampling/__init__.py:54-66) and the C ABI of
 // include/storm_b200.h.
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,6 +33,15 @@ int fail(int code, const std::string& msg) {
 // trajectory replayed as one CUDA graph the launch gaps are already hidden, and dependents that become resident early only
 // take issue slots from the running kernel.  Off by default; STORM_B200_PDL = 1 | 2 | 3 switches it on for the small kernels /
 // the conv kernels / both (profiles/r2_bench_history.md).
+// NVTX ranges on the host side of the path (enhance > stft / sampler trajectory > network evaluation / istft): header-only
+// NVTX 3, a pointer check per call when no tool is attached.  A replayed CUDA graph shows as one "trajectory (graph replay)" range.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 int pdl_mode() {
   static const int m = [] { const char* e = getenv("STORM_B200_PDL"); return e ? atoi(e) : 0; }();
   return m;
@@ -728,6 +738,7 @@ static int ensure_temb_cache(StormHandle* h, int B) {
 // time-embedding biases are reused across calls with the same value
 static int net_forward(StormHandle* h, UnpackSrc src, const float* t, float* out, int B, int F, int T, cudaStream_t st,
                        const float* t_uniform = nullptr) {
+  NvtxRange nvtx_range("storm_b200: NCSN++ evaluation");
   if (!h->weights_loaded) return fail(STORM_E_STATE, "weights not loaded: call storm_load_weights first");
   const StormNetConfig& c = h->cfg;
   const int nres = c.num_levels;
@@ -964,6 +975,7 @@ static int check_sampler(const StormSamplerConfig* sc) {
 static int pc_sample_body(StormHandle* h, const float* Y, const float* cond0, const float* cond1, float* X, int B, int F, int T,
                           const StormSamplerConfig& sc, uint64_t seed, const uint64_t* seed_dev, const uint64_t* ids_dev,
                           const float* noise, int* nfe_out, cudaStream_t st) {
+  NvtxRange nvtx_range("storm_b200: sampler trajectory");
   const int64_t n = (int64_t)F * T;
   const int ncplx = h->in_ch() / 2;
   if (ncplx == 3 && !cond1) return fail(STORM_E_INVALID, "6-channel score net needs two conditioning spectrograms");
@@ -1184,7 +1196,10 @@ static int pc_sample(StormHandle* h, const float* Y, const float* cond0, const f
   STORM_CUDA_TRY(cudaMemcpyAsync(g->Y, Y, spec_bytes, cudaMemcpyDeviceToDevice, st));
   if (cond0) STORM_CUDA_TRY(cudaMemcpyAsync(g->c0, cond0, spec_bytes, cudaMemcpyDeviceToDevice, st));
   if (cond1) STORM_CUDA_TRY(cudaMemcpyAsync(g->c1, cond1, spec_bytes, cudaMemcpyDeviceToDevice, st));
-  STORM_CUDA_TRY(cudaGraphLaunch(g->exec, st));
+  {
+    NvtxRange r("storm_b200: trajectory (graph replay)");
+    STORM_CUDA_TRY(cudaGraphLaunch(g->exec, st));
+  }
   STORM_CUDA_TRY(cudaMemcpyAsync(X, g->X, spec_bytes, cudaMemcpyDeviceToDevice, st));
   h->temb_cache_valid = false;
   h->launches += g->launches_per_replay;
@@ -1550,11 +1565,18 @@ int storm_enhance_ragged(StormHandle* h, const float* wav_in, float* wav_out, in
   STORM_TRY(lease.get((size_t)B * 4, &p)); float* norm = (float*)p;
   STORM_TRY(lease.get((size_t)B * F * T_pad * 8, &p)); float* Y = (float*)p;
   STORM_TRY(lease.get((size_t)B * F * T_pad * 8, &p)); float* X = (float*)p;
-  LAUNCH(h, launch_wave_norm(wav_in, B, L, lengths, norm, st));
-  LAUNCH(h, launch_stft(wav_in, norm, B, L, lengths, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
-                        sp->spec_abs_exponent, st));
+  NvtxRange nvtx_range("storm_b200: enhance");
+  {
+    NvtxRange r("storm_b200: normalise + STFT");
+    LAUNCH(h, launch_wave_norm(wav_in, B, L, lengths, norm, st));
+    LAUNCH(h, launch_stft(wav_in, norm, B, L, lengths, Y, T_pad, sp->n_fft, sp->hop_length, sp->sqrt_window, sp->spec_factor,
+                          sp->spec_abs_exponent, st));
+  }
   STORM_TRY(pc_sample(h, Y, nullptr, nullptr, X, B, F, T_pad, *sc, seed, utt_ids, nullptr, nfe_out, st));
-  STORM_TRY(storm_istft_ragged(h, X, norm, B, T_pad, wav_out, L, lengths, sp, stream));
+  {
+    NvtxRange r("storm_b200: iSTFT");
+    STORM_TRY(storm_istft_ragged(h, X, norm, B, T_pad, wav_out, L, lengths, sp, stream));
+  }
   return 0;
 }
 int storm_enhance(StormHandle* h, const float* wav_in, float* wav_out, int32_t B, int32_t L, const StormSamplerConfig* sc,
