@@ -1870,6 +1870,7 @@ bool choose_cfg_p(const ConvParams& p, TcpCfg& c) {
   // (128 tiles of 256 pixels x 256 channels) run full-rate N=256 MMAs on 128 SMs instead of 512 smem-bound N=128 ones
   static int min_fill = -1;
   if (min_fill < 0) { const char* e = getenv("STORM_B200_TC_MINFILL"); min_fill = e ? atoi(e) : 120; }
+  // (two co-resident CTAs for the pure 1x1 GEMM launches were measured too: output-branch GEMM 229 -> 254 us, not kept)
   const bool big_first = g_tc_force_per_sm == 3 || p.nseg == 2;
   const Cand* cands = nblk == 1 ? (big_first ? cands1m : cands1b) : (big_first ? cands2m : cands2b);
   const int ncand = nblk == 1 ? 4 : 5;

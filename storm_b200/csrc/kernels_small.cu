@@ -279,7 +279,7 @@ int launch_gn_partial(const Act& a, cudaStream_t st) {
 __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restrict__ part0, int C0, int nchunk0,
                                                           const double* __restrict__ part1, int C1, int nchunk1,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ ss, float* __restrict__ ms, int HW, int G) {
+                                                          float* __restrict__ ss, float* __restrict__ ms, double inv_n, int G) {
   pdl_enter();
   const int g = blockIdx.x, b = blockIdx.y;
   const int C = C0 + C1;
@@ -313,13 +313,20 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
   if (threadIdx.x == 0) {
     double S = 0, Q = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { S += rs[i]; Q += rq[i]; }
-    double n = (double)cpg * HW;
-    double mean = S / n;
-    double var = Q / n - mean * mean;
+    // fp64 division and square root are software sequences of ~100 instructions each on this part (one thread, on the critical
+    // path of a 4-us kernel that runs 45 times per evaluation): multiply by the host-computed 1/n, and refine a single-precision
+    // rsqrt with two Newton steps in fp64 (relative error ~1e-7 -> 1e-14 -> below 1 ulp)
+    const double mean = S * inv_n;
+    const double msq = Q * inv_n;
+    double var = msq - mean * mean;
     if (var < 0) var = 0;
+    const double ve = var + 1e-6;
+    double r = (double)rsqrtf((float)ve);
+    r = r * (1.5 - 0.5 * ve * r * r);
+    r = r * (1.5 - 0.5 * ve * r * r);
     rs[0] = mean;
-    rq[0] = 1.0 / sqrt(var + 1e-6);
-    if (ms) ms[(size_t)b * G + g] = (float)(Q / n);      // mean square of the RAW group: magnitude of the un-normalised tensor
+    rq[0] = r;
+    if (ms) ms[(size_t)b * G + g] = (float)msq;          // mean square of the RAW group: magnitude of the un-normalised tensor
   }
   __syncthreads();
   const double mean = rs[0], rstd = rq[0];
@@ -337,7 +344,7 @@ int launch_gn_finalize(const Act& a0, const Act* a1, const float* gamma, const f
   const int G = gn_groups(C);
   if (G < 1 || C % G != 0) return fail(-1, "gn_finalize: channels not divisible into groups");
   storm_launch(gn_finalize_kernel, dim3(G, a0.B), 128, 0, st, a0.part, a0.C, a0.nchunk, a1 ? a1->part : nullptr, a1 ? a1->C : 0,
-                                                     a1 ? a1->nchunk : 0, gamma, beta, ss, ms, a0.H * a0.W, G);
+                                                     a1 ? a1->nchunk : 0, gamma, beta, ss, ms, 1.0 / ((double)(C / G) * a0.H * a0.W), G);
   STORM_LAUNCH_CHECK();
   return 0;
 }
