@@ -321,11 +321,7 @@ bool attention_tc_eligible(int N, int C) { return N >= TK && N % TK == 0 && C % 
 int launch_attention_tc(const float* q, const float* k, const float* vT, float* o, int B, int N, int C, cudaStream_t st) {
   if (!attention_tc_eligible(N, C)) return fail(-1, "attention_tc: shape not eligible");
   const int smem = SQ * QK_STAGE + SV * V_STAGE_MAX + P_BYTES + 8 * (2 * SQ + 2 * SV + 5) + 16;
-  static bool attr = false;
-  if (!attr) {
-    STORM_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  STORM_SET_SMEM_ONCE((attn_tc_kernel), 200 * 1024);
   storm_launch_m(2, attn_tc_kernel, dim3(N / TQ, B), A_THREADS, smem, st, q, k, vT, o, N, C, 1.0f / sqrtf((float)C));
   STORM_LAUNCH_CHECK();
   return 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <utility>
 
@@ -26,6 +27,21 @@ int fail(int code, const std::string& msg);
     if (_e != cudaSuccess)                                                                          \
       return ::storm::fail(-2, std::string("kernel launch failed: ") + cudaGetErrorString(_e) +     \
                                    " at " + __FILE__ + ":" + std::to_string(__LINE__));             \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remembered per call site and device, so a second handle on another
+// GPU of the same process gets it too
+#define STORM_SET_SMEM_ONCE(kernel, bytes)                                                           \
+  do {                                                                                               \
+    static std::mutex mu_;                                                                           \
+    static bool done_[64] = {};                                                                      \
+    int dev_ = 0;                                                                                    \
+    STORM_CUDA_TRY(cudaGetDevice(&dev_));                                                            \
+    std::lock_guard<std::mutex> lk_(mu_);                                                            \
+    if (dev_ < 0 || dev_ >= 64 || !done_[dev_]) {                                                    \
+      STORM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes))); \
+      if (dev_ >= 0 && dev_ < 64) done_[dev_] = true;                                                \
+    }                                                                                                \
   } while (0)
 
 #define STORM_TRY(expr)          \

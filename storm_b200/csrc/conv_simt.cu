@@ -177,11 +177,7 @@ int launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     if (p.seg[i].taps != 9 && p.seg[i].taps != 1) return fail(-1, "conv_simt: taps must be 9 or 1");
     if (!p.seg[i].w) return fail(-3, "conv_simt: missing packed weights");
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    STORM_CUDA_TRY(cudaFuncSetAttribute(conv_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  STORM_SET_SMEM_ONCE((conv_simt_kernel), SMEM_BYTES);
   dim3 grid(ceil_div(p.W, TW) * ceil_div(p.H, TH), ceil_div(p.Cout, BN), p.B);
   storm_launch(conv_simt_kernel, grid, NT, SMEM_BYTES, st, p);
   STORM_LAUNCH_CHECK();

@@ -266,11 +266,7 @@ int launch_gn_partial(const Act& a, cudaStream_t st) {
   int threads = 256;
   int rows = threads / C4;
   size_t smem = (size_t)rows * C4 * 8 * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    STORM_CUDA_TRY(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+  STORM_SET_SMEM_ONCE((gn_partial_kernel), 64 * 1024);
   storm_launch(gn_partial_kernel, dim3(a.nchunk, a.B), threads, smem, st, a.p, a.part, a.H * a.W, a.C, a.nchunk);
   STORM_LAUNCH_CHECK();
   return 0;
@@ -691,11 +687,7 @@ int launch_resample(const Act& x, const float* ss, float* h_out, float* x_out, i
     return 0;
   }
   if (mode == 2 && x.C % 16 == 0) {
-    static bool attr = false;
-    if (!attr) {
-      STORM_CUDA_TRY(cudaFuncSetAttribute(resample_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    STORM_SET_SMEM_ONCE((resample_tiled_kernel<2>), 64 * 1024);
     dim3 grid(ceil_div(x.H / 2, 8) * ceil_div(x.W / 2, 8), x.C / 16, x.B);
     storm_launch(resample_tiled_kernel<2>, grid, 256, 2 * 18 * 18 * 20 * sizeof(float), st, x.p, ss, h_out, x_out, x.H, x.W, x.C);
     STORM_LAUNCH_CHECK();
@@ -1156,11 +1148,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
 int launch_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int N, int C, cudaStream_t st) {
   if (C > 256 || C % 4 != 0) return fail(-1, "attention_simt: C must be <= 256 and a multiple of 4");
   size_t smem = ((size_t)AQ * (C + 4) + (size_t)AK * (C + 4) + (size_t)AK * C + AQ * AK + 2 * AQ) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    STORM_CUDA_TRY(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
+  STORM_SET_SMEM_ONCE((attention_simt_kernel), 100 * 1024);
   storm_launch(attention_simt_kernel, dim3(ceil_div(N, AQ), B), 256, smem, st, q, k, v, o, N, C, 1.0f / sqrtf((float)C));
   STORM_LAUNCH_CHECK();
   return 0;
