@@ -705,7 +705,14 @@ struct Fwd {
     }
     h->pool.put(ss);
     STORM_TRY(alloc(o, x.H, x.W, C));
-    if (use_tc_attn) { LAUNCH(h, launch_attention_tc(q.p, k.p, v.p, o.p, B, N, C, st)); }
+    if (use_tc_attn) {
+      void* scratch = nullptr;                   // packed bf16 hi/lo operand images of q, k, v
+      STORM_TRY(h->pool.get(attention_tc_scratch_bytes(B, N, C), &scratch));
+      const int rc_attn = launch_attention_tc(q.p, k.p, v.p, o.p, B, N, C, scratch, st);
+      h->pool.put(scratch);
+      if (rc_attn != 0) return rc_attn;
+      h->launches += 2;                          // operand pre-pass + attention kernel
+    }
     else { LAUNCH(h, launch_attention_simt(q.p, k.p, v.p, o.p, B, N, C, st)); }
     release(q); release(k); release(v);
     STORM_TRY(alloc(out, x.H, x.W, C));
@@ -1499,7 +1506,11 @@ int storm_debug_attention(int32_t engine, const float* q, const float* k, const 
   int rc;
   if (engine == 0) {
     if (!attention_tc_eligible(N, C)) return fail(STORM_E_INVALID, "storm_debug_attention: shape not eligible for the tcgen05 kernel");
-    rc = launch_attention_tc(q, k, v, o, B, N, C, st);
+    void* scratch = nullptr;
+    if (cudaMalloc(&scratch, attention_tc_scratch_bytes(B, N, C)) != cudaSuccess) return fail(STORM_E_NOMEM, "storm_debug_attention: scratch");
+    rc = launch_attention_tc(q, k, v, o, B, N, C, scratch, st);
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
   } else {
     rc = launch_attention_simt(q, k, v, o, B, N, C, st);
   }

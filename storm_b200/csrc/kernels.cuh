@@ -66,7 +66,8 @@ int launch_head(const float* pyr, const float* t, const float* w, const float* b
 int launch_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int N, int C, cudaStream_t st);
 // tcgen05 version: vT is channel-major [B][C][N]; needs N % 128 == 0, C % 16 == 0, C <= 256
 bool attention_tc_eligible(int N, int C);
-int launch_attention_tc(const float* q, const float* k, const float* vT, float* o, int B, int N, int C, cudaStream_t st);
+size_t attention_tc_scratch_bytes(int B, int N, int C);
+int launch_attention_tc(const float* q, const float* k, const float* vT, float* o, int B, int N, int C, void* scratch, cudaStream_t st);
 
 // ---- sampler elementwise updates (sdes.py:233-237, predictors.py:41-69, correctors.py:37-93) ----------
 struct UpdateCoef { float a, b, c, e; };   // x_mean = a x + b y + c d ; x = x_mean + e z
