@@ -12,7 +12,7 @@ ncu -i gpurun_out/r2_ncu_full_Q.ncu-rep --page raw --csv > gpurun_out/r2_ncu_ful
 STORM_B200_TCQ=0 STORM_B200_TCR=0 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_P.txt 2>&1
 STORM_B200_TCQ=1 STORM_B200_TCR=0 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_Q.txt 2>&1
 STORM_B200_TCR=1 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_R.txt 2>&1
-SEL="test_half_resolution_residual or (test_fused_conv and 0-case) or (test_attention_core and 0-3-128-192) or test_fir_resample or test_pair_kernel_tile_heights"
+SEL="test_half_resolution_residual or (test_fused_conv and 0-case) or (test_attention_core and 3-128-192-0) or test_fir_resample or test_pair_kernel_tile_heights"
 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_conv.py -q -x -k "$SEL" > gpurun_out/r2_racecheck.log 2>&1
 tail -3 gpurun_out/r2_racecheck.log
 STORM_B200_TCR=0 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_conv.py -q -x -k "$SEL" > gpurun_out/r2_racecheck_PQ.log 2>&1

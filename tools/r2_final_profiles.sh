@@ -11,7 +11,7 @@ ncu -i gpurun_out/r2_ncu_full_Q.ncu-rep --page raw --csv > gpurun_out/r2_ncu_ful
 STORM_B200_TCQ=0 STORM_B200_TCR=0 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_P.txt 2>&1
 STORM_B200_TCQ=1 STORM_B200_TCR=0 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_Q.txt 2>&1
 STORM_B200_TCR=1 timeout 300 python tools/conv_timeline.py > gpurun_out/r2_conv_timeline_R.txt 2>&1
-timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_conv.py -q -x -k "test_half_resolution_residual or (test_fused_conv and 0-case) or (test_attention_core and 0-3-128-192)" > gpurun_out/r2_racecheck.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_conv.py -q -x -k "test_half_resolution_residual or (test_fused_conv and 0-case) or (test_attention_core and 3-128-192-0)" > gpurun_out/r2_racecheck.log 2>&1
 tail -4 gpurun_out/r2_racecheck.log
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_conv.py -q -x -k "test_half_resolution_residual or (test_fused_conv and 0-case) or test_attention_core or test_dynamic_range_sweep" > gpurun_out/r2_memcheck.log 2>&1
 tail -4 gpurun_out/r2_memcheck.log
