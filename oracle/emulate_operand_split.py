@@ -15,6 +15,9 @@ f16_f8f8_noscale_l    2               the same with e4m3(w) * e5m2(l): no scalin
 skip_f16_act          2 (skip: 1.5)   f16_f8f8, but the raw 1x1 skip convs drop the residual plane l    1.9e-4
 f16_act               2               (wh16 + wl16) * h16: fp16 activations, exact weights             8.0e-4
 f16_main              1               wh16 * h16 only                                                  1.6e-3
+f16_mxf4              1.5 (if kind::mxf4 runs at twice the fp8 rate)   wh16*h16 + mxfp4(wl)*mxfp4(h) + mxfp4(w)*mxfp4(l): both correction
+                                      products in OCP MXFP4 (e2m1, one power-of-two scale per 32 channels)   1.8e-4   
+f16_nvf4              1.5             the same in NVFP4 (e2m1, one e4m3 scale per 16 channels + a per-tensor power of two)
 (bf16 x 3, conv_tc.cu mode 0, is measured on the GPU: 2.8e-5.)  The north-star tolerance is 1e-3.
 """
 import os
@@ -40,6 +43,35 @@ def q8(x, dt, k):
     return (x * s).clamp(-lim, lim).to(dt).float() / s
 
 
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+
+
+def q4(x, dim, nv):
+    """Block-scaled fp4 (e2m1) along `dim` (the K dimension = input channels): OCP MXFP4 (blocks of 32, power-of-two scale chosen
+    as floor(log2(max)) - 2, values above 6 saturate) or NVFP4 (blocks of 16, scale = e4m3(max / 6))."""
+    blk = 16 if nv else 32
+    xm = x.movedim(dim, -1)
+    shp = xm.shape
+    C = shp[-1]
+    pad = (-C) % blk
+    if pad:
+        xm = F.pad(xm, (0, pad))
+    xb = xm.reshape(*xm.shape[:-1], -1, blk)
+    amax = xb.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30)
+    if nv:
+        # NVFP4's e4m3 block scales only span 2^-9 .. 448: a per-tensor power of two (the format's second-level scale) centres them
+        g = torch.exp2(torch.floor(torch.log2(amax.max())) - 6.0)
+        scale = (amax / (6.0 * g)).clamp(2.0 ** -9, 448.0).to(E4).float().clamp_min(2.0 ** -9) * g
+    else:
+        scale = torch.exp2(torch.floor(torch.log2(amax)) - 2.0)
+    y = (xb / scale).clamp(-6.0, 6.0)
+    mag = y.abs()
+    idx = torch.bucketize(mag, (_E2M1[:-1] + _E2M1[1:]) / 2)          # round to nearest representable magnitude
+    q = _E2M1[idx] * torch.sign(y) * scale
+    q = q.reshape(*xm.shape)[..., :C].reshape(shp)
+    return q.movedim(-1, dim)
+
+
 def make_lin(mode):
     def lin(op, x, w):
         if mode == "exact":
@@ -54,6 +86,10 @@ def make_lin(mode):
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E4, 6), q8(w, E5, -6))
         if mode == "f16_f8f8_noscale_l":      # residual unscaled in e5m2, weights unscaled in e4m3 (one multiply less per element)
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E5, 0), q8(w, E4, 0))
+        if mode in ("f16_mxf4", "f16_nvf4"):
+            nv = mode == "f16_nvf4"
+            kd = 0 if w.dim() == 2 else 1          # NIN weights are [Cin, Cout], conv weights [Cout, Cin, kh, kw]
+            return op(h, wh) + op(q4(h, 1, nv), q4(w - wh, kd, nv)) + op(q4(x - h, 1, nv), q4(w, kd, nv))
         raise SystemExit(f"unknown mode {mode}")
     return lin
 
