@@ -26,6 +26,17 @@ __device__ __forceinline__ void umma_f8(uint32_t d, uint64_t a, uint64_t b, uint
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a),
                "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// block-scaled fp4: kind::mxf4 (e2m1 x e2m1, one ue8m0 scale per 32 elements of K, K = 64 per instruction); scale factors in TMEM.
+// Instruction descriptor of the block-scaled kinds (no accumulator-format field: bits 4-5 are the B scale-factor id):
+// a_format [7,10) = b_format [10,13) = 1 (e2m1), K-major, N >> 3 at [17,23), scale_format [23] = 1 (ue8m0), M >> 4 at [24,29), K64 [31] = 0
+__host__ __device__ inline uint32_t make_idesc_mxf4(int n) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_mxf4(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, uint32_t sfa, uint32_t sfb) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc),
+               "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+}
 __device__ __forceinline__ void commit_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   uint32_t ok = 0;
@@ -115,6 +126,13 @@ __global__ void __launch_bounds__(128, 1) rate(int n, int mode, int iters, long 
         if (mode == 0) {            // bf16 x3 on two 16-channel chunks
           umma_f16(d, wa, db + off, ibf, i > 0); umma_f16(d, wa, db + 680 + off, ibf, 1); umma_f16(d, wa + 512, db + off, ibf, 1);
           umma_f16(d, wa + 1024, db + 1360 + off, ibf, 1); umma_f16(d, wa + 1024, db + 2040 + off, ibf, 1); umma_f16(d, wa + 1536, db + 1360 + off, ibf, 1);
+        } else if (mode == 2) {     // f16 x2 (K=16 each) + ONE mxf4 (K=64: both correction products of the 32 channels concatenated along K)
+          umma_f16(tm, wa, db + off, i16, i > 0); umma_f16(tm, wa + 512, db + 680 + off, i16, 1);
+          umma_mxf4(tm, wa + 1024, db + 1360 + off, make_idesc_mxf4(n), 1, tm + 256, tm + 264);
+        } else if (mode == 3) {     // mxf4 only: cycles per instruction (timing only - operands and scale factors are whatever is there)
+          umma_mxf4(tm, wa + 1024, db + 1360 + off, make_idesc_mxf4(n), i > 0, tm + 256, tm + 264);
+        } else if (mode == 4) {     // fp8 only, for comparison
+          umma_f8(tm, wa + 1024, db + 1360 + off, i8a, i > 0);
         } else {                    // f16 x2 (K=16 each) + fp8 x2 (K=32 each)
           umma_f16(d, wa, db + off, i16, i > 0); umma_f16(d, wa + 512, db + 680 + off, i16, 1);
           umma_f8(d, wa + 1024, db + 1360 + off, i8a, 1); umma_f8(d, wa + 1536, db + 2040 + off, i8b, 1);
@@ -174,14 +192,15 @@ int main() {
   // ---- rate
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  for (int n : {256, 128}) for (int mode : {0, 1}) {
+  for (int n : {256, 128}) for (int mode : {0, 1, 2, 3, 4}) {
     const int iters = 512;
     rate<<<148, 128, 160 * 1024>>>(n, mode, iters, d);
     e = cudaDeviceSynchronize();
     long long h[148]; cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
     printf("N=%d %-28s %8.1f cycles per (32 channels x 1 tap x 2 cout blocks)  [%d MMAs]  %s\n", n,
-           mode == 0 ? "bf16x3 (6 MMAs per block)" : "f16 x2 + fp8 x2 (4 MMAs)", (double)mx / iters, mode == 0 ? 12 : 8, cudaGetErrorString(e));
+           mode == 0 ? "bf16x3 (6 MMAs per block)" : mode == 1 ? "f16 x2 + fp8 x2 (4 MMAs)" : mode == 2 ? "f16 x2 + mxf4 x1 (3 MMAs)"
+           : mode == 3 ? "mxf4 x1 (K=64)" : "fp8 x1 (K=32)", (double)mx / iters, mode == 0 ? 12 : mode == 1 ? 8 : mode == 2 ? 6 : 2, cudaGetErrorString(e));
   }
   return 0;
 }
