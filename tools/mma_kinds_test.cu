@@ -97,6 +97,57 @@ __global__ void __launch_bounds__(128, 1) numeric(const uint8_t* img, float* out
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256));
 }
 
+// ---- numerics of kind::mxf4.block_scale.block32: D[128 x N] = sum over the two 32-element K blocks of sfa[m][blk] * sfb[n][blk] * (A_blk . B_blk)
+// img: [A fp4 v0 4096][B fp4 v0 N*32][A fp4 v1 4096][B fp4 v1 N*32][SFA atom 512][SFB atom 512]   (v0: element 2i in the low nibble, v1: high)
+__global__ void __launch_bounds__(128, 1) numeric_mxf4(const uint8_t* img, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int per = 4096 + N * 32, total = 2 * per + 1024;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) smem[i] = img[i];
+  if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t s0 = smem_u32(smem);
+    const uint32_t sfa_s = s0 + 2 * per, sfb_s = sfa_s + 512;
+    const uint32_t sfa_t = tm + 128, sfb_t = tm + 132;
+    // scale factors: 32 rows x 128 bit per copy (8-row core matrices of 128 contiguous bytes), broadcast to the four lane quadrants
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(sfa_t), "l"(make_desc(sfa_s, 128, 128)) : "memory");
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(sfb_t), "l"(make_desc(sfb_s, 128, 128)) : "memory");
+    umma_mxf4(tm + 0, make_desc(s0, 128, 256), make_desc(s0 + 4096, 128, 256), make_idesc_mxf4(N), 0, sfa_t, sfb_t);
+    umma_mxf4(tm + 64, make_desc(s0 + per, 128, 256), make_desc(s0 + per + 4096, 128, 256), make_idesc_mxf4(N), 0, sfa_t, sfb_t);
+    commit_wait(&bar, 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = 0; t < 2; ++t)
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 64 + c0);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                     "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                     "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                     "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                   : "r"(addr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) out[((size_t)t * 128 + warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256));
+}
+
 // rate: per "tap" of a 32-channel chunk the new split issues 2 f16 (K=16) + 2 fp8 (K=32) MMAs, the current one 6 bf16 MMAs
 __global__ void __launch_bounds__(128, 1) rate(int n, int mode, int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -188,6 +239,55 @@ int main() {
       bad += err > 1e-6;
     }
     printf("%-34s %s  max abs err %.3g  mismatches %d / %d\n", names[t], cudaGetErrorString(e), maxerr, bad, 128 * N);
+  }
+  // ---- numerics of the block-scaled fp4 kind
+  {
+    static const float e2m1[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+    auto A4 = [](int m, int k) { return (m * 5 + k * 3) % 15; };            // 4-bit code: bit 3 = sign, bits 0-2 = magnitude index
+    auto B4 = [](int n, int k) { return (n * 7 + k * 11 + 3) % 16; };
+    auto val = [&](int code) { return (code & 8 ? -1.f : 1.f) * e2m1[code & 7]; };
+    auto sfa = [](int m, int blk) { return (m * 3 + blk) % 5 - 2; };          // exponent of the ue8m0 scale
+    auto sfb = [](int n, int blk) { return (n + 2 * blk) % 4 - 1; };
+    const int per4 = 4096 + N * 32;
+    std::vector<uint8_t> im4(2 * per4 + 1024, 0);
+    for (int v = 0; v < 2; ++v) {
+      auto put4 = [&](size_t base, int r, int k, int code) {
+        const int b = k / 2;
+        uint8_t& by = im4[base + (size_t)(r / 8) * 256 + (b / 16) * 128 + (r % 8) * 16 + b % 16];
+        const bool hi = ((k & 1) != 0) != (v == 1);
+        by = hi ? (uint8_t)((by & 0x0F) | (code << 4)) : (uint8_t)((by & 0xF0) | code);
+      };
+      for (int m = 0; m < 128; ++m) for (int k = 0; k < 64; ++k) put4((size_t)v * per4, m, k, A4(m, k));
+      for (int n = 0; n < N; ++n) for (int k = 0; k < 64; ++k) put4((size_t)v * per4 + 4096, n, k, B4(n, k));
+    }
+    for (int r = 0; r < 128; ++r) for (int j = 0; j < 4; ++j) {
+      im4[2 * per4 + (r % 32) * 16 + (r / 32) * 4 + j] = (uint8_t)(127 + (j < 2 ? sfa(r, j) : 0));
+      im4[2 * per4 + 512 + (r % 32) * 16 + (r / 32) * 4 + j] = (uint8_t)(127 + ((j < 2 && r < N) ? sfb(r, j) : 0));
+    }
+    uint8_t* d4; float* o4; cudaMalloc(&d4, im4.size()); cudaMalloc(&o4, 2 * 128 * N * 4);
+    cudaMemcpy(d4, im4.data(), im4.size(), cudaMemcpyHostToDevice);
+    cudaMemset(o4, 0, 2 * 128 * N * 4);
+    numeric_mxf4<<<1, 128, 2 * per4 + 1024>>>(d4, o4);
+    e = cudaDeviceSynchronize();
+    std::vector<float> o(2 * 128 * N);
+    cudaMemcpy(o.data(), o4, o.size() * 4, cudaMemcpyDeviceToHost);
+    for (int v = 0; v < 2; ++v) {
+      double maxerr = 0; int bad = 0;
+      for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+        double ref = 0;
+        for (int blk = 0; blk < 2; ++blk) {
+          double sacc = 0;
+          for (int k = 32 * blk; k < 32 * blk + 32; ++k) sacc += (double)val(A4(m, k)) * val(B4(n, k));
+          ref += sacc * exp2((double)sfa(m, blk) + sfb(n, blk));
+        }
+        const double err = fabs(o[((size_t)v * 128 + m) * N + n] - ref);
+        if (err > maxerr) maxerr = err;
+        bad += err > 1e-4;
+        if (m < 2 && n < 3) printf("    v%d D[%d][%d] = %g  (reference %g)\n", v, m, n, o[((size_t)v * 128 + m) * N + n], ref);
+      }
+      printf("kind::mxf4.block_scale (%s nibble first)  %s  max abs err %.3g  mismatches %d / %d\n", v == 0 ? "low" : "high", cudaGetErrorString(e),
+             maxerr, bad, 128 * N);
+    }
   }
   // ---- rate
   long long* d; cudaMalloc(&d, 148 * 8);
