@@ -17,7 +17,8 @@ f16_act               2               (wh16 + wl16) * h16: fp16 activations, exa
 f16_main              1               wh16 * h16 only                                                  1.6e-3
 f16_mxf4              1.5 (if kind::mxf4 runs at twice the fp8 rate)   wh16*h16 + mxfp4(wl)*mxfp4(h) + mxfp4(w)*mxfp4(l): both correction
                                       products in OCP MXFP4 (e2m1, one power-of-two scale per 32 channels)   1.8e-4   
-f16_nvf4              1.5             the same in NVFP4 (e2m1, one e4m3 scale per 16 channels + a per-tensor power of two)
+f16_nvf4              1.5             the same in NVFP4 (e2m1, one e4m3 scale per 16 channels + a per-tensor power of two)   1.8e-4
+f16_mxf4_pix          1.5             f16_mxf4 with ONE exponent per pixel for all channels of the activation planes (weights: 32-channel blocks)   2.2e-4
 (bf16 x 3, conv_tc.cu mode 0, is measured on the GPU: 2.8e-5.)  The north-star tolerance is 1e-3.
 """
 import os
@@ -46,13 +47,13 @@ def q8(x, dt, k):
 _E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
 
 
-def q4(x, dim, nv):
+def q4(x, dim, nv, whole=False):
     """Block-scaled fp4 (e2m1) along `dim` (the K dimension = input channels): OCP MXFP4 (blocks of 32, power-of-two scale chosen
     as floor(log2(max)) - 2, values above 6 saturate) or NVFP4 (blocks of 16, scale = e4m3(max / 6))."""
-    blk = 16 if nv else 32
     xm = x.movedim(dim, -1)
     shp = xm.shape
     C = shp[-1]
+    blk = C if whole else (16 if nv else 32)          # whole: ONE scale per row (e.g. per pixel for all channels)
     pad = (-C) % blk
     if pad:
         xm = F.pad(xm, (0, pad))
@@ -86,10 +87,11 @@ def make_lin(mode):
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E4, 6), q8(w, E5, -6))
         if mode == "f16_f8f8_noscale_l":      # residual unscaled in e5m2, weights unscaled in e4m3 (one multiply less per element)
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E5, 0), q8(w, E4, 0))
-        if mode in ("f16_mxf4", "f16_nvf4"):
+        if mode in ("f16_mxf4", "f16_nvf4", "f16_mxf4_pix"):
             nv = mode == "f16_nvf4"
+            pix = mode == "f16_mxf4_pix"          # activations: one exponent per pixel for all channels (weights keep 32-channel blocks)
             kd = 0 if w.dim() == 2 else 1          # NIN weights are [Cin, Cout], conv weights [Cout, Cin, kh, kw]
-            return op(h, wh) + op(q4(h, 1, nv), q4(w - wh, kd, nv)) + op(q4(x - h, 1, nv), q4(w, kd, nv))
+            return op(h, wh) + op(q4(h, 1, nv, pix), q4(w - wh, kd, nv)) + op(q4(x - h, 1, nv, pix), q4(w, kd, nv))
         raise SystemExit(f"unknown mode {mode}")
     return lin
 
