@@ -18,6 +18,8 @@ f16_main              1               wh16 * h16 only                           
 f16_mxf4              1.5 (if kind::mxf4 runs at twice the fp8 rate)   wh16*h16 + mxfp4(wl)*mxfp4(h) + mxfp4(w)*mxfp4(l): both correction
                                       products in OCP MXFP4 (e2m1, one power-of-two scale per 32 channels)   1.8e-4   
 f16_nvf4              1.5             the same in NVFP4 (e2m1, one e4m3 scale per 16 channels + a per-tensor power of two)   1.8e-4
+f16_mxf4_fixed        1.5             activation fp4 planes with ONE power-of-two scale per sample (from its rms), weights in 32-channel blocks   4.5e-4
+f16_mxf4_pix_tied     1.5             f16_mxf4_pix with the residual plane's exponent tied to the main plane's (exponent - 11): one factor per pixel   2.4e-4
 f16_mxf4_pix          1.5             f16_mxf4 with ONE exponent per pixel for all channels of the activation planes (weights: 32-channel blocks)   2.2e-4
 (bf16 x 3, conv_tc.cu mode 0, is measured on the GPU: 2.8e-5.)  The north-star tolerance is 1e-3.
 """
@@ -87,6 +89,30 @@ def make_lin(mode):
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E4, 6), q8(w, E5, -6))
         if mode == "f16_f8f8_noscale_l":      # residual unscaled in e5m2, weights unscaled in e4m3 (one multiply less per element)
             return op(h, wh) + op(q8(x, E5, -12), q8(w - wh, E4, 12)) + op(q8(x - h, E5, 0), q8(w, E4, 0))
+        if mode == "f16_mxf4_fixed":
+            # no activation exponents at all: ONE power of two per sample (from the tensor's rms, which GroupNorm already measures),
+            # values above 6 * scale saturate; residual plane at scale * 2^-11
+            kd = 0 if w.dim() == 2 else 1
+            rms = h.pow(2).mean(dim=(1, 2, 3), keepdim=True).sqrt().clamp_min(1e-30)
+            sc = torch.exp2(torch.round(torch.log2(rms)))
+
+            def q4f(v, s_):
+                y = (v / s_).clamp(-6.0, 6.0)
+                idx = torch.bucketize(y.abs().contiguous(), (_E2M1[:-1] + _E2M1[1:]) / 2)
+                return _E2M1[idx] * torch.sign(y) * s_
+            return op(h, wh) + op(q4f(h, sc), q4(w - wh, kd, False)) + op(q4f(x - h, sc * 2.0 ** -11), q4(w, kd, False))
+        if mode == "f16_mxf4_pix_tied":
+            # the kernel-shaped variant: ONE exponent per pixel from max|h| over all channels; the residual plane uses the same
+            # exponent - 11 (|l| <= 2^-11 |h| element-wise), so a single per-pixel factor multiplies the whole correction accumulator
+            kd = 0 if w.dim() == 2 else 1
+            amax = h.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+            sc = torch.exp2(torch.floor(torch.log2(amax)) - 2.0)
+
+            def q4s(v, s_):
+                y = (v / s_).clamp(-6.0, 6.0)
+                idx = torch.bucketize(y.abs().contiguous(), (_E2M1[:-1] + _E2M1[1:]) / 2)
+                return _E2M1[idx] * torch.sign(y) * s_
+            return op(h, wh) + op(q4s(h, sc), q4(w - wh, kd, False)) + op(q4s(x - h, sc * 2.0 ** -11), q4(w, kd, False))
         if mode in ("f16_mxf4", "f16_nvf4", "f16_mxf4_pix"):
             nv = mode == "f16_nvf4"
             pix = mode == "f16_mxf4_pix"          # activations: one exponent per pixel for all channels (weights keep 32-channel blocks)
