@@ -292,7 +292,7 @@ int main() {
   // ---- rate
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  for (int n : {256, 128}) for (int mode : {0, 1, 2, 3, 4}) {
+  for (int n : {256, 240, 128}) for (int mode : {0, 1, 2, 3, 4}) {
     const int iters = 512;
     rate<<<148, 128, 160 * 1024>>>(n, mode, iters, d);
     e = cudaDeviceSynchronize();
