@@ -33,8 +33,8 @@
 #include "conv_tc.cuh"
 
 // 1: producer thread 0 of CTA 0 also records where ITS cycles go (dbg[6..10], tools/conv_timeline.py); costs registers in the
-// producer warps, so it is compiled out of the shipped library (build with -DSTORM_TC_PRODUCER_TIMING=1 to get the numbers of
-// profiles/r2_conv_timeline_producer.txt)
+// producer warps, so it is compiled out of the shipped library (build with -DSTORM_TC_PRODUCER_TIMING=1; the producer-side numbers
+// quoted in profiles/r2_bench_history.md were taken that way)
 #ifndef STORM_TC_PRODUCER_TIMING
 #define STORM_TC_PRODUCER_TIMING 0
 #endif
